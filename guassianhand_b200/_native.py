@@ -1,0 +1,119 @@
+"""ctypes binding of libghr.so -- mirrors include/ghr.h field by field.
+
+The library is the product; there is no fallback.  If it is missing or does not export the ABI
+this module raises, and every rasterizer call fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libghr.so")
+
+GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
+GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
+GHR_ABI_VERSION = 1
+
+EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",
+           "ghr_mark_visible", "ghr_read_status_async"]
+
+_vp = C.c_void_p
+
+
+class GhrDims(C.Structure):
+    _fields_ = [("P", C.c_int32), ("V", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("M", C.c_int32),
+                ("sh_degree", C.c_int32), ("R_cap", C.c_int64)]
+
+
+class GhrLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "state_bytes", "temp_bytes", "temp_bwd_bytes", "off_status", "off_geom", "off_clamped", "off_ranges",
+        "off_tilemax", "off_records", "off_final_T", "off_ncontrib")]
+
+
+class GhrStatus(C.Structure):
+    _fields_ = [("R", C.c_uint64), ("overflow", C.c_uint32), ("n_visible", C.c_uint32),
+                ("reserved", C.c_uint64 * 2)]
+
+
+class GhrForwardArgs(C.Structure):
+    _fields_ = [
+        ("dims", GhrDims), ("flags", C.c_uint32), ("scale_modifier", C.c_float), ("tanfovx", C.c_float),
+        ("tanfovy", C.c_float),
+        ("viewmatrix", _vp), ("projmatrix", _vp), ("campos", _vp), ("tanfov", _vp), ("bg", _vp),
+        ("bg_stride", C.c_int32),
+        ("means3D", _vp), ("opacities", _vp), ("scales", _vp), ("rotations", _vp), ("cov3D_precomp", _vp),
+        ("shs", _vp), ("colors_precomp", _vp),
+        ("out_color", _vp), ("radii", _vp),
+        ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
+        ("dbg_keys_sorted", _vp), ("dbg_point_list", _vp),
+        ("host_status", _vp), ("seq", C.c_uint64),
+    ]
+
+
+class GhrBackwardArgs(C.Structure):
+    _fields_ = [
+        ("dims", GhrDims), ("flags", C.c_uint32), ("scale_modifier", C.c_float), ("tanfovx", C.c_float),
+        ("tanfovy", C.c_float),
+        ("viewmatrix", _vp), ("projmatrix", _vp), ("campos", _vp), ("tanfov", _vp), ("bg", _vp),
+        ("bg_stride", C.c_int32),
+        ("means3D", _vp), ("opacities", _vp), ("scales", _vp), ("rotations", _vp), ("cov3D_precomp", _vp),
+        ("shs", _vp), ("colors_precomp", _vp),
+        ("dL_dout_color", _vp),
+        ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
+        ("accumulate", C.c_int32),
+        ("dL_dmeans3D", _vp), ("dL_dmeans2D", _vp), ("dL_dcolors", _vp), ("dL_dopacity", _vp),
+        ("dL_dcov3D", _vp), ("dL_dsh", _vp), ("dL_dscales", _vp), ("dL_drotations", _vp), ("dL_dconic", _vp),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load libghr.so (built in-tree by guassianhand_b200.build).  Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA library is required (there is no CPU fallback). "
+            "Build it with `python -m guassianhand_b200.build`.")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise RuntimeError(f"libghr.so does not export {name}")
+    L.ghr_abi_version.restype = C.c_int
+    L.ghr_last_error.restype = C.c_char_p
+    L.ghr_layout.restype = C.c_int
+    L.ghr_layout.argtypes = [C.POINTER(GhrDims), C.POINTER(GhrLayout)]
+    L.ghr_forward.restype = C.c_int
+    L.ghr_forward.argtypes = [C.POINTER(GhrForwardArgs), _vp]
+    L.ghr_backward.restype = C.c_int
+    L.ghr_backward.argtypes = [C.POINTER(GhrBackwardArgs), _vp]
+    L.ghr_mark_visible.restype = C.c_int
+    L.ghr_mark_visible.argtypes = [C.c_int32, _vp, _vp, _vp, _vp, _vp]
+    L.ghr_read_status_async.restype = C.c_int
+    L.ghr_read_status_async.argtypes = [_vp, _vp, _vp]
+    L.ghr_struct_size.restype = C.c_size_t
+    L.ghr_struct_size.argtypes = [C.c_char_p]
+    for cls in (GhrDims, GhrLayout, GhrStatus, GhrForwardArgs, GhrBackwardArgs):
+        want = L.ghr_struct_size(cls.__name__.encode())
+        if want != C.sizeof(cls):
+            raise RuntimeError(f"ctypes mirror of {cls.__name__} is {C.sizeof(cls)} bytes, libghr.so says {want}")
+    if L.ghr_abi_version() != GHR_ABI_VERSION:
+        raise RuntimeError("libghr.so ABI version mismatch; rebuild with `python -m guassianhand_b200.build --force`")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "libghr"):
+    if rc != GHR_OK:
+        msg = lib().ghr_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def layout(P, V, H, W, M, sh_degree, R_cap) -> GhrLayout:
+    d = GhrDims(P, V, H, W, M, sh_degree, R_cap)
+    out = GhrLayout()
+    check(lib().ghr_layout(C.byref(d), C.byref(out)), "ghr_layout")
+    return out

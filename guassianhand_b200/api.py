@@ -1,0 +1,442 @@
+"""Host side of the rasterizer: the `diff_gaussian_rasterization` surface GuassianHand calls,
+plus a multi-view batched entry.
+
+Mirrors (names, argument meaning, error behaviour) the third-party module the reference imports
+at /root/reference/tgs/models/renderer_one_shot.py:3 and uses at :281-296, :338-346, :355-379:
+
+    GaussianRasterizationSettings  -- 12-field NamedTuple, same field order
+    GaussianRasterizer(raster_settings).forward(means3D, means2D, opacities, shs, colors_precomp,
+                                                scales, rotations, cov3D_precomp) -> (color, radii)
+    GaussianRasterizer.markVisible(positions) -> bool[P]
+
+PyTorch is plumbing here: it owns device memory, the stream and autograd bookkeeping.  All math
+runs in libghr.so (hand-written sm_100a CUDA behind the C ABI of include/ghr.h).  There is no CPU
+or eager fallback: without the library, or without CUDA tensors, calls raise.
+"""
+import ctypes as C
+import itertools
+import threading
+import time
+from typing import NamedTuple, Optional
+
+import torch
+from torch import nn
+
+from . import _native as N
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# ------------------------------------------------------------------ workspaces
+
+class _Workspace:
+    """Per (device, stream) scratch: temp buffer, pinned status slots, instance-capacity policy.
+
+    Upstream sizes its binning buffers after a blocking D2H read of num_rendered in the middle of
+    every forward.  Here the buffers are sized from a running high-water mark and
+    the library reports R to pinned host memory as soon as the scan finishes; the host polls that
+    word while the GPU is already sorting and blending.  Overflow (R > capacity) re-runs the
+    forward once with a larger capacity, so results are always exact.
+    """
+
+    def __init__(self, device):
+        self.device = device
+        self.temp = torch.empty(0, dtype=torch.uint8, device=device)
+        self.cap = {}          # (P, V, H, W) -> entries
+        self.pinned = torch.zeros(64, 4, dtype=torch.int64).pin_memory()   # 64 slots of GhrStatus
+        self.slot = 0
+
+    def get_temp(self, nbytes: int) -> torch.Tensor:
+        if self.temp.numel() < nbytes:
+            self.temp = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=self.device)
+        return self.temp
+
+    def capacity(self, key, P, V) -> int:
+        c = self.cap.get(key)
+        if c is None:
+            c = max(8 * P * V, 1 << 16)
+            self.cap[key] = c
+        return c
+
+    def next_slot(self):
+        self.slot = (self.slot + 1) % self.pinned.shape[0]
+        row = self.pinned[self.slot]
+        row.zero_()
+        return row
+
+
+_ws_lock = threading.Lock()
+_workspaces = {}
+_seq = itertools.count(1)
+
+
+def _workspace(device, stream) -> _Workspace:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    with _ws_lock:
+        ws = _workspaces.get(key)
+        if ws is None:
+            ws = _Workspace(torch.device("cuda", key[0]))
+            _workspaces[key] = ws
+        return ws
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and t.numel() and not t.is_cuda:
+            raise RuntimeError("guassianhand_b200: all tensors must be CUDA tensors (there is no CPU path)")
+
+
+class _Cams(NamedTuple):
+    V: int
+    H: int
+    W: int
+    view: torch.Tensor        # [V,16]
+    proj: torch.Tensor        # [V,16]
+    campos: torch.Tensor      # [V,3]
+    tanfov: Optional[torch.Tensor]   # [V,2] device, or None -> scalars
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor          # [3] or [V,3]
+    bg_stride: int
+
+
+def _fill_common(a, cams: _Cams, P, M, sh_degree, R_cap, scale_modifier, flags, means3D, opacities, scales,
+                 rotations, cov3D, shs, colors):
+    a.dims = N.GhrDims(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
+    a.flags = flags
+    a.scale_modifier = scale_modifier
+    a.tanfovx, a.tanfovy = cams.tanfovx, cams.tanfovy
+    a.viewmatrix, a.projmatrix, a.campos = cams.view.data_ptr(), cams.proj.data_ptr(), cams.campos.data_ptr()
+    a.tanfov = _ptr(cams.tanfov)
+    a.bg, a.bg_stride = cams.bg.data_ptr(), cams.bg_stride
+    a.means3D, a.opacities = _ptr(means3D), _ptr(opacities)
+    a.scales, a.rotations, a.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3D)
+    a.shs, a.colors_precomp = _ptr(shs), _ptr(colors)
+
+
+class ForwardResult(NamedTuple):
+    color: torch.Tensor       # [V,3,H,W]
+    radii: torch.Tensor       # [V,P] int32
+    state: torch.Tensor       # uint8 blob (geometry, sorted instances, ranges, final_T, n_contrib)
+    R_cap: int
+    R: Optional[int]          # known when check == "poll"
+    debug: Optional[dict]
+
+
+def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
+                scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
+                R_cap: Optional[int] = None) -> ForwardResult:
+    """Enqueue one libghr forward (V views).  check: "poll" (exact, re-runs on overflow),
+    "none" (caller checks GhrStatus later; needed under CUDA-graph capture)."""
+    L = N.lib()
+    dev = means3D.device
+    stream = torch.cuda.current_stream(dev)
+    ws = _workspace(dev, stream)
+    P = means3D.shape[0]
+    M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
+    key = (P, cams.V, cams.H, cams.W)
+    cap = int(R_cap) if R_cap is not None else ws.capacity(key, P, cams.V)
+    while True:
+        lay = N.layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
+        state = torch.empty(lay.state_bytes, dtype=torch.uint8, device=dev)
+        temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+        color = torch.empty(cams.V, 3, cams.H, cams.W, dtype=torch.float32, device=dev)
+        radii = torch.empty(cams.V, max(P, 1), dtype=torch.int32, device=dev)
+        dbg = None
+        a = N.GhrForwardArgs()
+        _fill_common(a, cams, P, M, sh_degree, cap, scale_modifier, flags, means3D, opacities, scales, rotations,
+                     cov3D, shs, colors)
+        a.out_color, a.radii = color.data_ptr(), radii.data_ptr()
+        a.state, a.state_bytes = state.data_ptr(), lay.state_bytes
+        a.temp, a.temp_bytes = temp.data_ptr(), temp.numel()
+        if want_debug:
+            dbg = dict(keys=torch.zeros(max(cap, 1), dtype=torch.int64, device=dev),
+                       point_list=torch.zeros(max(cap, 1), dtype=torch.int32, device=dev), layout=lay)
+            a.dbg_keys_sorted, a.dbg_point_list = dbg["keys"].data_ptr(), dbg["point_list"].data_ptr()
+        row = None
+        seq = next(_seq)
+        a.seq = seq
+        if check == "poll":
+            row = ws.next_slot()
+            a.host_status = row.data_ptr()
+        N.check(L.ghr_forward(C.byref(a), stream.cuda_stream), "ghr_forward")
+        R = None
+        if check == "poll":
+            t0 = time.perf_counter()
+            while int(row[2]) != seq:           # reserved[0]
+                if time.perf_counter() - t0 > 10.0:
+                    stream.synchronize()
+                    if int(row[2]) != seq:
+                        raise RuntimeError("ghr_forward: status report never arrived")
+            R = int(row[0])
+            overflow = int(row[1]) & 0xFFFFFFFF
+            if R_cap is None:
+                ws.cap[key] = max(ws.cap[key], int(R * 1.5) + (1 << 14))
+            if overflow:
+                if R_cap is not None:
+                    raise RuntimeError(f"ghr_forward: {R} instances exceed the fixed capacity R_cap={cap}")
+                cap = ws.cap[key]
+                continue
+        return ForwardResult(color, radii[:, :P], state, cap, R, dbg)
+
+
+def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, scales, rotations, cov3D, shs,
+                 colors, sh_degree, scale_modifier, flags=0, want_means2D=True, accumulate_into=None,
+                 want_conic=False, accumulate=True):
+    """Enqueue one libghr backward.  Returns dict of gradient tensors (summed over views, except
+    dL_dmeans2D which is per view)."""
+    L = N.lib()
+    dev = means3D.device
+    stream = torch.cuda.current_stream(dev)
+    ws = _workspace(dev, stream)
+    P = means3D.shape[0]
+    M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
+    lay = N.layout(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
+    temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+    a = N.GhrBackwardArgs()
+    _fill_common(a, cams, P, M, sh_degree, R_cap, scale_modifier, flags, means3D, opacities, scales, rotations, cov3D,
+                 shs, colors)
+    dL_dout = _f32c(dL_dout)
+    a.dL_dout_color = dL_dout.data_ptr()
+    a.state, a.state_bytes = fwd_state.data_ptr(), fwd_state.numel()
+    a.temp, a.temp_bytes = temp.data_ptr(), temp.numel()
+    g = None if accumulate_into is None else dict(accumulate_into)
+    a.accumulate = 1 if (g is not None and accumulate) else 0
+    if g is None:
+        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+        g = dict(dL_dmeans3D=new(P, 3), dL_dopacity=new(P, 1), dL_dcov3D=new(P, 6))
+        if M > 0:
+            g["dL_dsh"] = new(P, M, 3)
+        else:
+            g["dL_dcolors"] = new(P, 3)
+        if scales is not None and scales.numel():
+            g["dL_dscales"] = new(P, 3)
+            g["dL_drotations"] = new(P, 4)
+    if want_means2D:
+        g["dL_dmeans2D"] = torch.empty(cams.V, P, 3, dtype=torch.float32, device=dev)
+    if want_conic:
+        g["dL_dconic"] = torch.empty(cams.V, P, 4, dtype=torch.float32, device=dev)
+    for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dcov3D", "dL_dsh", "dL_dscales",
+              "dL_drotations", "dL_dconic"):
+        setattr(a, k, _ptr(g.get(k)))
+    N.check(L.ghr_backward(C.byref(a), stream.cuda_stream), "ghr_backward")
+    return g
+
+
+def _cams_from_settings(rs: GaussianRasterizationSettings) -> _Cams:
+    _require_cuda(rs.viewmatrix, rs.projmatrix, rs.campos, rs.bg)
+    return _Cams(V=1, H=int(rs.image_height), W=int(rs.image_width),
+                 view=_f32c(rs.viewmatrix).view(1, 16), proj=_f32c(rs.projmatrix).view(1, 16),
+                 campos=_f32c(rs.campos).view(1, 3), tanfov=None, tanfovx=float(rs.tanfovx),
+                 tanfovy=float(rs.tanfovy), bg=_f32c(rs.bg).view(3), bg_stride=0)
+
+
+def _flags(rs) -> int:
+    return (N.GHR_FLAG_PREFILTERED if rs.prefiltered else 0) | (N.GHR_FLAG_DEBUG if rs.debug else 0)
+
+
+def _opt(t):
+    return None if t is None or t.numel() == 0 else _f32c(t)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """Same argument order and gradient order as upstream's autograd node."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        _require_cuda(means3D, opacities)
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        rs = raster_settings
+        cams = _cams_from_settings(rs)
+        means3D_c, opac_c = _f32c(means3D), _f32c(opacities)
+        sh_c, col_c, sc_c, rot_c, cov_c = _opt(sh), _opt(colors_precomp), _opt(scales), _opt(rotations), _opt(cov3Ds_precomp)
+        args = (cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(rs.sh_degree), float(rs.scale_modifier))
+        if rs.debug:
+            cpu_args = [None if t is None or not torch.is_tensor(t) else t.detach().cpu().clone()
+                        for t in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)]
+            try:
+                res = forward_raw(*args, flags=_flags(rs))
+            except Exception:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise
+        else:
+            res = forward_raw(*args, flags=_flags(rs))
+        ctx.raster_settings = rs
+        ctx.cams = cams
+        ctx.R_cap = res.R_cap
+        ctx.num_rendered = res.R
+        ctx.save_for_backward(means3D_c, opac_c, sc_c if sc_c is not None else torch.empty(0),
+                              rot_c if rot_c is not None else torch.empty(0),
+                              cov_c if cov_c is not None else torch.empty(0),
+                              sh_c if sh_c is not None else torch.empty(0),
+                              col_c if col_c is not None else torch.empty(0), res.state)
+        radii = res.radii[0]
+        ctx.mark_non_differentiable(radii)
+        return res.color[0], radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        rs = ctx.raster_settings
+        means3D, opac, sc, rot, cov, sh, col, state = ctx.saved_tensors
+        none_if_empty = lambda t: None if t.numel() == 0 else t
+        sc, rot, cov, sh, col = map(none_if_empty, (sc, rot, cov, sh, col))
+        call = lambda: backward_raw(ctx.cams, state, ctx.R_cap, grad_out_color.unsqueeze(0), means3D, opac, sc, rot,
+                                    cov, sh, col, int(rs.sh_degree), float(rs.scale_modifier), flags=_flags(rs))
+        if rs.debug:
+            try:
+                g = call()
+            except Exception:
+                torch.save([t.detach().cpu() for t in ctx.saved_tensors[:-1]] + [grad_out_color.detach().cpu()],
+                           "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise
+        else:
+            g = call()
+        P = means3D.shape[0]
+        need = ctx.needs_input_grad
+        return (
+            g["dL_dmeans3D"] if need[0] else None,
+            g["dL_dmeans2D"][0] if need[1] else None,
+            g.get("dL_dsh") if need[2] else None,
+            g.get("dL_dcolors") if need[3] else None,
+            g["dL_dopacity"].view(P, -1) if need[4] else None,
+            g.get("dL_dscales") if need[5] else None,
+            g.get("dL_drotations") if need[6] else None,
+            g["dL_dcov3D"] if need[7] else None,
+            None,
+        )
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            _require_cuda(positions, rs.viewmatrix)
+            pos = _f32c(positions)
+            P = pos.shape[0]
+            out = torch.zeros(P, dtype=torch.bool, device=pos.device)
+            stream = torch.cuda.current_stream(pos.device)
+            N.check(N.lib().ghr_mark_visible(P, _ptr(pos), _f32c(rs.viewmatrix).data_ptr(),
+                                             _f32c(rs.projmatrix).data_ptr(), _ptr(out), stream.cuda_stream),
+                    "ghr_mark_visible")
+        return out
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        e = lambda t: torch.Tensor([]) if t is None else t
+        return rasterize_gaussians(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
+                                   e(cov3D_precomp), rs)
+
+
+# ------------------------------------------------------------------ multi-view batched entry
+
+class ViewBatch(NamedTuple):
+    """V cameras with a shared image size: the per-view part of GaussianRasterizationSettings
+    stacked along dim 0 (renderer_one_shot.py:494-503 loops over exactly these per view)."""
+    image_height: int
+    image_width: int
+    viewmatrix: torch.Tensor     # [V,4,4]
+    projmatrix: torch.Tensor     # [V,4,4]
+    campos: torch.Tensor         # [V,3]
+    tanfov: torch.Tensor         # [V,2]  (tanfovx, tanfovy)
+    bg: torch.Tensor             # [3] or [V,3]
+    sh_degree: int = 0
+    scale_modifier: float = 1.0
+
+    def cams(self) -> _Cams:
+        V = self.viewmatrix.shape[0]
+        bg = _f32c(self.bg)
+        return _Cams(V=V, H=int(self.image_height), W=int(self.image_width), view=_f32c(self.viewmatrix).view(V, 16),
+                     proj=_f32c(self.projmatrix).view(V, 16), campos=_f32c(self.campos).view(V, 3),
+                     tanfov=_f32c(self.tanfov).view(V, 2), tanfovx=0.0, tanfovy=0.0, bg=bg,
+                     bg_stride=3 if bg.dim() == 2 else 0)
+
+
+class _RasterizeViews(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, views: ViewBatch):
+        _require_cuda(means3D, opacities, views.viewmatrix)
+        cams = views.cams()
+        means3D_c, opac_c = _f32c(means3D), _f32c(opacities)
+        sh_c, col_c, sc_c, rot_c, cov_c = _opt(sh), _opt(colors_precomp), _opt(scales), _opt(rotations), _opt(cov3Ds_precomp)
+        res = forward_raw(cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(views.sh_degree),
+                          float(views.scale_modifier))
+        ctx.cams, ctx.views, ctx.R_cap = cams, views, res.R_cap
+        z = torch.empty(0)
+        ctx.save_for_backward(means3D_c, opac_c, sc_c if sc_c is not None else z, rot_c if rot_c is not None else z,
+                              cov_c if cov_c is not None else z, sh_c if sh_c is not None else z,
+                              col_c if col_c is not None else z, res.state)
+        ctx.mark_non_differentiable(res.radii)
+        return res.color, res.radii
+
+    @staticmethod
+    def backward(ctx, grad_color, _):
+        means3D, opac, sc, rot, cov, sh, col, state = ctx.saved_tensors
+        nz = lambda t: None if t.numel() == 0 else t
+        sc, rot, cov, sh, col = map(nz, (sc, rot, cov, sh, col))
+        v = ctx.views
+        g = backward_raw(ctx.cams, state, ctx.R_cap, grad_color, means3D, opac, sc, rot, cov, sh, col,
+                         int(v.sh_degree), float(v.scale_modifier), want_means2D=False)
+        need = ctx.needs_input_grad
+        P = means3D.shape[0]
+        return (g["dL_dmeans3D"] if need[0] else None, g.get("dL_dsh") if need[1] else None,
+                g.get("dL_dcolors") if need[2] else None, g["dL_dopacity"].view(P, -1) if need[3] else None,
+                g.get("dL_dscales") if need[4] else None, g.get("dL_drotations") if need[5] else None,
+                g["dL_dcov3D"] if need[6] else None, None)
+
+
+def rasterize_views(means3D, opacities, views: ViewBatch, shs=None, colors_precomp=None, scales=None,
+                    rotations=None, cov3D_precomp=None):
+    """Render V views of one Gaussian set in a single launch chain.
+    Returns (color [V,3,H,W], radii [V,P]); differentiable w.r.t. the Gaussian attributes with the
+    gradient summed over views (what the per-view Python loop + autograd of the reference yields)."""
+    if (shs is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+            ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+    e = lambda t: torch.Tensor([]) if t is None else t
+    return _RasterizeViews.apply(means3D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
+                                 e(cov3D_precomp), views)

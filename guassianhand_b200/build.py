@@ -1,0 +1,67 @@
+"""In-tree build of libghr.so (hand-written CUDA for sm_100a, C ABI in include/ghr.h).
+
+    python -m guassianhand_b200.build [--force]
+
+Plain nvcc, no torch headers: the library has no Python/torch dependency, PyTorch only owns the
+device memory and the stream the host code passes in.
+"""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libghr.so")
+OBJ = os.path.join(HERE, "csrc", "_obj")
+SOURCES = ["api.cu", "preprocess.cu", "sort.cu", "binning.cu", "blend.cu", "preprocess_bwd.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
+            return c
+    return "nvcc"
+
+
+def _stale():
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps.append(os.path.join(HERE, "..", "include", "ghr.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not _stale():
+        return OUT
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = _nvcc()
+
+    def one(src):
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        res = list(ex.map(one, SOURCES))
+    log = "\n".join(r[1] for r in res)
+    with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+        f.write(log)
+    if verbose:
+        print(log)
+    cmd = [nvcc, "-shared", "-o", OUT, *[r[0] for r in res], "-lcudart"]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

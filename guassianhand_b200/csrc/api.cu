@@ -1,0 +1,256 @@
+// C ABI of libghr.so (include/ghr.h): argument checks, buffer layout, kernel sequencing.
+// No allocation, no synchronisation (unless GHR_FLAG_DEBUG), everything on the caller's stream.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ghr_internal.cuh"
+
+namespace ghr {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int compute_layout(const GhrDims &d, Layout *L) {
+  if (d.P < 0 || d.V < 1 || d.H < 1 || d.W < 1 || d.M < 0 || d.R_cap < 0 || d.sh_degree < 0 || d.sh_degree > 3) {
+    set_error("ghr_layout: bad dims P=%d V=%d H=%d W=%d M=%d deg=%d R_cap=%lld", d.P, d.V, d.H, d.W, d.M,
+              d.sh_degree, (long long)d.R_cap);
+    return GHR_EINVAL;
+  }
+  memset(L, 0, sizeof(*L));
+  L->gx = (d.W + kTile - 1) / kTile;
+  L->gy = (d.H + kTile - 1) / kTile;
+  L->T = L->gx * L->gy;
+  const uint64_t VP = (uint64_t)d.V * d.P, VT = (uint64_t)d.V * L->T, VN = (uint64_t)d.V * d.H * d.W;
+  if (VP >= (1ull << 30) || VT >= (1ull << 31) || (uint64_t)d.R_cap >= (1ull << 30)) {
+    set_error("ghr_layout: V*P, V*T and R_cap must stay below 2^30 (got %llu, %llu, %lld)",
+              (unsigned long long)VP, (unsigned long long)VT, (long long)d.R_cap);
+    return GHR_EINVAL;
+  }
+  int bits = 1;
+  while ((1ull << bits) < VT) bits++;
+  L->tile_bits = bits;
+  L->npt = (bits + 7) / 8;
+  L->items_d = (VP > (1u << 21)) ? 16 : 4;
+  L->items_t = ((uint64_t)d.R_cap > (1u << 22)) ? 16 : 4;
+  L->nblk_d = (int)((d.P + (uint64_t)kSortThreads * L->items_d - 1) / ((uint64_t)kSortThreads * L->items_d));
+  L->nblk_t = (int)(((uint64_t)d.R_cap + (uint64_t)kSortThreads * L->items_t - 1) /
+                    ((uint64_t)kSortThreads * L->items_t));
+  L->nblk_scan = (int)((VP + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
+
+  // ---- state ----
+  size_t o = 0;
+  L->pub.off_status = o;   o = align_up(o + sizeof(GhrStatus));
+  L->pub.off_geom = o;     o = align_up(o + VP * 48);
+  L->pub.off_clamped = o;  o = align_up(o + (d.M > 0 ? VP : 0));
+  L->pub.off_ranges = o;   o = align_up(o + VT * 8);
+  L->pub.off_tilemax = o;  o = align_up(o + VT * 4);
+  L->pub.off_records = o;  o = align_up(o + (size_t)d.R_cap * kRecBytes);
+  L->pub.off_final_T = o;  o = align_up(o + VN * 4);
+  L->pub.off_ncontrib = o; o = align_up(o + VN * 4);
+  L->pub.state_bytes = o;
+
+  // ---- temp (forward): zeroed prefix first ----
+  size_t t = 0;
+  L->t_dhist = t;        t = align_up(t + (size_t)4 * d.V * 256 * 4);
+  L->t_thist = t;        t = align_up(t + (size_t)4 * 256 * 4);
+  L->t_tickets = t;      t = align_up(t + ((size_t)4 * d.V + 4 + 1) * 4);
+  L->t_scan_status = t;  t = align_up(t + (size_t)(L->nblk_scan + 1) * 8);
+  L->t_dstatus = t;      t = align_up(t + (size_t)4 * d.V * L->nblk_d * 256 * 4);
+  L->t_tstatus = t;      t = align_up(t + (size_t)L->npt * L->nblk_t * 256 * 4);
+  L->t_zero_bytes = t;
+  for (int b = 0; b < 2; b++) { L->t_dkeys[b] = t; t = align_up(t + VP * 4); }
+  for (int b = 0; b < 2; b++) { L->t_dvals[b] = t; t = align_up(t + VP * 4); }
+  for (int b = 0; b < 2; b++) { L->t_tkeys[b] = t; t = align_up(t + (size_t)d.R_cap * 4); }
+  for (int b = 0; b < 2; b++) { L->t_tvals[b] = t; t = align_up(t + (size_t)d.R_cap * 4); }
+  L->pub.temp_bytes = t;
+  L->pub.temp_bwd_bytes = align_up(VP * kAccStride * 4);
+  return GHR_OK;
+}
+
+static int check_cuda(cudaError_t e, const char *what, bool debug, cudaStream_t s) {
+  if (e == cudaSuccess && debug) {
+    e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return GHR_ECUDA;
+  }
+  return GHR_OK;
+}
+
+#define GHR_TRY(call, what)                                  \
+  do {                                                       \
+    int _rc = check_cuda((call), what, debug, s);            \
+    if (_rc != GHR_OK) return _rc;                           \
+  } while (0)
+
+}  // namespace ghr
+
+using namespace ghr;
+
+extern "C" {
+
+int ghr_abi_version(void) { return GHR_ABI_VERSION; }
+const char *ghr_last_error(void) { return g_err; }
+
+size_t ghr_struct_size(const char *name) {
+  if (!name) return 0;
+  if (!strcmp(name, "GhrDims")) return sizeof(GhrDims);
+  if (!strcmp(name, "GhrLayout")) return sizeof(GhrLayout);
+  if (!strcmp(name, "GhrStatus")) return sizeof(GhrStatus);
+  if (!strcmp(name, "GhrForwardArgs")) return sizeof(GhrForwardArgs);
+  if (!strcmp(name, "GhrBackwardArgs")) return sizeof(GhrBackwardArgs);
+  return 0;
+}
+
+int ghr_layout(const GhrDims *dims, GhrLayout *out) {
+  if (!dims || !out) { set_error("ghr_layout: NULL argument"); return GHR_EINVAL; }
+  Layout L;
+  int rc = compute_layout(*dims, &L);
+  if (rc != GHR_OK) return rc;
+  *out = L.pub;
+  return GHR_OK;
+}
+
+static int check_inputs(const char *fn, const GhrDims &d, const float *means3D, const float *opac, const float *scales,
+                        const float *rots, const float *cov, const float *shs, const float *colors,
+                        const float *view, const float *proj, const float *campos, const float *bg) {
+  if (d.P > 0 && (!means3D || !opac)) { set_error("%s: means3D/opacities are required", fn); return GHR_EINVAL; }
+  if (!view || !proj || !campos || !bg) { set_error("%s: viewmatrix/projmatrix/campos/bg are required", fn); return GHR_EINVAL; }
+  if (d.P > 0) {
+    if ((shs != nullptr) == (colors != nullptr)) { set_error("%s: provide exactly one of shs / colors_precomp", fn); return GHR_EINVAL; }
+    bool sr = scales != nullptr && rots != nullptr;
+    if (sr == (cov != nullptr) || ((scales != nullptr) != (rots != nullptr))) {
+      set_error("%s: provide exactly one of (scales, rotations) / cov3D_precomp", fn);
+      return GHR_EINVAL;
+    }
+    if (shs && d.M < (d.sh_degree + 1) * (d.sh_degree + 1)) {
+      set_error("%s: M=%d SH coefficients cannot hold degree %d", fn, d.M, d.sh_degree);
+      return GHR_EINVAL;
+    }
+  }
+  return GHR_OK;
+}
+
+int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
+  if (!a) { set_error("ghr_forward: NULL args"); return GHR_EINVAL; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const GhrDims &d = a->dims;
+  Layout L;
+  int rc = compute_layout(d, &L);
+  if (rc != GHR_OK) return rc;
+  rc = check_inputs("ghr_forward", d, a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs,
+                    a->colors_precomp, a->viewmatrix, a->projmatrix, a->campos, a->bg);
+  if (rc != GHR_OK) return rc;
+  if (!a->out_color || (d.P > 0 && !a->radii) || !a->state || !a->temp) {
+    set_error("ghr_forward: out_color/radii/state/temp are required");
+    return GHR_EINVAL;
+  }
+  if (a->state_bytes < L.pub.state_bytes || a->temp_bytes < L.pub.temp_bytes) {
+    set_error("ghr_forward: workspace too small (state %zu < %zu or temp %zu < %zu)", a->state_bytes,
+              L.pub.state_bytes, a->temp_bytes, L.pub.temp_bytes);
+    return GHR_ENOSPC;
+  }
+  const bool debug = a->flags & GHR_FLAG_DEBUG;
+  char *state = (char *)a->state, *temp = (char *)a->temp;
+  Cameras cam{a->viewmatrix, a->projmatrix, a->campos, a->tanfov, a->bg, a->tanfovx, a->tanfovy, a->bg_stride};
+  Gaussians g{a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs, a->colors_precomp};
+
+  GHR_TRY(cudaMemsetAsync(temp, 0, L.t_zero_bytes, s), "ghr_forward: memset(temp)");
+  {
+    // status starts as {R=0, overflow=0, n_visible=0, seq}: 32 bytes passed by value
+    GhrStatus st0;
+    memset(&st0, 0, sizeof(st0));
+    st0.reserved[0] = a->seq;
+    GHR_TRY(launch_init_status(state + L.pub.off_status, st0, s), "ghr_forward: init status");
+  }
+  GHR_TRY(launch_preprocess(d, L, cam, g, a->scale_modifier, a->flags, state, temp, a->radii, s),
+          "ghr_forward: preprocess");
+  if (d.P > 0) {
+    GHR_TRY(launch_depth_sort(d, L, temp, s), "ghr_forward: depth sort");
+    GHR_TRY(launch_scan_duplicate(d, L, state, temp, a->seq, s), "ghr_forward: scan+duplicate");
+    if (a->host_status)
+      GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost,
+                              s),
+              "ghr_forward: status copy");
+    if (d.R_cap > 0) {
+      GHR_TRY(launch_tile_sort(d, L, state, temp, s), "ghr_forward: tile sort");
+      GHR_TRY(launch_gather_ranges(d, L, state, temp, a->dbg_keys_sorted, a->dbg_point_list, s),
+              "ghr_forward: gather+ranges");
+    }
+  }
+  if (a->host_status && d.P == 0)
+    GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
+            "ghr_forward: status copy");
+  GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, s), "ghr_forward: blend");
+  return GHR_OK;
+}
+
+int ghr_backward(const GhrBackwardArgs *a, void *cuda_stream) {
+  if (!a) { set_error("ghr_backward: NULL args"); return GHR_EINVAL; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const GhrDims &d = a->dims;
+  Layout L;
+  int rc = compute_layout(d, &L);
+  if (rc != GHR_OK) return rc;
+  rc = check_inputs("ghr_backward", d, a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs,
+                    a->colors_precomp, a->viewmatrix, a->projmatrix, a->campos, a->bg);
+  if (rc != GHR_OK) return rc;
+  if (!a->dL_dout_color || !a->state || !a->temp) {
+    set_error("ghr_backward: dL_dout_color/state/temp are required");
+    return GHR_EINVAL;
+  }
+  if (a->state_bytes < L.pub.state_bytes || a->temp_bytes < L.pub.temp_bwd_bytes) {
+    set_error("ghr_backward: workspace too small (state %zu < %zu or temp %zu < %zu)", a->state_bytes,
+              L.pub.state_bytes, a->temp_bytes, L.pub.temp_bwd_bytes);
+    return GHR_ENOSPC;
+  }
+  if (d.P == 0) return GHR_OK;
+  const bool debug = a->flags & GHR_FLAG_DEBUG;
+  const char *state = (const char *)a->state;
+  float *acc = (float *)a->temp;
+  Cameras cam{a->viewmatrix, a->projmatrix, a->campos, a->tanfov, a->bg, a->tanfovx, a->tanfovy, a->bg_stride};
+  Gaussians g{a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs, a->colors_precomp};
+  GradOut go{a->accumulate, a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity, a->dL_dcov3D,
+             a->dL_dsh, a->dL_dscales, a->dL_drotations, a->dL_dconic};
+
+  GHR_TRY(cudaMemsetAsync(acc, 0, (size_t)d.V * d.P * kAccStride * sizeof(float), s), "ghr_backward: memset(acc)");
+  GHR_TRY(launch_blend_backward(d, L, cam, state, a->dL_dout_color, acc, s), "ghr_backward: blend");
+  GHR_TRY(launch_preprocess_backward(d, L, cam, g, a->scale_modifier, state, acc, go, s),
+          "ghr_backward: preprocess");
+  return GHR_OK;
+}
+
+int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                     uint8_t *present, void *cuda_stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+    set_error("ghr_mark_visible: bad arguments");
+    return GHR_EINVAL;
+  }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool debug = false;
+  GHR_TRY(launch_mark_visible(P, means3D, viewmatrix, present, s), "ghr_mark_visible");
+  return GHR_OK;
+}
+
+int ghr_read_status_async(const void *state, GhrStatus *host_status, void *cuda_stream) {
+  if (!state || !host_status) { set_error("ghr_read_status_async: NULL argument"); return GHR_EINVAL; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool debug = false;
+  GHR_TRY(cudaMemcpyAsync(host_status, state, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
+          "ghr_read_status_async");
+  return GHR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Internal declarations shared by the translation units of libghr.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ghr.h"
+
+namespace ghr {
+
+constexpr int kTile = 16;            // 16x16 pixel tiles
+constexpr int kRecBytes = 48;        // sorted instance record: 3 x float4
+constexpr int kSortThreads = 256;
+constexpr int kScanItems = 4;        // Gaussians per thread in scan_duplicate
+constexpr int kScanThreads = 256;
+constexpr int kAccStride = 12;       // floats per (view,Gaussian) backward accumulator
+
+// ---- canonical fp32 order: explicit rn intrinsics are never re-contracted ----
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float fsqrt(float a) { return __fsqrt_rn(a); }
+// a0*b0 + a1*b1  ->  fma(a0,b0, a1*b1)
+__device__ __forceinline__ float dot2(float a0, float b0, float a1, float b1) {
+  return ffma(a0, b0, fmul(a1, b1));
+}
+// a0*b0 + a1*b1 + a2*b2  ->  fma(a2,b2, fma(a0,b0, a1*b1))
+__device__ __forceinline__ float dot3(float a0, float b0, float a1, float b1, float a2, float b2) {
+  return ffma(a2, b2, ffma(a0, b0, fmul(a1, b1)));
+}
+__device__ __forceinline__ float dot3a(float a0, float b0, float a1, float b1, float a2, float b2, float c) {
+  return fadd(dot3(a0, b0, a1, b1, a2, b2), c);
+}
+
+struct Cameras {
+  const float *view, *proj, *campos, *tanfov, *bg;
+  float tanfovx, tanfovy;
+  int bg_stride;
+};
+
+struct Gaussians {
+  const float *means3D, *opacities, *scales, *rotations, *cov3D_precomp, *shs, *colors_precomp;
+};
+
+// Host-side layout of the two caller-owned buffers.
+struct Layout {
+  GhrLayout pub;
+  int gx, gy, T;               // tiles per view
+  int tile_bits, npt;          // bits / 8-bit passes of the (view,tile) key
+  int items_d, items_t;        // radix items per thread (depth / tile sorts)
+  int nblk_d, nblk_t, nblk_scan;
+  // temp (forward)
+  size_t t_zero_bytes;         // prefix of temp that must be zeroed before a forward
+  size_t t_dhist, t_thist, t_tickets, t_scan_status, t_dstatus, t_tstatus;
+  size_t t_dkeys[2], t_dvals[2], t_tkeys[2], t_tvals[2];
+};
+
+int compute_layout(const GhrDims &d, Layout *L);
+void set_error(const char *fmt, ...);
+
+// ---- kernel launchers (each returns cudaGetLastError()) ----
+cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &cam, const Gaussians &g,
+                              float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,
+                              cudaStream_t s);
+cudaError_t launch_depth_sort(const GhrDims &d, const Layout &L, char *temp, cudaStream_t s);
+cudaError_t launch_scan_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t seq,
+                                  cudaStream_t s);
+cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s);
+cudaError_t launch_tile_sort(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
+cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state, char *temp,
+                                 uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s);
+cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
+                                 float *out_color, cudaStream_t s);
+cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
+                                  const float *dL_dout, float *acc, cudaStream_t s);
+struct GradOut {
+  int accumulate;
+  float *dmeans3D, *dmeans2D, *dcolors, *dopacity, *dcov3D, *dsh, *dscales, *drots, *dconic;
+};
+cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const Cameras &cam,
+                                       const Gaussians &g, float scale_modifier, const char *state,
+                                       const float *acc, const GradOut &go, cudaStream_t s);
+cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present,
+                                cudaStream_t s);
+
+// which final sorted buffers hold the results (ping-pong parity)
+inline int depth_sorted_buf() { return 0; }                 // 4 passes: ends in buffer 0
+inline int tile_sorted_buf(const Layout &L) { return L.npt & 1; }  // input in buffer 0
+
+}  // namespace ghr

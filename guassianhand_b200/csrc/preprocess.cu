@@ -1,0 +1,248 @@
+// Per-(view, Gaussian) preprocess: frustum cull, 3D covariance, EWA projection to the 2D conic,
+// radius / tile rectangle, SH colour, depth key + digit histograms for the depth sort.
+// Replaces upstream preprocessCUDA<3> -- one thread per
+// (view, Gaussian), view-independent inputs are read once per thread; output is one 48-byte
+// record (3 x STG.128) instead of seven scattered arrays.
+#include "ghr_internal.cuh"
+
+namespace ghr {
+
+namespace {
+
+__constant__ float SH_C2c[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float SH_C3c[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                -0.5900435899266435f};
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+
+// A.2 step 3
+__device__ __forceinline__ void cov3d_from_scale_rot(const float *scale, float mod, const float4 q, float *c) {
+  float s0 = fmul(mod, scale[0]), s1 = fmul(mod, scale[1]), s2 = fmul(mod, scale[2]);
+  float r = q.x, x = q.y, y = q.z, z = q.w;
+  float R00 = ffma(-2.f, ffma(y, y, fmul(z, z)), 1.f);
+  float R01 = fmul(2.f, ffma(x, y, -fmul(r, z)));
+  float R02 = fmul(2.f, ffma(x, z, fmul(r, y)));
+  float R10 = fmul(2.f, ffma(x, y, fmul(r, z)));
+  float R11 = ffma(-2.f, ffma(x, x, fmul(z, z)), 1.f);
+  float R12 = fmul(2.f, ffma(y, z, -fmul(r, x)));
+  float R20 = fmul(2.f, ffma(x, z, -fmul(r, y)));
+  float R21 = fmul(2.f, ffma(y, z, fmul(r, x)));
+  float R22 = ffma(-2.f, ffma(x, x, fmul(y, y)), 1.f);
+  float A00 = fmul(R00, s0), A01 = fmul(R01, s1), A02 = fmul(R02, s2);
+  float A10 = fmul(R10, s0), A11 = fmul(R11, s1), A12 = fmul(R12, s2);
+  float A20 = fmul(R20, s0), A21 = fmul(R21, s1), A22 = fmul(R22, s2);
+  c[0] = dot3(A00, A00, A01, A01, A02, A02);
+  c[1] = dot3(A00, A10, A01, A11, A02, A12);
+  c[2] = dot3(A00, A20, A01, A21, A02, A22);
+  c[3] = dot3(A10, A10, A11, A11, A12, A12);
+  c[4] = dot3(A10, A20, A11, A21, A12, A22);
+  c[5] = dot3(A20, A20, A21, A21, A22, A22);
+}
+
+// A.3
+__device__ __forceinline__ void sh_to_rgb(int D, const float *sh, float px, float py, float pz,
+                                          const float *campos, float *rgb, uint32_t *clamp_bits) {
+  float dx = fsub(px, campos[0]), dy = fsub(py, campos[1]), dz = fsub(pz, campos[2]);
+  float len = fsqrt(dot3(dx, dx, dy, dy, dz, dz));
+  float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+  uint32_t bits = 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    float r = fmul(SH_C0, sh[ch]);
+    if (D > 0) {
+      r = ffma(-fmul(SH_C1, y), sh[1 * 3 + ch], r);
+      r = ffma(fmul(SH_C1, z), sh[2 * 3 + ch], r);
+      r = ffma(-fmul(SH_C1, x), sh[3 * 3 + ch], r);
+      if (D > 1) {
+        float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+        float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+        r = ffma(fmul(SH_C2c[0], xy), sh[4 * 3 + ch], r);
+        r = ffma(fmul(SH_C2c[1], yz), sh[5 * 3 + ch], r);
+        r = ffma(fmul(SH_C2c[2], fsub(ffma(2.0f, zz, -xx), yy)), sh[6 * 3 + ch], r);
+        r = ffma(fmul(SH_C2c[3], xz), sh[7 * 3 + ch], r);
+        r = ffma(fmul(SH_C2c[4], fsub(xx, yy)), sh[8 * 3 + ch], r);
+        if (D > 2) {
+          r = ffma(fmul(fmul(SH_C3c[0], y), ffma(3.0f, xx, -yy)), sh[9 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[1], xy), z), sh[10 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[2], y), fsub(ffma(4.0f, zz, -xx), yy)), sh[11 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[3], z), ffma(-3.0f, yy, ffma(2.0f, zz, -fmul(3.0f, xx)))), sh[12 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[4], x), fsub(ffma(4.0f, zz, -xx), yy)), sh[13 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[5], z), fsub(xx, yy)), sh[14 * 3 + ch], r);
+          r = ffma(fmul(fmul(SH_C3c[6], x), ffma(-3.0f, yy, xx)), sh[15 * 3 + ch], r);
+        }
+      }
+    }
+    r = fadd(r, 0.5f);
+    if (r < 0.f) bits |= (1u << ch);
+    rgb[ch] = fmaxf(r, 0.f);
+  }
+  *clamp_bits = bits;
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, float scale_modifier, uint32_t flags,
+                  Cameras cam, Gaussians g, float4 *__restrict__ geom, uint8_t *__restrict__ clamped,
+                  int32_t *__restrict__ radii, uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ dhist,
+                  uint2 *__restrict__ ranges, uint32_t *__restrict__ tilemax, int VT) {
+  __shared__ uint32_t s_hist[4][256];
+  const int v = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) (&s_hist[0][0])[k] = 0;
+  // zero the per-tile outputs (grid-stride over all threads of the launch)
+  {
+    size_t gtid = ((size_t)v * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    size_t gsz = (size_t)gridDim.x * gridDim.y * blockDim.x;
+    for (size_t t = gtid; t < (size_t)VT; t += gsz) {
+      ranges[t] = make_uint2(0u, 0u);
+      tilemax[t] = 0u;
+    }
+  }
+  __syncthreads();
+
+  uint32_t key = 0xFFFFFFFFu;
+  if (i < P) {
+    const float *Vm = cam.view + 16 * v;
+    const float *PV = cam.proj + 16 * v;
+    float tanfovx = cam.tanfov ? cam.tanfov[2 * v] : cam.tanfovx;
+    float tanfovy = cam.tanfov ? cam.tanfov[2 * v + 1] : cam.tanfovy;
+    float px = g.means3D[3 * i], py = g.means3D[3 * i + 1], pz = g.means3D[3 * i + 2];
+    int radius = 0;
+    uint32_t tiles = 0;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    uint32_t cbits = 0;
+
+    float pvx = dot3a(Vm[0], px, Vm[4], py, Vm[8], pz, Vm[12]);
+    float pvy = dot3a(Vm[1], px, Vm[5], py, Vm[9], pz, Vm[13]);
+    float pvz = dot3a(Vm[2], px, Vm[6], py, Vm[10], pz, Vm[14]);
+    if (pvz > 0.2f) {
+      float phx = dot3a(PV[0], px, PV[4], py, PV[8], pz, PV[12]);
+      float phy = dot3a(PV[1], px, PV[5], py, PV[9], pz, PV[13]);
+      float phw = dot3a(PV[3], px, PV[7], py, PV[11], pz, PV[15]);
+      float p_w = fdiv(1.0f, fadd(phw, 0.0000001f));
+      float ppx = fmul(phx, p_w), ppy = fmul(phy, p_w);
+      float c3[6];
+      if (g.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c3[k] = g.cov3D_precomp[6 * (size_t)i + k];
+      } else {
+        float sc[3] = {g.scales[3 * i], g.scales[3 * i + 1], g.scales[3 * i + 2]};
+        float4 q = reinterpret_cast<const float4 *>(g.rotations)[i];
+        cov3d_from_scale_rot(sc, scale_modifier, q, c3);
+      }
+      // A.2 step 4
+      float fx = fdiv((float)W, fmul(2.0f, tanfovx));
+      float fy = fdiv((float)H, fmul(2.0f, tanfovy));
+      float limx = fmul(1.3f, tanfovx), limy = fmul(1.3f, tanfovy);
+      float txtz = fdiv(pvx, pvz), tytz = fdiv(pvy, pvz);
+      float tx = fmul(fminf(limx, fmaxf(-limx, txtz)), pvz);
+      float ty = fmul(fminf(limy, fmaxf(-limy, tytz)), pvz);
+      float tz = pvz;
+      float J00 = fdiv(fx, tz);
+      float J02 = fdiv(-fmul(fx, tx), fmul(tz, tz));
+      float J11 = fdiv(fy, tz);
+      float J12 = fdiv(-fmul(fy, ty), fmul(tz, tz));
+      float T0[3], T1[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        float W0 = Vm[4 * c + 0], W1 = Vm[4 * c + 1], W2 = Vm[4 * c + 2];
+        T0[c] = dot2(J00, W0, J02, W2);
+        T1[c] = dot2(J11, W1, J12, W2);
+      }
+      float u0[3], u1[3];
+      const float S[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        u0[r] = dot3(S[r][0], T0[0], S[r][1], T0[1], S[r][2], T0[2]);
+        u1[r] = dot3(S[r][0], T1[0], S[r][1], T1[1], S[r][2], T1[2]);
+      }
+      float a = fadd(dot3(T0[0], u0[0], T0[1], u0[1], T0[2], u0[2]), 0.3f);
+      float b = dot3(T0[0], u1[0], T0[1], u1[1], T0[2], u1[2]);
+      float c = fadd(dot3(T1[0], u1[0], T1[1], u1[1], T1[2], u1[2]), 0.3f);
+      float det = ffma(a, c, -fmul(b, b));
+      if (det != 0.0f) {
+        float det_inv = fdiv(1.f, det);
+        float conx = fmul(c, det_inv), cony = fmul(-b, det_inv), conz = fmul(a, det_inv);
+        float mid = fmul(0.5f, fadd(a, c));
+        float sq = fsqrt(fmaxf(0.1f, ffma(mid, mid, -det)));
+        float l1 = fadd(mid, sq), l2 = fsub(mid, sq);
+        int rad = (int)ceilf(fmul(3.f, fsqrt(fmaxf(l1, l2))));
+        float pix_x = fmul(ffma(fadd(ppx, 1.0f), (float)W, -1.0f), 0.5f);
+        float pix_y = fmul(ffma(fadd(ppy, 1.0f), (float)H, -1.0f), 0.5f);
+        float rf = (float)rad;
+        int minx = min(gx, max(0, (int)fdiv(fsub(pix_x, rf), 16.0f)));
+        int miny = min(gy, max(0, (int)fdiv(fsub(pix_y, rf), 16.0f)));
+        int maxx = min(gx, max(0, (int)fdiv(fsub(fadd(fadd(pix_x, rf), 16.0f), 1.0f), 16.0f)));
+        int maxy = min(gy, max(0, (int)fdiv(fsub(fadd(fadd(pix_y, rf), 16.0f), 1.0f), 16.0f)));
+        int tt = (maxx - minx) * (maxy - miny);
+        if (tt != 0) {
+          float rgb[3];
+          if (g.colors_precomp) {
+            rgb[0] = g.colors_precomp[3 * i];
+            rgb[1] = g.colors_precomp[3 * i + 1];
+            rgb[2] = g.colors_precomp[3 * i + 2];
+          } else {
+            sh_to_rgb(D, g.shs + (size_t)i * M * 3, px, py, pz, cam.campos + 3 * v, rgb, &cbits);
+          }
+          radius = rad;
+          tiles = (uint32_t)tt;
+          key = __float_as_uint(pvz);
+          q0 = make_float4(pix_x, pix_y, conx, cony);
+          q1 = make_float4(conz, g.opacities[i], rgb[0], rgb[1]);
+          q2 = make_float4(rgb[2], pvz, __int_as_float(rad), __uint_as_float(tiles));
+        }
+      }
+    } else if (flags & GHR_FLAG_PREFILTERED) {
+      // upstream traps here ("Point is filtered although prefiltered is set"); we only cull.
+    }
+    size_t e = (size_t)v * P + i;
+    geom[3 * e + 0] = q0;
+    geom[3 * e + 1] = q1;
+    geom[3 * e + 2] = q2;
+    if (clamped) clamped[e] = (uint8_t)cbits;
+    radii[e] = radius;
+    depth_keys[e] = key;
+#pragma unroll
+    for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) {
+    uint32_t c = (&s_hist[0][0])[k];
+    int p = k >> 8, dgt = k & 255;
+    if (c) atomicAdd(&dhist[((size_t)p * V + v) * 256 + dgt], c);
+  }
+}
+
+__global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ Vm,
+                                    uint8_t *__restrict__ present) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float pvz = dot3a(Vm[2], means3D[3 * i], Vm[6], means3D[3 * i + 1], Vm[10], means3D[3 * i + 2], Vm[14]);
+  present[i] = pvz > 0.2f;
+}
+
+}  // namespace
+
+cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &cam, const Gaussians &g,
+                              float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,
+                              cudaStream_t s) {
+  int nb = (d.P + 255) / 256;
+  if (nb == 0) nb = 1;
+  dim3 grid(nb, d.V), block(256);
+  preprocess_kernel<<<grid, block, 0, s>>>(
+      d.P, d.V, d.H, d.W, d.M, d.sh_degree, L.gx, L.gy, scale_modifier, flags, cam, g,
+      (float4 *)(state + L.pub.off_geom), d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr, radii,
+      (uint32_t *)(temp + L.t_dkeys[0]), (uint32_t *)(temp + L.t_dhist), (uint2 *)(state + L.pub.off_ranges),
+      (uint32_t *)(state + L.pub.off_tilemax), d.V * L.T);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present,
+                                cudaStream_t s) {
+  if (P <= 0) return cudaSuccess;
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, view, present);
+  return cudaGetLastError();
+}
+
+}  // namespace ghr

@@ -1,0 +1,93 @@
+"""Camera-sharded data parallelism for the multi-view fitting step.
+
+The reference's only multi-GPU mechanism is Lightning DDP (/root/reference/infer_one_shot.py:631,638):
+an NCCL all-reduce of ~444 MB of *parameter* gradients per step.  Here the views of a step are
+sharded across ranks (one process per GPU), Gaussians are replicated, the forward needs no
+communication, and the only exchange is ONE all-reduce (sum) of the packed Gaussian-attribute
+gradient buffer -- 56 B x P for the colors_precomp path.  The rasterizer backward writes straight
+into that packed buffer (one flat allocation, one segment per attribute), so there is no
+pack/concat kernel before the collective.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_views(n_views: int, rank: int, world: int) -> range:
+    """Contiguous, balanced split of view indices [0, n_views): the first (n_views % world) ranks
+    take one extra view."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, rem = divmod(n_views, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+class PackedGrads:
+    """One flat fp32 buffer holding every Gaussian-attribute gradient that is summed over views.
+
+    Segment order (floats per Gaussian): means3D 3 | scales 3 | rotations 4 | opacity 1 |
+    colors 3 (colors_precomp path) or sh 3*M (SH path).  `views()` returns tensors aliasing the
+    buffer with the shapes ghr_backward writes."""
+
+    def __init__(self, P: int, M: int = 0, device="cpu", with_cov3D: bool = False):
+        self.P, self.M = int(P), int(M)
+        segs: List[Tuple[str, Tuple[int, ...]]] = [
+            ("dL_dmeans3D", (P, 3)), ("dL_dscales", (P, 3)), ("dL_drotations", (P, 4)), ("dL_dopacity", (P, 1))]
+        segs.append(("dL_dsh", (P, M, 3)) if M > 0 else ("dL_dcolors", (P, 3)))
+        if with_cov3D:
+            segs.append(("dL_dcov3D", (P, 6)))
+        self.segments = segs
+        n = sum(int(torch.Size(s).numel()) for _, s in segs)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        self._views: Dict[str, torch.Tensor] = {}
+        o = 0
+        for name, shape in segs:
+            k = int(torch.Size(shape).numel())
+            self._views[name] = self.flat[o:o + k].view(*shape)
+            o += k
+
+    @property
+    def floats_per_gaussian(self) -> int:
+        return self.flat.numel() // max(self.P, 1)
+
+    @property
+    def nbytes(self) -> int:
+        return self.flat.numel() * 4
+
+    def views(self) -> Dict[str, torch.Tensor]:
+        return dict(self._views)
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+    def all_reduce_(self, group=None, async_op: bool = False):
+        """Sum over ranks, in place.  No-op without an initialised process group (N=1)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
+                   group=None, sh_degree: int = 0, scale_modifier: float = 1.0,
+                   R_cap: Optional[int] = None, check: str = "poll"):
+    """One camera-sharded step on this rank: forward + backward of the LOCAL views, gradients written
+    into `grads` (overwritten), then the all-reduce.  Returns (color [V,3,H,W], radii [V,P]).
+
+    gauss: dict with means3D, opacities, scales, rotations and colors_precomp or shs (CUDA fp32).
+    views: guassianhand_b200.api.ViewBatch of the local shard.  dL_dout: [V,3,H,W]."""
+    from . import api
+    cams = views.cams()
+    f32 = api._f32c
+    means3D, opac = f32(gauss["means3D"]), f32(gauss["opacities"])
+    sc, rot = f32(gauss["scales"]), f32(gauss["rotations"])
+    shs = f32(gauss["shs"]) if gauss.get("shs") is not None else None
+    col = f32(gauss["colors_precomp"]) if gauss.get("colors_precomp") is not None else None
+    res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier, check=check,
+                          R_cap=R_cap)
+    api.backward_raw(cams, res.state, res.R_cap, dL_dout, means3D, opac, sc, rot, None, shs, col, sh_degree,
+                     scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False)
+    grads.all_reduce_(group)
+    return res.color, res.radii

@@ -1,0 +1,166 @@
+/*
+ * ghr.h -- C ABI of libghr.so, the B200-native (sm_100a) Gaussian-splatting rasterizer.
+ *
+ * Drop-in boundary.  GuassianHand calls the rasterizer only through the Python package
+ * `diff_gaussian_rasterization` (/root/reference/tgs/models/renderer_one_shot.py:3, :281-296,
+ * :338-346, :355-379; same lines in renderer_one_shot_edit.py).  That package's native surface is
+ * a pybind module with three entry points (upstream rasterize_points.cu):
+ *     rasterize_gaussians(...)            -> ghr_forward
+ *     rasterize_gaussians_backward(...)   -> ghr_backward
+ *     mark_visible(...)                   -> ghr_mark_visible
+ * The functions below are what an FFI binding of that path binds instead.  Conventions:
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions across the ABI.
+ *   - every pointer in the argument structs is a DEVICE pointer unless its comment says "host";
+ *     NULL means "absent" for the optional inputs.  All arrays are contiguous fp32 / int32.
+ *   - the caller owns all memory.  The library never allocates device memory and never
+ *     synchronises unless GHR_FLAG_DEBUG is set; all work is enqueued on the given stream
+ *     (a cudaStream_t passed as void*).
+ *   - return value: 0 on success, negative GHR_E* on failure; ghr_last_error() gives the text
+ *     (thread-local).  Capacity overflow of the binning buffers is reported asynchronously in
+ *     GhrStatus (device) because detecting it on the host would need the device sync this
+ *     design removes; see ghr_read_status().
+ *   - V >= 1 cameras ("views") may be rendered by one call: Gaussians are shared, every
+ *     per-view array is laid out view-major.  V == 1 is exactly the upstream call.
+ */
+#ifndef GHR_H_
+#define GHR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GHR_OK 0
+#define GHR_EINVAL (-1)     /* bad argument (NULL required pointer, negative size, ...) */
+#define GHR_ENOSPC (-2)     /* state/temp buffer smaller than ghr_layout() demands */
+#define GHR_ECUDA (-3)      /* a CUDA call failed; text in ghr_last_error() */
+#define GHR_EOVERFLOW (-4)  /* ghr_read_status: R exceeded R_cap in the last forward */
+
+#define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
+#define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
+
+#define GHR_ABI_VERSION 1
+
+/* Problem dimensions.  T = ceil(W/16)*ceil(H/16) tiles per view, N = H*W pixels per view. */
+typedef struct GhrDims {
+  int32_t P;         /* Gaussians */
+  int32_t V;         /* views (cameras) in this call */
+  int32_t H, W;      /* image size, identical for all views of a call */
+  int32_t M;         /* SH coefficients per Gaussian (shs.shape[1]); 0 with colors_precomp */
+  int32_t sh_degree; /* active SH degree 0..3 (settings.sh_degree) */
+  int64_t R_cap;     /* capacity (entries) of the (tile, Gaussian) instance buffers, all views */
+} GhrDims;
+
+/* Byte offsets inside the caller-provided `state` buffer (kept from forward to backward) and
+ * sizes of both buffers.  Filled by ghr_layout(); also lets tests read intermediates. */
+typedef struct GhrLayout {
+  size_t state_bytes, temp_bytes, temp_bwd_bytes;
+  size_t off_status;   /* GhrStatus */
+  size_t off_geom;     /* float4[3] per (view, Gaussian): {x,y,conic.x,conic.y} {conic.z,opacity,r,g}
+                          {b, depth, radius(int bits), tiles_touched(uint bits)} */
+  size_t off_clamped;  /* uint8 per (view, Gaussian): bit c set if SH colour channel c was clamped */
+  size_t off_ranges;   /* uint32[2] per (view, tile): [start,end) into the sorted instances */
+  size_t off_tilemax;  /* uint32 per (view, tile): max n_contrib in the tile */
+  size_t off_records;  /* 48-byte instance records in sorted order:
+                          {x,y,conic.x,conic.y} {conic.z,opacity,r,g} {b, id(uint bits), 0, 0} */
+  size_t off_final_T;  /* float per (view, pixel) */
+  size_t off_ncontrib; /* uint32 per (view, pixel) */
+} GhrLayout;
+
+typedef struct GhrStatus {
+  uint64_t R;          /* number of (tile, Gaussian) instances the forward produced (all views) */
+  uint32_t overflow;   /* 1 if R > R_cap: the forward output is invalid, retry with larger R_cap */
+  uint32_t n_visible;  /* Gaussians (summed over views) with radius > 0 */
+  uint64_t reserved[2]; /* [0] = GhrForwardArgs.seq of the forward that wrote this status */
+} GhrStatus;
+
+typedef struct GhrForwardArgs {
+  GhrDims dims;
+  uint32_t flags;
+  float scale_modifier;
+  float tanfovx, tanfovy;      /* host scalars; used when `tanfov` is NULL */
+  /* cameras */
+  const float *viewmatrix;     /* [V,16]  settings.viewmatrix  (= w2c^T, renderer_one_shot.py:96) */
+  const float *projmatrix;     /* [V,16]  settings.projmatrix  (:104-106) */
+  const float *campos;         /* [V,3]   settings.campos      (:107) */
+  const float *tanfov;         /* [V,2] (tanfovx, tanfovy) per view, or NULL */
+  const float *bg;             /* [3] (bg_stride 0) or [V,3] (bg_stride 3) */
+  int32_t bg_stride;
+  /* Gaussians, shared by all views */
+  const float *means3D;        /* [P,3] */
+  const float *opacities;      /* [P]   */
+  const float *scales;         /* [P,3] or NULL */
+  const float *rotations;      /* [P,4] or NULL */
+  const float *cov3D_precomp;  /* [P,6] or NULL */
+  const float *shs;            /* [P,M,3] or NULL */
+  const float *colors_precomp; /* [P,3] or NULL */
+  /* outputs */
+  float *out_color;            /* [V,3,H,W] */
+  int32_t *radii;              /* [V,P] */
+  /* workspaces */
+  void *state; size_t state_bytes;
+  void *temp;  size_t temp_bytes;
+  /* optional parity/debug exports (device, may be NULL): the upstream intermediates */
+  uint64_t *dbg_keys_sorted;   /* [R_cap] (tile<<32 | depth bits), tile local to its view */
+  uint32_t *dbg_point_list;    /* [R_cap] Gaussian index within its view */
+  /* optional early status report: if non-NULL (PINNED HOST memory), GhrStatus is copied there
+   * as soon as R is known (after the scan, before the tile sort and the blend are enqueued), with
+   * reserved[0] == seq.  The host can poll it while the GPU keeps working -- this replaces the
+   * blocking D2H read of num_rendered in upstream's forward without stalling the pipeline. */
+  GhrStatus *host_status;
+  uint64_t seq;
+} GhrForwardArgs;
+
+typedef struct GhrBackwardArgs {
+  GhrDims dims;
+  uint32_t flags;
+  float scale_modifier;
+  float tanfovx, tanfovy;
+  const float *viewmatrix, *projmatrix, *campos, *tanfov, *bg;
+  int32_t bg_stride;
+  const float *means3D, *opacities, *scales, *rotations, *cov3D_precomp, *shs, *colors_precomp;
+  const float *dL_dout_color;  /* [V,3,H,W] */
+  const void *state; size_t state_bytes;   /* as written by ghr_forward */
+  void *temp; size_t temp_bytes;           /* >= layout.temp_bwd_bytes */
+  /* Gradient outputs.  Summed over the V views.  accumulate != 0: "+=" into the buffers
+   * (multi-call accumulation before an all-reduce), else overwritten.  NULL = not wanted. */
+  int32_t accumulate;
+  float *dL_dmeans3D;   /* [P,3] */
+  float *dL_dmeans2D;   /* [V,P,3] per view, NDC units (x 0.5W, 0.5H), z = 0; never accumulated */
+  float *dL_dcolors;    /* [P,3]   (colors_precomp path) */
+  float *dL_dopacity;   /* [P]     */
+  float *dL_dcov3D;     /* [P,6]   (always available; the grad when cov3D_precomp is used) */
+  float *dL_dsh;        /* [P,M,3] (SH path) */
+  float *dL_dscales;    /* [P,3] */
+  float *dL_drotations; /* [P,4] */
+  float *dL_dconic;     /* [V,P,4] optional debug export (xx, xy, 0, yy) */
+} GhrBackwardArgs;
+
+int ghr_abi_version(void);
+const char *ghr_last_error(void);
+/* sizeof() of an ABI struct by name ("GhrForwardArgs", ...), 0 if unknown: lets a foreign-language
+ * binding verify its mirror of the structs at load time. */
+size_t ghr_struct_size(const char *name);
+
+/* Sizes/offsets of the caller-owned buffers for the given dimensions. */
+int ghr_layout(const GhrDims *dims, GhrLayout *out);
+
+/* Replaces upstream rasterize_gaussians(): preprocess -> bin -> sort -> blend, V views. */
+int ghr_forward(const GhrForwardArgs *args, void *cuda_stream);
+
+/* Replaces upstream rasterize_gaussians_backward(). */
+int ghr_backward(const GhrBackwardArgs *args, void *cuda_stream);
+
+/* Replaces upstream mark_visible(): present[i] = (view-space z > 0.2). */
+int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
+                     uint8_t *present, void *cuda_stream);
+
+/* Enqueue an async copy of GhrStatus from `state` into pinned host memory `host_status`. */
+int ghr_read_status_async(const void *state, GhrStatus *host_status, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GHR_H_ */

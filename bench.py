@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""Benchmark of the rasterizer hot path: fwd+bwd views/s on the BASELINE.json C2 scene
+(two-hand, 60k Gaussians, 512x334, precomputed colours), camera-sharded over N GPUs.
+
+    python bench.py [--gpus N --steps K --warmup W] [--views B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch: B distinct views (default 8 = the per-GPU share
+of BASELINE config 3, a 64-view fitting step on 8 GPUs) rendered forward + backward by ONE batched
+call chain on every rank, gradients summed over views in the packed buffer, then (N>1) one NCCL
+all-reduce of that buffer.  Weak scaling: B views per rank per step.
+  value   : views/s over all ranks, inputs resident in HBM, CUDA events, max over ranks, L2 flushed
+            between steps.
+  e2e     : same metric through the public autograd API (guassianhand_b200.rasterize_views) with
+            host buffers: H2D of Gaussian attributes + cameras and D2H of gradients + loss inside
+            the timed region (wall clock, max over ranks).
+  roofline: dominant kernel's algorithmic bytes / its live CUDA-event duration vs the measured HBM
+            peak (MEASURED_PEAKS.json), plus an FP32 view of the blend kernels.
+  cpu_baseline / --impl reference: the CPU oracle (oracle/gs_oracle.c, OpenMP, all host threads)
+            on a bounded sample of the same workload.  The reference's own implementation of this
+            path (pip diff-gaussian-rasterization) is absent from /root/reference and from the box,
+            so the oracle port is the reference arm (kind "port").
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2 = dict(P=60000, H=512, W=334, pool_views=64, seed=0)
+METRIC = "fwd+bwd views/s @512x334 two-hand Gaussians"
+UNIT = "views/s"
+
+
+def _workload(B):
+    return (f"BASELINE config 2 scene (two-hand, {C2['P']} Gaussians, {C2['H']}x{C2['W']}, colors_precomp, "
+            f"scale/rotation covariance); step = {B} distinct views fwd+bwd per rank in one batched call "
+            f"(config 3 shard: 64-view pool), grads summed over views")
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML every `period` s while running."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.005):
+        self.samples, self.reasons, self.period, self.on = [], 0, period, False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def _run(self):
+        while self.on:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.reasons |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self.on = True
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        if self.nv:
+            self.on = False
+            self.t.join()
+
+    def summary(self):
+        if not self.nv or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        names = [n for b, n in self.REASONS.items() if self.reasons & b and n != "gpu_idle"]
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": names,
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+def cpu_views_per_s(n_views, threads=None, budget_s=None):
+    """fwd+bwd of `n_views` C2 views through the CPU oracle; returns (views/s, views done, threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from guassianhand_b200 import scenes
+    from oracle import oracle_lib as ol
+    import util
+    L = ol.lib()
+    if threads:
+        L.gso_set_num_threads(int(threads))
+    nthr = L.gso_num_threads()
+    sc = scenes.two_hand_scene(C2["P"], seed=C2["seed"])
+    cams = scenes.fibonacci_cameras(C2["pool_views"], C2["H"], C2["W"], seed=C2["seed"])
+    rng = np.random.default_rng(1)
+    dL = (rng.normal(size=(3, C2["H"], C2["W"])) / (C2["H"] * C2["W"])).astype(np.float32)
+    bg = np.zeros(3, np.float32)
+    done, t0 = 0, time.perf_counter()
+    for v in range(n_views):
+        osc = util.oracle_scene(sc, cams[v % len(cams)], bg)
+        ol.forward_backward(osc, dL)
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, nthr
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncpu = os.cpu_count()
+    # warm-up (also builds/loads the oracle), then K steps of one view each
+    for _ in range(max(args.warmup, 1)):
+        cpu_views_per_s(1, threads=ncpu)
+    t0 = time.perf_counter()
+    vps, done, nthr = cpu_views_per_s(args.steps, threads=ncpu, budget_s=240.0)
+    dt = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(done, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": _workload(args.views), "sample": "1 view fwd+bwd per step on the host CPU"},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
+                         "sample": f"{done} single views of the C2 scene, oracle/gs_oracle.c with OpenMP on "
+                                   f"{nthr} threads (upstream diff-gaussian-rasterization is not installable here)"},
+        "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+
+def algorithmic_bytes(stage, P, V, N, T, R, M=0):
+    """SURVEY.md §8(d) per-stage algorithmic bytes, for V views with R instances in total."""
+    sh_f = (12 * M + 12) * P * V if M else 0
+    sh_b = (24 * M + 3) * P * V if M else 0
+    return {
+        "preprocess": 80 * P * V + sh_f,
+        "depth_sort": 8 * P * V,           # compulsory: 4B key + 4B index in, sorted index out
+        "scan_duplicate": (8 + 20) * P * V + 12 * R,
+        "tile_sort": 24 * R,
+        "gather_ranges": 8 * R + 8 * T * V,
+        "blend_forward": 40 * R + 20 * N * V,
+        "blend_backward": 40 * R + (20 * N + 36 * P) * V,
+        "preprocess_backward": 120 * P * V + sh_b,
+    }[stage]
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from guassianhand_b200 import _native as NV, api, scenes
+    from guassianhand_b200.dist import PackedGrads, fit_step_grads
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import util
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    NV.lib()
+    B, K, Wm = args.views, args.steps, max(args.warmup, 3)
+    P, H, W = C2["P"], C2["H"], C2["W"]
+    N, T = H * W, ((W + 15) // 16) * ((H + 15) // 16)
+
+    sc = scenes.two_hand_scene(P, seed=C2["seed"])
+    cams = scenes.fibonacci_cameras(C2["pool_views"], H, W, seed=C2["seed"])
+    bg = np.zeros(3, np.float32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    gauss = dict(means3D=t(sc.means3D), opacities=t(sc.opacities), scales=t(sc.scales), rotations=t(sc.rotations),
+                 colors_precomp=t(sc.colors))
+    n_groups = max(1, len(cams) // (B * world)) if B * world <= len(cams) else 1
+
+    def group_cams(step):
+        base = (step % n_groups) * B * world + rank * B
+        return [cams[(base + j) % len(cams)] for j in range(B)]
+
+    view_groups = [util.gpu_views(group_cams(g), bg, dev) for g in range(n_groups)]
+    rng = np.random.default_rng(1 + rank)
+    dL = t((rng.normal(size=(B, 3, H, W)) / N).astype(np.float32))
+    grads = PackedGrads(P, 0, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---- calibration: instance counts per view group (poll mode, exact) ----
+    Rs, pairs = [], []
+    for g in range(n_groups):
+        res = fit_step_grads(gauss, view_groups[g], dL, grads)
+        Rs.append(res.R)
+        lay = NV.layout(P, B, H, W, 0, 0, res.R_cap)
+        nc = res.state[lay.off_ncontrib: lay.off_ncontrib + B * N * 4].view(torch.int32)
+        pairs.append(int(nc.sum(dtype=torch.int64).item()))
+    R_cap = int(max(Rs) * 1.25) + (1 << 14)
+    lay = NV.layout(P, B, H, W, 0, 0, R_cap)
+    npt = (max(1, int(np.ceil(np.log2(max(B * T, 2))))) + 7) // 8
+    launches_per_step = 1 + 1 + 4 + 1 + npt + 1 + 1 + 2       # init, preprocess, 4 depth passes, scan, tile passes, gather, blend | 2 bwd
+
+    status_pin = torch.zeros(K + Wm, 4, dtype=torch.int64).pin_memory()
+
+    def step(i, fe=None, be=None):
+        res = fit_step_grads(gauss, view_groups[i % n_groups], dL, grads, R_cap=R_cap, check="none",
+                             fwd_events=fe, bwd_events=be)
+        return res
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(Wm):
+        step(i)
+    sync_all()
+
+    fwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_FWD) for _ in range(K)]
+    bwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_BWD) for _ in range(K)]
+    ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stream = torch.cuda.current_stream()
+    sync_all()
+    with ClockSampler(local) as clk:
+        for i in range(K):
+            flush.zero_()                                   # L2 flush, outside the timed events
+            ev_s[i].record()
+            res = step(i, fwd_ev[i], bwd_ev[i])
+            ev_e[i].record()
+            NV.check(NV.lib().ghr_read_status_async(res.state.data_ptr(), status_pin[i].data_ptr(),
+                                                    stream.cuda_stream), "status")
+        sync_all()
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))
+    if int((status_pin[:K, 1] & 0xFFFFFFFF).sum()) != 0:
+        raise RuntimeError("bench: instance capacity overflow inside the timed region; result invalid")
+    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms_max = float(tmax.item())
+    value = world * B * K / (total_ms_max / 1000.0)
+
+    stage_ms = {}
+    for si, name in enumerate(NV.FWD_STAGES):
+        stage_ms[name] = float(np.mean([fwd_ev[i].elapsed_ms(si) for i in range(K)]))
+    for si, name in enumerate(NV.BWD_STAGES):
+        stage_ms[name] = float(np.mean([bwd_ev[i].elapsed_ms(si) for i in range(K)]))
+    for e in fwd_ev + bwd_ev:
+        e.close()
+    R_mean = float(np.mean(status_pin[:K, 0].numpy()))
+    I_mean = float(np.mean(pairs))
+
+    # ---- single-view latency (the shape the reference itself runs: 1 view per call) ----
+    v1 = util.gpu_views([cams[0]], bg, dev)
+    dL1 = dL[:1].contiguous()
+    r1 = fit_step_grads(gauss, v1, dL1, grads)
+    cap1 = int(r1.R * 1.25) + (1 << 14)
+    for _ in range(5):
+        fit_step_grads(gauss, v1, dL1, grads, R_cap=cap1, check="none")
+    torch.cuda.synchronize()
+    s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n1 = 50
+    s1.record()
+    for _ in range(n1):
+        fit_step_grads(gauss, v1, dL1, grads, R_cap=cap1, check="none")
+    e1.record()
+    torch.cuda.synchronize()
+    single_ms = s1.elapsed_time(e1) / n1
+
+    # ---- FP32 peak probe (dependent FMA chains) ----
+    import ctypes as C
+    sink = torch.zeros(1, device=dev)
+    flops = C.c_double()
+    NV.check(NV.lib().ghr_fp32_probe(1 << 14, sink.data_ptr(), C.byref(flops), stream.cuda_stream), "probe")
+    torch.cuda.synchronize()
+    ps, pe = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ps.record()
+    NV.check(NV.lib().ghr_fp32_probe(1 << 14, sink.data_ptr(), C.byref(flops), stream.cuda_stream), "probe")
+    pe.record()
+    torch.cuda.synchronize()
+    fp32_peak = flops.value / (ps.elapsed_time(pe) * 1e-3) / 1e12
+
+    # ---- e2e through the public autograd API with host buffers ----
+    host = {k: v.detach().cpu().pin_memory() for k, v in gauss.items()}
+    host_views = [{"viewmatrix": vg.viewmatrix.cpu().pin_memory(), "projmatrix": vg.projmatrix.cpu().pin_memory(),
+                   "campos": vg.campos.cpu().pin_memory(), "tanfov": vg.tanfov.cpu().pin_memory()}
+                  for vg in view_groups]
+    host_grads = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+    bg_dev = t(bg)
+    h2d = sum(v.numel() * 4 for v in host.values()) + sum(v.numel() * 4 for v in host_views[0].values())
+    d2h = sum(v.numel() * 4 for v in host_grads.values()) + 4
+
+    def e2e_step(i):
+        leaf = {k: v.to(dev, non_blocking=True).requires_grad_(True) for k, v in host.items()}
+        hv = host_views[i % n_groups]
+        views = api.ViewBatch(image_height=H, image_width=W, viewmatrix=hv["viewmatrix"].to(dev, non_blocking=True),
+                              projmatrix=hv["projmatrix"].to(dev, non_blocking=True),
+                              campos=hv["campos"].to(dev, non_blocking=True),
+                              tanfov=hv["tanfov"].to(dev, non_blocking=True), bg=bg_dev)
+        imgs, _ = api.rasterize_views(leaf["means3D"], leaf["opacities"], views, colors_precomp=leaf["colors_precomp"],
+                                      scales=leaf["scales"], rotations=leaf["rotations"])
+        loss = (imgs * dL).sum()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([leaf[k].grad.reshape(-1) for k in host])
+            dist.all_reduce(flat)
+            o = 0
+            for k in host:
+                n = host[k].numel()
+                host_grads[k].copy_(flat[o:o + n].view_as(host[k]), non_blocking=True)
+                o += n
+        else:
+            for k in host:
+                host_grads[k].copy_(leaf[k].grad, non_blocking=True)
+        return float(loss.item())
+
+    for i in range(3):
+        e2e_step(i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K / float(te.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        dom = max(stage_ms, key=stage_ms.get)
+        alg = algorithmic_bytes(dom, P, B, N, T, R_mean)
+        ach = alg / (stage_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        step_bytes = sum(algorithmic_bytes(s, P, B, N, T, R_mean) for s in stage_ms)
+        blend_flops = {"blend_forward": 24.0 * I_mean, "blend_backward": 70.0 * I_mean}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload(B), "views_per_rank_per_step": B, "gaussians": P, "image": [H, W],
+                       "instances_per_step": R_mean, "blend_pairs_per_step": I_mean, "R_cap": R_cap,
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"camera-sharded dp{world}",
+                       "collective": "none (N=1)" if world == 1 else "NCCL all-reduce of packed grads (56 B x P)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
+                         "launch_ms": stage_ms[dom], "peak_source": peak_src},
+            "roofline_step": {"algorithmic_bytes_per_step": step_bytes,
+                              "achieved_GBps": step_bytes / (total_ms_max / K * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": step_bytes / (total_ms_max / K * 1e-3) / 1e9 / hbm_peak},
+            "roofline_fp32": {"peak_tflops_measured": fp32_peak, "peak_tflops_nominal": 74.4,
+                              **{k: {"flops_per_launch": f, "achieved_tflops": f / (stage_ms[k] * 1e-3) / 1e12,
+                                     "frac": f / (stage_ms[k] * 1e-3) / 1e12 / fp32_peak}
+                                 for k, f in blend_flops.items()}},
+            "stage_ms": stage_ms,
+            "single_view": {"ms_per_view": single_ms, "views_per_s": 1000.0 / single_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "guassianhand_b200.rasterize_views + autograd, pinned host buffers, wall clock"},
+            "gpu_launches": launches_per_step * K,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            vps, done, nthr = cpu_views_per_s(64, threads=os.cpu_count(), budget_s=12.0)
+            line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
+                                    "sample": f"{done} single views of the same C2 scene, fwd+bwd, "
+                                              f"oracle/gs_oracle.c OpenMP on {nthr} threads"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--views", type=int, default=8, help="views per rank per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -11,10 +11,14 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 1
+GHR_ABI_VERSION = 2
+GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 6, 2
+FWD_STAGES = ["preprocess", "depth_sort", "scan_duplicate", "tile_sort", "gather_ranges", "blend_forward"]
+BWD_STAGES = ["blend_backward", "preprocess_backward"]
 
 EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",
-           "ghr_mark_visible", "ghr_read_status_async"]
+           "ghr_mark_visible", "ghr_read_status_async", "ghr_event_create", "ghr_event_destroy", "ghr_event_record",
+           "ghr_event_elapsed_ms", "ghr_fp32_probe"]
 
 _vp = C.c_void_p
 
@@ -46,7 +50,7 @@ class GhrForwardArgs(C.Structure):
         ("out_color", _vp), ("radii", _vp),
         ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
         ("dbg_keys_sorted", _vp), ("dbg_point_list", _vp),
-        ("host_status", _vp), ("seq", C.c_uint64),
+        ("host_status", _vp), ("seq", C.c_uint64), ("stage_events", _vp),
     ]
 
 
@@ -63,6 +67,7 @@ class GhrBackwardArgs(C.Structure):
         ("accumulate", C.c_int32),
         ("dL_dmeans3D", _vp), ("dL_dmeans2D", _vp), ("dL_dcolors", _vp), ("dL_dopacity", _vp),
         ("dL_dcov3D", _vp), ("dL_dsh", _vp), ("dL_dscales", _vp), ("dL_drotations", _vp), ("dL_dconic", _vp),
+        ("stage_events", _vp),
     ]
 
 
@@ -94,6 +99,11 @@ def lib():
     L.ghr_mark_visible.argtypes = [C.c_int32, _vp, _vp, _vp, _vp, _vp]
     L.ghr_read_status_async.restype = C.c_int
     L.ghr_read_status_async.argtypes = [_vp, _vp, _vp]
+    L.ghr_event_create.argtypes = [C.POINTER(_vp)]
+    L.ghr_event_destroy.argtypes = [_vp]
+    L.ghr_event_record.argtypes = [_vp, _vp]
+    L.ghr_event_elapsed_ms.argtypes = [_vp, _vp, C.POINTER(C.c_float)]
+    L.ghr_fp32_probe.argtypes = [C.c_int32, _vp, C.POINTER(C.c_double), _vp]
     L.ghr_struct_size.restype = C.c_size_t
     L.ghr_struct_size.argtypes = [C.c_char_p]
     for cls in (GhrDims, GhrLayout, GhrStatus, GhrForwardArgs, GhrBackwardArgs):
@@ -117,3 +127,29 @@ def layout(P, V, H, W, M, sh_degree, R_cap) -> GhrLayout:
     out = GhrLayout()
     check(lib().ghr_layout(C.byref(d), C.byref(out)), "ghr_layout")
     return out
+
+
+class StageEvents:
+    """2*n cudaEvent_t handles (start, stop per stage) for GhrForwardArgs/GhrBackwardArgs.stage_events."""
+
+    def __init__(self, n: int):
+        self.n = n
+        self.arr = (_vp * (2 * n))()
+        for i in range(2 * n):
+            e = _vp()
+            check(lib().ghr_event_create(C.byref(e)), "ghr_event_create")
+            self.arr[i] = e.value
+
+    def ptr(self):
+        return C.cast(self.arr, _vp).value
+
+    def elapsed_ms(self, i: int) -> float:
+        ms = C.c_float()
+        check(lib().ghr_event_elapsed_ms(self.arr[2 * i], self.arr[2 * i + 1], C.byref(ms)), "ghr_event_elapsed_ms")
+        return float(ms.value)
+
+    def close(self):
+        for i in range(2 * self.n):
+            if self.arr[i]:
+                lib().ghr_event_destroy(self.arr[i])
+                self.arr[i] = None

@@ -148,7 +148,7 @@ class ForwardResult(NamedTuple):
 
 def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
                 scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
-                R_cap: Optional[int] = None) -> ForwardResult:
+                R_cap: Optional[int] = None, stage_events=None) -> ForwardResult:
     """Enqueue one libghr forward (V views).  check: "poll" (exact, re-runs on overflow),
     "none" (caller checks GhrStatus later; needed under CUDA-graph capture)."""
     L = N.lib()
@@ -176,6 +176,8 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
             dbg = dict(keys=torch.zeros(max(cap, 1), dtype=torch.int64, device=dev),
                        point_list=torch.zeros(max(cap, 1), dtype=torch.int32, device=dev), layout=lay)
             a.dbg_keys_sorted, a.dbg_point_list = dbg["keys"].data_ptr(), dbg["point_list"].data_ptr()
+        if stage_events is not None:
+            a.stage_events = stage_events.ptr()
         row = None
         seq = next(_seq)
         a.seq = seq
@@ -205,7 +207,7 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
 
 def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, scales, rotations, cov3D, shs,
                  colors, sh_degree, scale_modifier, flags=0, want_means2D=True, accumulate_into=None,
-                 want_conic=False, accumulate=True):
+                 want_conic=False, accumulate=True, stage_events=None):
     """Enqueue one libghr backward.  Returns dict of gradient tensors (summed over views, except
     dL_dmeans2D which is per view)."""
     L = N.lib()
@@ -242,6 +244,8 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dcov3D", "dL_dsh", "dL_dscales",
               "dL_drotations", "dL_dconic"):
         setattr(a, k, _ptr(g.get(k)))
+    if stage_events is not None:
+        a.stage_events = stage_events.ptr()
     N.check(L.ghr_backward(C.byref(a), stream.cuda_stream), "ghr_backward")
     return g
 

@@ -94,6 +94,24 @@ static int check_cuda(cudaError_t e, const char *what, bool debug, cudaStream_t 
     if (_rc != GHR_OK) return _rc;                           \
   } while (0)
 
+struct StageTimer {
+  void **ev; cudaStream_t s;
+  void start(int i) { if (ev) cudaEventRecord((cudaEvent_t)ev[2 * i], s); }
+  void stop(int i) { if (ev) cudaEventRecord((cudaEvent_t)ev[2 * i + 1], s); }
+};
+
+__global__ void fp32_probe_kernel(int iters, float *sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+        a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; i++) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (r == 123.456f) *sink = r;
+}
+
 }  // namespace ghr
 
 using namespace ghr;
@@ -166,6 +184,8 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   Cameras cam{a->viewmatrix, a->projmatrix, a->campos, a->tanfov, a->bg, a->tanfovx, a->tanfovy, a->bg_stride};
   Gaussians g{a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs, a->colors_precomp};
 
+  StageTimer tm{a->stage_events, s};
+  tm.start(0);
   GHR_TRY(cudaMemsetAsync(temp, 0, L.t_zero_bytes, s), "ghr_forward: memset(temp)");
   {
     // status starts as {R=0, overflow=0, n_visible=0, seq}: 32 bytes passed by value
@@ -176,23 +196,34 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   }
   GHR_TRY(launch_preprocess(d, L, cam, g, a->scale_modifier, a->flags, state, temp, a->radii, s),
           "ghr_forward: preprocess");
+  tm.stop(0);
   if (d.P > 0) {
+    tm.start(1);
     GHR_TRY(launch_depth_sort(d, L, temp, s), "ghr_forward: depth sort");
+    tm.stop(1);
+    tm.start(2);
     GHR_TRY(launch_scan_duplicate(d, L, state, temp, a->seq, s), "ghr_forward: scan+duplicate");
+    tm.stop(2);
     if (a->host_status)
       GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost,
                               s),
               "ghr_forward: status copy");
     if (d.R_cap > 0) {
+      tm.start(3);
       GHR_TRY(launch_tile_sort(d, L, state, temp, s), "ghr_forward: tile sort");
+      tm.stop(3);
+      tm.start(4);
       GHR_TRY(launch_gather_ranges(d, L, state, temp, a->dbg_keys_sorted, a->dbg_point_list, s),
               "ghr_forward: gather+ranges");
+      tm.stop(4);
     }
   }
+  tm.start(5);
   if (a->host_status && d.P == 0)
     GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
             "ghr_forward: status copy");
   GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, s), "ghr_forward: blend");
+  tm.stop(5);
   return GHR_OK;
 }
 
@@ -224,10 +255,15 @@ int ghr_backward(const GhrBackwardArgs *a, void *cuda_stream) {
   GradOut go{a->accumulate, a->dL_dmeans3D, a->dL_dmeans2D, a->dL_dcolors, a->dL_dopacity, a->dL_dcov3D,
              a->dL_dsh, a->dL_dscales, a->dL_drotations, a->dL_dconic};
 
+  StageTimer tm{a->stage_events, s};
+  tm.start(0);
   GHR_TRY(cudaMemsetAsync(acc, 0, (size_t)d.V * d.P * kAccStride * sizeof(float), s), "ghr_backward: memset(acc)");
   GHR_TRY(launch_blend_backward(d, L, cam, state, a->dL_dout_color, acc, s), "ghr_backward: blend");
+  tm.stop(0);
+  tm.start(1);
   GHR_TRY(launch_preprocess_backward(d, L, cam, g, a->scale_modifier, state, acc, go, s),
           "ghr_backward: preprocess");
+  tm.stop(1);
   return GHR_OK;
 }
 
@@ -241,6 +277,41 @@ int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool debug = false;
   GHR_TRY(launch_mark_visible(P, means3D, viewmatrix, present, s), "ghr_mark_visible");
+  return GHR_OK;
+}
+
+int ghr_event_create(void **event_out) {
+  if (!event_out) { set_error("ghr_event_create: NULL"); return GHR_EINVAL; }
+  cudaEvent_t e;
+  cudaError_t rc = cudaEventCreate(&e);
+  if (rc != cudaSuccess) { set_error("ghr_event_create: %s", cudaGetErrorString(rc)); return GHR_ECUDA; }
+  *event_out = (void *)e;
+  return GHR_OK;
+}
+int ghr_event_destroy(void *event) {
+  if (event) cudaEventDestroy((cudaEvent_t)event);
+  return GHR_OK;
+}
+int ghr_event_record(void *event, void *cuda_stream) {
+  cudaError_t rc = cudaEventRecord((cudaEvent_t)event, (cudaStream_t)cuda_stream);
+  if (rc != cudaSuccess) { set_error("ghr_event_record: %s", cudaGetErrorString(rc)); return GHR_ECUDA; }
+  return GHR_OK;
+}
+int ghr_event_elapsed_ms(void *start, void *stop, float *ms_out) {
+  if (!ms_out) { set_error("ghr_event_elapsed_ms: NULL"); return GHR_EINVAL; }
+  cudaError_t rc = cudaEventElapsedTime(ms_out, (cudaEvent_t)start, (cudaEvent_t)stop);
+  if (rc != cudaSuccess) { set_error("ghr_event_elapsed_ms: %s", cudaGetErrorString(rc)); return GHR_ECUDA; }
+  return GHR_OK;
+}
+
+int ghr_fp32_probe(int32_t iters, float *sink, double *flops_out, void *cuda_stream) {
+  if (iters <= 0 || !sink) { set_error("ghr_fp32_probe: bad arguments"); return GHR_EINVAL; }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool debug = false;
+  const int blocks = 148 * 8, threads = 256;
+  fp32_probe_kernel<<<blocks, threads, 0, s>>>(iters, sink);
+  if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * blocks * threads;
+  GHR_TRY(cudaGetLastError(), "ghr_fp32_probe");
   return GHR_OK;
 }
 

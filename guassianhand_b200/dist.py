@@ -72,9 +72,9 @@ class PackedGrads:
 
 def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
                    group=None, sh_degree: int = 0, scale_modifier: float = 1.0,
-                   R_cap: Optional[int] = None, check: str = "poll"):
+                   R_cap: Optional[int] = None, check: str = "poll", fwd_events=None, bwd_events=None):
     """One camera-sharded step on this rank: forward + backward of the LOCAL views, gradients written
-    into `grads` (overwritten), then the all-reduce.  Returns (color [V,3,H,W], radii [V,P]).
+    into `grads` (overwritten), then the all-reduce.  Returns the api.ForwardResult (color, radii, state).
 
     gauss: dict with means3D, opacities, scales, rotations and colors_precomp or shs (CUDA fp32).
     views: guassianhand_b200.api.ViewBatch of the local shard.  dL_dout: [V,3,H,W]."""
@@ -86,8 +86,9 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
     shs = f32(gauss["shs"]) if gauss.get("shs") is not None else None
     col = f32(gauss["colors_precomp"]) if gauss.get("colors_precomp") is not None else None
     res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier, check=check,
-                          R_cap=R_cap)
+                          R_cap=R_cap, stage_events=fwd_events)
     api.backward_raw(cams, res.state, res.R_cap, dL_dout, means3D, opac, sc, rot, None, shs, col, sh_degree,
-                     scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False)
+                     scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False,
+                     stage_events=bwd_events)
     grads.all_reduce_(group)
-    return res.color, res.radii
+    return res

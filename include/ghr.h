@@ -41,7 +41,11 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 1
+#define GHR_ABI_VERSION 2
+
+/* stage ids for the optional stage_events arrays */
+#define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges, 5 blend */
+#define GHR_NSTAGES_BWD 2 /* 0 blend backward, 1 preprocess backward */
 
 /* Problem dimensions.  T = ceil(W/16)*ceil(H/16) tiles per view, N = H*W pixels per view. */
 typedef struct GhrDims {
@@ -111,6 +115,9 @@ typedef struct GhrForwardArgs {
    * blocking D2H read of num_rendered in upstream's forward without stalling the pipeline. */
   GhrStatus *host_status;
   uint64_t seq;
+  /* optional per-stage timing: HOST array of 2*GHR_NSTAGES_FWD cudaEvent_t (start,stop per stage,
+   * created with ghr_event_create), recorded on the stream around each stage; NULL = off. */
+  void **stage_events;
 } GhrForwardArgs;
 
 typedef struct GhrBackwardArgs {
@@ -136,6 +143,7 @@ typedef struct GhrBackwardArgs {
   float *dL_dscales;    /* [P,3] */
   float *dL_drotations; /* [P,4] */
   float *dL_dconic;     /* [V,P,4] optional debug export (xx, xy, 0, yy) */
+  void **stage_events;  /* HOST array of 2*GHR_NSTAGES_BWD cudaEvent_t or NULL */
 } GhrBackwardArgs;
 
 int ghr_abi_version(void);
@@ -156,6 +164,16 @@ int ghr_backward(const GhrBackwardArgs *args, void *cuda_stream);
 /* Replaces upstream mark_visible(): present[i] = (view-space z > 0.2). */
 int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *cuda_stream);
+
+/* Thin event helpers so a host without a CUDA binding can time stages (cudaEvent_t as void*). */
+int ghr_event_create(void **event_out);
+int ghr_event_destroy(void *event);
+int ghr_event_record(void *event, void *cuda_stream);
+int ghr_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both must have completed */
+
+/* FP32 roofline denominator: launches a dependent-FMA kernel (8 chains/thread) on `cuda_stream`;
+ * *flops_out = floating-point operations it executes.  Time it with events. `sink` = 4 device bytes. */
+int ghr_fp32_probe(int32_t iters, float *sink, double *flops_out, void *cuda_stream);
 
 /* Enqueue an async copy of GhrStatus from `state` into pinned host memory `host_status`. */
 int ghr_read_status_async(const void *state, GhrStatus *host_status, void *cuda_stream);

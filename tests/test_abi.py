@@ -18,7 +18,7 @@ def native():
 def _declared():
     src = open(os.path.join(ROOT, "include", "ghr.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ghr_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ghr_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported(native):

@@ -1,0 +1,128 @@
+"""The drop-in Python surface on the GPU, driven the way GuassianHand drives it
+(/root/reference/tgs/models/renderer_one_shot.py:259-382): zero `means2D` grad holder, keyword
+arguments, an RGB render and an all-ones mask render sharing the geometry, both differentiated."""
+import numpy as np
+import pytest
+import torch
+
+from guassianhand_b200 import scenes
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _settings(cam, bg, dev, sh_degree=0, debug=False):
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    # the reference hands over a NON-contiguous view for viewmatrix (w2c.transpose(0,1), :96)
+    view = t(cam.viewmatrix.T).transpose(0, 1)
+    return GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=t(bg),
+        scale_modifier=1.0, viewmatrix=view, projmatrix=t(cam.projmatrix), sh_degree=sh_degree,
+        campos=t(cam.campos), prefiltered=False, debug=debug)
+
+
+def test_reference_call_pattern_rgb_plus_mask(cuda_device):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = cuda_device
+    sc = scenes.two_hand_scene(4000, seed=9)
+    cam = scenes.fibonacci_cameras(2, 96, 80, seed=9)[1]
+    bg = np.array([0.2, 0.3, 0.4], np.float32)
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    xyz, opacity, scaling, rotation, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+    screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
+    screenspace_points.retain_grad()
+    rasterizer = GaussianRasterizer(raster_settings=_settings(cam, bg, dev))
+    with torch.autocast(device_type="cuda", dtype=torch.float32):
+        rendered_image, radii = rasterizer(means3D=xyz, means2D=screenspace_points, shs=None, colors_precomp=colors,
+                                           opacities=opacity, scales=scaling, rotations=rotation, cov3D_precomp=None)
+    mask_rasterizer = GaussianRasterizer(raster_settings=_settings(cam, np.zeros(3, np.float32), dev))
+    rendered_mask, radii2 = mask_rasterizer(means3D=xyz, means2D=screenspace_points,
+                                            colors_precomp=torch.ones_like(xyz), opacities=opacity, scales=scaling,
+                                            rotations=rotation, cov3D_precomp=None)
+    assert rendered_image.shape == (3, cam.H, cam.W) and radii.dtype == torch.int32 and radii.shape == (sc.P,)
+    assert torch.equal(radii, radii2)
+    rng = np.random.default_rng(0)
+    w_img = torch.from_numpy((rng.normal(size=(3, cam.H, cam.W)) / (cam.H * cam.W)).astype(np.float32)).to(dev)
+    w_msk = torch.from_numpy((rng.normal(size=(3, cam.H, cam.W)) / (cam.H * cam.W)).astype(np.float32)).to(dev)
+    loss = (rendered_image.permute(1, 2, 0) * w_img.permute(1, 2, 0)).sum() + (rendered_mask * w_msk).sum()
+    loss.backward()
+    # oracle: the two renders' gradients add
+    f1, g1 = util.run_oracle(sc, cam, bg, w_img.cpu().numpy())
+    ones = scenes.GaussianScene(**{**sc.__dict__})
+    ones.colors = np.ones_like(sc.colors)
+    f2, g2 = util.run_oracle(ones, cam, np.zeros(3, np.float32), w_msk.cpu().numpy())
+    assert np.array_equal(radii.cpu().numpy(), f1["radii"])
+    assert np.abs(rendered_image.detach().cpu().numpy() - f1["out_color"]).max() <= 1e-5
+    assert np.abs(rendered_mask.detach().cpu().numpy() - f2["out_color"]).max() <= 1e-5
+    tol = 1e-4
+    assert util.rel_err(xyz.grad.cpu().numpy(), g1["dL_dmeans3D"].astype(np.float64) + g2["dL_dmeans3D"]) <= tol
+    assert util.rel_err(opacity.grad.cpu().numpy().reshape(-1), g1["dL_dopacity"].astype(np.float64) + g2["dL_dopacity"]) <= tol
+    assert util.rel_err(scaling.grad.cpu().numpy(), g1["dL_dscales"].astype(np.float64) + g2["dL_dscales"]) <= tol
+    assert util.rel_err(rotation.grad.cpu().numpy(), g1["dL_drots"].astype(np.float64) + g2["dL_drots"]) <= tol
+    assert util.rel_err(colors.grad.cpu().numpy(), g1["dL_dcolors"]) <= tol
+    assert util.rel_err(screenspace_points.grad.cpu().numpy(),
+                        g1["dL_dmeans2D"].astype(np.float64) + g2["dL_dmeans2D"]) <= tol
+    assert (screenspace_points.grad[:, 2] == 0).all()
+
+
+def test_sh_path_and_mark_visible(cuda_device):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from oracle import oracle_lib as ol
+    dev = cuda_device
+    sc = scenes.random_scene(1200, seed=6, sh_degree=3)
+    cam = scenes.simple_camera(64, 64)
+    bg = np.zeros(3, np.float32)
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    xyz, opacity, scaling, rotation, shs = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.shs))
+    m2d = torch.zeros_like(xyz, requires_grad=True)
+    r = GaussianRasterizer(raster_settings=_settings(cam, bg, dev, sh_degree=3))
+    img, radii = r(means3D=xyz, means2D=m2d, shs=shs, opacities=opacity, scales=scaling, rotations=rotation)
+    w = torch.from_numpy(np.random.default_rng(1).normal(size=(3, 64, 64)).astype(np.float32) / 4096).to(dev)
+    (img * w).sum().backward()
+    f, g = util.run_oracle(sc, cam, bg, w.cpu().numpy())
+    assert util.rel_err(shs.grad.cpu().numpy(), g["dL_dsh"]) <= 1e-4
+    assert util.rel_err(xyz.grad.cpu().numpy(), g["dL_dmeans3D"]) <= 1e-4
+    vis = r.markVisible(xyz.detach())
+    assert vis.dtype == torch.bool
+    assert np.array_equal(vis.cpu().numpy(), ol.mark_visible(sc.means3D, cam.viewmatrix, cam.projmatrix))
+
+
+def test_argument_errors_match_upstream(cuda_device):
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = cuda_device
+    cam = scenes.simple_camera(32, 32)
+    r = GaussianRasterizer(raster_settings=_settings(cam, np.zeros(3, np.float32), dev))
+    x = torch.zeros(4, 3, device=dev)
+    o = torch.ones(4, 1, device=dev)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        r(means3D=x, means2D=x, opacities=o, scales=x, rotations=torch.zeros(4, 4, device=dev))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=x, means2D=x, opacities=o, colors_precomp=x)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        r(means3D=x.cpu(), means2D=x.cpu(), opacities=o.cpu(), colors_precomp=x.cpu(), scales=x.cpu(),
+          rotations=torch.zeros(4, 4))
+
+
+def test_batched_views_autograd_equals_view_loop(cuda_device):
+    from guassianhand_b200 import rasterize_views
+    dev = cuda_device
+    sc = scenes.two_hand_scene(3000, seed=4)
+    cams = scenes.fibonacci_cameras(4, 80, 96, seed=4)
+    bg = np.array([0.0, 0.1, 0.2], np.float32)
+    views = util.gpu_views(cams, bg, dev)
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    xyz, opacity, scaling, rotation, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+    imgs, radii = rasterize_views(xyz, opacity, views, colors_precomp=colors, scales=scaling, rotations=rotation)
+    w = torch.from_numpy((np.random.default_rng(2).normal(size=(4, 3, 80, 96)) / 7680).astype(np.float32)).to(dev)
+    (imgs * w).sum().backward()
+    tot = {}
+    for v, cam in enumerate(cams):
+        f, g = util.run_oracle(sc, cam, bg, w[v].cpu().numpy())
+        assert np.abs(imgs[v].detach().cpu().numpy() - f["out_color"]).max() <= 1e-5
+        assert np.array_equal(radii[v].cpu().numpy(), f["radii"])
+        for k, a in g.items():
+            tot[k] = tot.get(k, 0) + a.astype(np.float64)
+    assert util.rel_err(xyz.grad.cpu().numpy(), tot["dL_dmeans3D"]) <= 1e-4
+    assert util.rel_err(colors.grad.cpu().numpy(), tot["dL_dcolors"]) <= 1e-4
+    assert util.rel_err(rotation.grad.cpu().numpy(), tot["dL_drots"]) <= 1e-4

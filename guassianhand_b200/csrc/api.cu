@@ -49,7 +49,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   // ---- state ----
   size_t o = 0;
   L->pub.off_status = o;   o = align_up(o + sizeof(GhrStatus));
-  L->pub.off_geom = o;     o = align_up(o + VP * 48);
+  L->pub.off_geom = o;     o = align_up(o + VP * 64);
   L->pub.off_clamped = o;  o = align_up(o + (d.M > 0 ? VP : 0));
   L->pub.off_ranges = o;   o = align_up(o + VT * 8);
   L->pub.off_tilemax = o;  o = align_up(o + VT * 4);

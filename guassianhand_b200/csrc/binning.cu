@@ -72,12 +72,12 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
       uint32_t v = (uint32_t)(e / P);
       uint32_t id = order[e];
       uint32_t g = v * (uint32_t)P + id;
-      float4 q2 = geom[3 * (size_t)g + 2];
-      tt[k] = __float_as_uint(q2.w);
+      float4 q3 = geom[4 * (size_t)g + 3];
+      tt[k] = __float_as_uint(q3.y);
       if (tt[k]) {
-        float4 q0 = geom[3 * (size_t)g + 0];
+        float4 q0 = geom[4 * (size_t)g + 0];
         xy[k] = make_float2(q0.x, q0.y);
-        rad[k] = __float_as_int(q2.z);
+        rad[k] = __float_as_int(q3.x);
         gid[k] = g;
         nvis++;
       }
@@ -184,16 +184,16 @@ gather_ranges_kernel(int P, int T, uint64_t R_cap, const GhrStatus *__restrict__
   for (; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t tk = tkeys[r];
     uint32_t g = tvals[r];
-    float4 q0 = geom[3 * (size_t)g + 0];
-    float4 q1 = geom[3 * (size_t)g + 1];
-    float4 q2 = geom[3 * (size_t)g + 2];
+    float4 q0 = geom[4 * (size_t)g + 0];
+    float4 q1 = geom[4 * (size_t)g + 1];
+    float4 q2 = geom[4 * (size_t)g + 2];
     uint32_t id = g % (uint32_t)P;
     records[3 * r + 0] = q0;
     records[3 * r + 1] = q1;
-    records[3 * r + 2] = make_float4(q2.x, __uint_as_float(id), 0.f, 0.f);
+    records[3 * r + 2] = make_float4(q2.x, q2.y, q2.z, __uint_as_float(id));
     if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
     if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
-    if (dbg_keys) dbg_keys[r] = ((uint64_t)(tk % (uint32_t)T) << 32) | __float_as_uint(q2.y);
+    if (dbg_keys) dbg_keys[r] = ((uint64_t)(tk % (uint32_t)T) << 32) | __float_as_uint(q2.w);
     if (dbg_plist) dbg_plist[r] = id;
   }
 }

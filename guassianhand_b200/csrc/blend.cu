@@ -4,7 +4,9 @@
 // renderCUDA<3> backward (K7, A.6).  One CTA per (tile, view), one thread per pixel, a warp covers
 // an 8x4 pixel block.  The tile's instance list is a contiguous slab of 48-byte records (written
 // by gather_ranges), streamed into shared memory by 1-D bulk async copies (cp.async.bulk ->
-// UBLKCP) that complete on mbarriers, three stages deep, issued by one elected thread.
+// UBLKCP) that complete on mbarriers, three stages deep, issued by one elected thread.  Inside a
+// stage each warp first culls: lane l tests instance (base+l)'s conservative alpha>=1/255 box against
+// the warp's 8x4 pixel block, a ballot compacts the survivors, and only those are blended.
 // Backward: per-instance partial gradients are reduced across the warp with a reduce-scatter
 // butterfly (16 shuffles for 9 values) and leave the SM as one RED.ADD per value per warp.
 #include "ghr_internal.cuh"
@@ -73,6 +75,10 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint2 *__re
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
+  const int lane = tid & 31;
+  // pixel block of this warp (all lanes): x in [bx0,bx1], y in [by0,by1]
+  const float bx0 = (float)((tile % gx) * kTile + (((tid >> 5) & 1) << 3)), bx1 = bx0 + 7.f;
+  const float by0 = (float)((tile / gx) * kTile + ((tid >> 6) << 2)), by1 = by0 + 3.f;
 
   const uint2 range = ranges[(size_t)v * T + tile];
   const uint32_t n = range.y - range.x;
@@ -105,25 +111,40 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint2 *__re
     const uint32_t cnt = min((uint32_t)kBatch, n - r * kBatch);
     const float4 *rec = &sb.rec[s][0];
     if (!__all_sync(0xFFFFFFFFu, done)) {
-      for (uint32_t j = 0; j < cnt && !done; j++) {
-        float4 a = rec[3 * j], b = rec[3 * j + 1];
-        float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-        float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-        float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-        if (power > 0.0f) continue;
-        float alpha = fminf(0.99f, fmul(b.y, expf(power)));
-        if (alpha < kAlphaMin) continue;
-        float test_T = fmul(Tr, fsub(1.f, alpha));
-        if (test_T < 0.0001f) {
-          done = true;
-          continue;
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        // each lane tests ONE instance's cull box against this warp's 8x4 pixel block
+        const uint32_t e = base + lane;
+        bool hit = false;
+        if (e < cnt) {
+          const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * e]);
+          const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * e + 1].z);
+          hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
         }
-        float cb = rec[3 * j + 2].x;
-        C0 = ffma(fmul(b.z, alpha), Tr, C0);
-        C1 = ffma(fmul(b.w, alpha), Tr, C1);
-        C2 = ffma(fmul(cb, alpha), Tr, C2);
-        Tr = test_T;
-        last = r * kBatch + j + 1;
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+        while (mask) {
+          const uint32_t j = base + (uint32_t)__ffs(mask) - 1u;
+          mask &= mask - 1u;
+          if (done) continue;
+          float4 a = rec[3 * j], b = rec[3 * j + 1];
+          float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+          float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
+          float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
+          if (power > 0.0f) continue;
+          float alpha = fminf(0.99f, fmul(b.y, expf(power)));
+          if (alpha < kAlphaMin) continue;
+          float test_T = fmul(Tr, fsub(1.f, alpha));
+          if (test_T < 0.0001f) {
+            done = true;
+            continue;
+          }
+          float4 c = rec[3 * j + 2];
+          C0 = ffma(fmul(c.x, alpha), Tr, C0);
+          C1 = ffma(fmul(c.y, alpha), Tr, C1);
+          C2 = ffma(fmul(c.z, alpha), Tr, C2);
+          Tr = test_T;
+          last = r * kBatch + j + 1;
+        }
+        if (__all_sync(0xFFFFFFFFu, done)) break;
       }
     }
     int ndone = __syncthreads_count(done);
@@ -199,6 +220,8 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
+  const float bx0 = (float)((tile % gx) * kTile + (((tid >> 5) & 1) << 3)), bx1 = bx0 + 7.f;
+  const float by0 = (float)((tile / gx) * kTile + ((tid >> 6) << 2)), by1 = by0 + 3.f;
 
   const uint2 range = ranges[(size_t)v * T + tile];
   const uint32_t n = min(range.y - range.x, maxc);     // instances past the last contributor never matter
@@ -251,48 +274,60 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
     const uint32_t cnt = min((uint32_t)kBatch, n - rr * kBatch);
     const float4 *rec = &sb.rec[s][0];
     const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
-    for (int j = (int)cnt - 1; j >= 0; j--) {
-      const uint32_t e = rr * kBatch + (uint32_t)j;   // position in the tile list
-      if (e >= wlast) continue;                       // warp-uniform
-      float4 a = rec[3 * j], b = rec[3 * j + 1];
-      float vals[9];
+    for (int base = (int)((cnt - 1) & ~31u); base >= 0; base -= 32) {
+      const uint32_t el = (uint32_t)base + lane;          // index inside the stage
+      bool hit = false;
+      if (el < cnt && rr * kBatch + el < wlast) {
+        const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * el]);
+        const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * el + 1].z);
+        hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
+      }
+      uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+      while (mask) {
+        const int bit = 31 - __clz(mask);                 // back to front
+        mask &= ~(1u << bit);
+        const int j = base + bit;
+        const uint32_t e = rr * kBatch + (uint32_t)j;     // position in the tile list
+        float4 a = rec[3 * j], b = rec[3 * j + 1];
+        float vals[9];
 #pragma unroll
-      for (int t = 0; t < 9; t++) vals[t] = 0.f;
-      bool contrib = false;
-      if (e < last) {
-        float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-        float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-        float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-        if (power <= 0.0f) {
-          float G = expf(power);
-          float alpha = fminf(0.99f, fmul(b.y, G));
-          if (alpha >= kAlphaMin) {
-            contrib = true;
-            float cb = rec[3 * j + 2].x;
-            float rc = __frcp_rn(1.f - alpha);
-            Tr = Tr * rc;
-            float wgt = alpha * Tr;
-            acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-            acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-            acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-            lc0 = b.z; lc1 = b.w; lc2 = cb;
-            float dL_dalpha = (b.z - acc0) * dLp0 + (b.w - acc1) * dLp1 + (cb - acc2) * dLp2;
-            dL_dalpha *= Tr;
-            last_alpha = alpha;
-            dL_dalpha += (-T_final * rc) * bgdot;
-            float wG = G * dL_dalpha;
-            float m10 = wG * dx, m01 = wG * dy;
-            vals[0] = wgt * dLp0; vals[1] = wgt * dLp1; vals[2] = wgt * dLp2;
-            vals[3] = wG; vals[4] = m10; vals[5] = m01;
-            vals[6] = m10 * dx; vals[7] = m10 * dy; vals[8] = m01 * dy;
+        for (int t = 0; t < 9; t++) vals[t] = 0.f;
+        bool contrib = false;
+        if (e < last) {
+          float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+          float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
+          float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
+          if (power <= 0.0f) {
+            float G = expf(power);
+            float alpha = fminf(0.99f, fmul(b.y, G));
+            if (alpha >= kAlphaMin) {
+              contrib = true;
+              float4 c = rec[3 * j + 2];
+              float rc = __frcp_rn(1.f - alpha);
+              Tr = Tr * rc;
+              float wgt = alpha * Tr;
+              acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
+              acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
+              acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
+              lc0 = c.x; lc1 = c.y; lc2 = c.z;
+              float dL_dalpha = (c.x - acc0) * dLp0 + (c.y - acc1) * dLp1 + (c.z - acc2) * dLp2;
+              dL_dalpha *= Tr;
+              last_alpha = alpha;
+              dL_dalpha += (-T_final * rc) * bgdot;
+              float wG = G * dL_dalpha;
+              float m10 = wG * dx, m01 = wG * dy;
+              vals[0] = wgt * dLp0; vals[1] = wgt * dLp1; vals[2] = wgt * dLp2;
+              vals[3] = wG; vals[4] = m10; vals[5] = m01;
+              vals[6] = m10 * dx; vals[7] = m10 * dy; vals[8] = m01 * dy;
+            }
           }
         }
-      }
-      if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
-      float tot = warp_reduce_scatter9(vals, lane);
-      if (owner) {
-        uint32_t id = __float_as_uint(rec[3 * j + 2].y);
-        atomicAdd(accv + (size_t)id * kAccStride, tot);
+        if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
+        float tot = warp_reduce_scatter9(vals, lane);
+        if (owner) {
+          uint32_t id = __float_as_uint(rec[3 * j + 2].w);
+          atomicAdd(accv + (size_t)id * kAccStride, tot);
+        }
       }
     }
     __syncthreads();

@@ -1,8 +1,7 @@
 // Per-(view, Gaussian) preprocess: frustum cull, 3D covariance, EWA projection to the 2D conic,
 // radius / tile rectangle, SH colour, depth key + digit histograms for the depth sort.
 // Replaces upstream preprocessCUDA<3> -- one thread per
-// (view, Gaussian), view-independent inputs are read once per thread; output is one 48-byte
-// record (3 x STG.128) instead of seven scattered arrays.
+// (view, Gaussian); output is one 64-byte record (4 x STG.128) instead of seven scattered arrays.
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -110,7 +109,8 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     float px = g.means3D[3 * i], py = g.means3D[3 * i + 1], pz = g.means3D[3 * i + 2];
     int radius = 0;
     uint32_t tiles = 0;
-    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0;
+    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+    q1.z = -1.f; q1.w = -1.f;   // empty cull box
     uint32_t cbits = 0;
 
     float pvx = dot3a(Vm[0], px, Vm[4], py, Vm[8], pz, Vm[12]);
@@ -188,18 +188,35 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
           radius = rad;
           tiles = (uint32_t)tt;
           key = __float_as_uint(pvz);
+          // Conservative half-extents of the region where alpha >= 1/255 can hold (blend kernels use
+          // them for warp-level culling only; never part of the canonical arithmetic):
+          // alpha = o*exp(power) >= 1/255  =>  d^T Q d <= 2 ln(255 o), bbox = sqrt(2 tau Q^-1_ii).
+          const float opac = g.opacities[i];
+          float wxh = -1.f, wyh = -1.f;
+          if (opac >= 0.0039f) {
+            float tau = fmaxf(logf(255.f * opac), 0.f) + 1e-3f;
+            float detq = conx * conz - cony * cony;
+            if (detq > 0.f && detq > 1e-3f * conx * conz) {
+              wxh = sqrtf(2.f * tau * conz / detq) * 1.002f + 0.05f;
+              wyh = sqrtf(2.f * tau * conx / detq) * 1.002f + 0.05f;
+            } else {
+              wxh = wyh = 1e30f;   // ill-conditioned conic: never cull
+            }
+          }
           q0 = make_float4(pix_x, pix_y, conx, cony);
-          q1 = make_float4(conz, g.opacities[i], rgb[0], rgb[1]);
-          q2 = make_float4(rgb[2], pvz, __int_as_float(rad), __uint_as_float(tiles));
+          q1 = make_float4(conz, opac, wxh, wyh);
+          q2 = make_float4(rgb[0], rgb[1], rgb[2], pvz);
+          q3 = make_float4(__int_as_float(rad), __uint_as_float(tiles), 0.f, 0.f);
         }
       }
     } else if (flags & GHR_FLAG_PREFILTERED) {
       // upstream traps here ("Point is filtered although prefiltered is set"); we only cull.
     }
     size_t e = (size_t)v * P + i;
-    geom[3 * e + 0] = q0;
-    geom[3 * e + 1] = q1;
-    geom[3 * e + 2] = q2;
+    geom[4 * e + 0] = q0;
+    geom[4 * e + 1] = q1;
+    geom[4 * e + 2] = q2;
+    geom[4 * e + 3] = q3;
     if (clamped) clamped[e] = (uint8_t)cbits;
     radii[e] = radius;
     depth_keys[e] = key;

@@ -65,12 +65,12 @@ preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale
 
   for (int v = 0; v < V; v++) {
     const size_t e = (size_t)v * P + i;
-    const float4 q2 = geom[3 * e + 2];
-    const int radius = __float_as_int(q2.z);
+    const float4 q3 = geom[4 * e + 3];
+    const int radius = __float_as_int(q3.x);
     float g2x = 0.f, g2y = 0.f, gA = 0.f, gB = 0.f, gC = 0.f;
     if (radius > 0) {
-      const float4 q0 = geom[3 * e + 0];
-      const float4 q1 = geom[3 * e + 1];
+      const float4 q0 = geom[4 * e + 0];
+      const float4 q1 = geom[4 * e + 1];
       const float *a = acc + e * kAccStride;
       const float4 a0 = *reinterpret_cast<const float4 *>(a);
       const float4 a1 = *reinterpret_cast<const float4 *>(a + 4);

@@ -39,12 +39,12 @@ def test_abi_version_and_struct_sizes(native):
 def test_layout_is_pure_host_logic(native):
     lay = native.layout(60000, 1, 512, 334, 0, 0, 1 << 20)
     assert lay.off_status == 0 and lay.off_geom >= 32
-    assert lay.off_records - lay.off_geom >= 60000 * 48
+    assert lay.off_records - lay.off_geom >= 60000 * 64
     assert lay.state_bytes >= lay.off_ncontrib + 512 * 334 * 4
     assert lay.temp_bwd_bytes >= 60000 * 12 * 4
     # multi-view scales the per-view parts
     lay4 = native.layout(60000, 4, 512, 334, 0, 0, 1 << 20)
-    assert lay4.off_ranges - lay4.off_geom >= 4 * 60000 * 48
+    assert lay4.off_ranges - lay4.off_geom >= 4 * 60000 * 64
 
 
 def test_bad_dims_are_rejected_with_message(native):

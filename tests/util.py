@@ -60,7 +60,7 @@ def run_gpu(scene, cams, bg, dL=None, scale_modifier=1.0, cov3D=None, R_cap=None
     gx, gy = (W + 15) // 16, (H + 15) // 16
     T = gx * gy
     st = res.state.cpu().numpy()
-    geom = st[lay.off_geom: lay.off_geom + V * P * 48].view(np.float32).reshape(V, P, 12)
+    geom = st[lay.off_geom: lay.off_geom + V * P * 64].view(np.float32).reshape(V, P, 16)
     ranges = st[lay.off_ranges: lay.off_ranges + V * T * 8].view(np.uint32).reshape(V, T, 2)
     final_T = st[lay.off_final_T: lay.off_final_T + V * H * W * 4].view(np.float32).reshape(V, H, W)
     ncontrib = st[lay.off_ncontrib: lay.off_ncontrib + V * H * W * 4].view(np.uint32).reshape(V, H, W)
@@ -78,9 +78,9 @@ def run_gpu(scene, cams, bg, dL=None, scale_modifier=1.0, cov3D=None, R_cap=None
         nz = rv[:, 1] > 0
         rv[nz] -= s0                       # per-view offsets, as a single-view upstream call has
         out.append(dict(
-            depths=geom[v, :, 9].copy(), radii=radii[v], xy=geom[v, :, 0:2].copy(),
-            conic_opacity=geom[v][:, [2, 3, 4, 5]].copy(), rgb=geom[v][:, [6, 7, 8]].copy(),
-            tiles_touched=geom[v, :, 11].copy().view(np.uint32), keys=keys[s0:e0], point_list=plist[s0:e0],
+            depths=geom[v, :, 11].copy(), radii=radii[v], xy=geom[v, :, 0:2].copy(),
+            conic_opacity=geom[v][:, [2, 3, 4, 5]].copy(), rgb=geom[v][:, [8, 9, 10]].copy(),
+            tiles_touched=geom[v, :, 13].copy().view(np.uint32), keys=keys[s0:e0], point_list=plist[s0:e0],
             ranges=rv.astype(np.uint32), out_color=color[v], final_T=final_T[v], n_contrib=ncontrib[v], R=e0 - s0))
     grads = None
     if dL is not None:

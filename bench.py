@@ -216,7 +216,7 @@ def run_ours(args):
     R_cap = int(max(Rs) * 1.25) + (1 << 14)
     lay = NV.layout(P, B, H, W, 0, 0, R_cap)
     npt = (max(1, int(np.ceil(np.log2(max(B * T, 2))))) + 7) // 8
-    launches_per_step = 1 + 1 + 4 + 1 + npt + 1 + 1 + 2       # init, preprocess, 4 depth passes, scan, tile passes, gather, blend | 2 bwd
+    launches_per_step = 1 + 1 + 4 + 1 + npt + 1 + 1 + 1 + 2       # init, preprocess, 4 depth passes, scan, tile passes, gather, schedule, blend | 2 bwd
 
     status_pin = torch.zeros(K + Wm, 4, dtype=torch.int64).pin_memory()
 

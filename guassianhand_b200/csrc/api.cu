@@ -56,6 +56,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->pub.off_records = o;  o = align_up(o + (size_t)d.R_cap * kRecBytes);
   L->pub.off_final_T = o;  o = align_up(o + VN * 4);
   L->pub.off_ncontrib = o; o = align_up(o + VN * 4);
+  L->pub.off_order = o;    o = align_up(o + VT * 4);
   L->pub.state_bytes = o;
 
   // ---- temp (forward): zeroed prefix first ----
@@ -218,6 +219,7 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
       tm.stop(4);
     }
   }
+  GHR_TRY(launch_tile_schedule(d, L, state, s), "ghr_forward: tile schedule");
   tm.start(5);
   if (a->host_status && d.P == 0)
     GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),

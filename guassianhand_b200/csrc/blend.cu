@@ -1,23 +1,30 @@
 // Per-tile alpha blending, forward and backward.
 //
 // Forward replaces upstream renderCUDA<3> forward; backward replaces
-// renderCUDA<3> backward (K7, A.6).  One CTA per (tile, view), one thread per pixel, a warp covers
-// an 8x4 pixel block.  The tile's instance list is a contiguous slab of 48-byte records (written
-// by gather_ranges), streamed into shared memory by 1-D bulk async copies (cp.async.bulk ->
-// UBLKCP) that complete on mbarriers, three stages deep, issued by one elected thread.  Inside a
-// stage each warp first culls: lane l tests instance (base+l)'s conservative alpha>=1/255 box against
-// the warp's 8x4 pixel block, a ballot compacts the survivors, and only those are blended.
-// Backward: per-instance partial gradients are reduced across the warp with a reduce-scatter
-// butterfly (16 shuffles for 9 values) and leave the SM as one RED.ADD per value per warp.
+// renderCUDA<3> backward (K7, A.6).  One CTA per (view, tile), taken heaviest-first from the tile
+// schedule.  8 consumer warps (one thread per pixel, a warp covers an 8x4 pixel block) + 1 producer
+// warp.  The tile's instance list is a contiguous slab of 48-byte records (written by
+// gather_ranges); the producer streams it into a ring of shared-memory stages with 1-D bulk async
+// copies (cp.async.bulk -> UBLKCP) completing on "full" mbarriers; consumer warps release a stage on
+// its "empty" mbarrier, so warps drift apart by up to kStages-1 stages instead of meeting at a CTA
+// barrier every round.  Inside a stage each warp first culls: lane l tests instance (base+l)'s
+// conservative alpha>=1/255 box against the warp's pixel block, a ballot compacts the survivors,
+// and only those are blended.  Backward: per-instance partial gradients are reduced across the warp
+// with a reduce-scatter butterfly (16 shuffles for 9 values) and leave the SM as one RED.ADD per
+// value per warp.
 #include "ghr_internal.cuh"
 
 namespace ghr {
 
 namespace {
 
-constexpr int kBatch = 256;   // instances per stage
-constexpr int kStages = 3;
+constexpr int kStageN = 128;  // instances per stage (6 KB)
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr int kIlpF = 4;      // forward: instances blended per inner iteration
+constexpr int kIlpB = 2;      // backward
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -29,6 +36,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -50,9 +60,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 struct __align__(128) StageBuf {
-  float4 rec[kStages][kBatch * 3];
-  uint64_t bar[kStages];
+  float4 rec[kStages][kStageN * 3];
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint32_t done_warps;
+  uint32_t stop_round;
 };
+
+__device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&sb.full[s], 1);
+      mbar_init(&sb.empty[s], kConsumerWarps);
+    }
+    sb.done_warps = 0;
+    sb.stop_round = 0xFFFFFFFFu;
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
 
 // thread -> pixel inside the tile: warp w covers the 8x4 block (w&1, w>>1)
 __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
@@ -61,58 +87,67 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
   ly = ((w >> 1) << 2) + (l >> 3);
 }
 
-__global__ void __launch_bounds__(256)
-blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint2 *__restrict__ ranges,
-                     const float4 *__restrict__ records, float *__restrict__ final_T,
-                     uint32_t *__restrict__ n_contrib, uint32_t *__restrict__ tilemax,
-                     float *__restrict__ out_color) {
+__global__ void __launch_bounds__(kBlendThreads)
+blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
+                     const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
+                     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+                     uint32_t *__restrict__ tilemax, float *__restrict__ out_color) {
   __shared__ StageBuf sb;
-  const int tile = blockIdx.x, v = blockIdx.y;
-  const int tid = threadIdx.x;
+  const uint32_t vt = order[blockIdx.x];
+  const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const uint2 range = ranges[vt];
+  const uint32_t n = range.y - range.x;
+  const uint32_t rounds = (n + kStageN - 1) / kStageN;
+  const float4 *src = records + 3 * (size_t)range.x;
+  stage_init(sb, tid);
+
+  if (warp == kConsumerWarps) {
+    // ---------------- producer ----------------
+    if (lane == 0) {
+      for (uint32_t r = 0; r < rounds; r++) {
+        const int s = r % kStages;
+        if (r >= kStages) mbar_wait(&sb.empty[s], ((r / kStages) - 1) & 1);
+        if (*(volatile uint32_t *)&sb.done_warps == kConsumerWarps) {
+          // every pixel of the tile has terminated: complete the phase without data ("poison")
+          *(volatile uint32_t *)&sb.stop_round = r;
+          mbar_arrive(&sb.full[s]);
+          break;
+        }
+        const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
+        mbar_expect_tx(&sb.full[s], cnt * kRecBytes);
+        bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)r * kStageN, cnt * kRecBytes, &sb.full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
   int lx, ly;
   pixel_of_thread(tid, lx, ly);
   const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  const int lane = tid & 31;
-  // pixel block of this warp (all lanes): x in [bx0,bx1], y in [by0,by1]
-  const float bx0 = (float)((tile % gx) * kTile + (((tid >> 5) & 1) << 3)), bx1 = bx0 + 7.f;
-  const float by0 = (float)((tile / gx) * kTile + ((tid >> 6) << 2)), by1 = by0 + 3.f;
-
-  const uint2 range = ranges[(size_t)v * T + tile];
-  const uint32_t n = range.y - range.x;
-  const uint32_t rounds = (n + kBatch - 1) / kBatch;
-  const float4 *src = records + 3 * (size_t)range.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; s++) mbar_init(&sb.bar[s], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  uint32_t issued = 0;
-  auto issue = [&](uint32_t r) {
-    uint32_t cnt = min((uint32_t)kBatch, n - r * kBatch);
-    uint32_t bytes = cnt * kRecBytes;
-    int s = r % kStages;
-    mbar_expect_tx(&sb.bar[s], bytes);
-    bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)r * kBatch, bytes, &sb.bar[s]);
-  };
-  if (tid == 0)
-    for (; issued < rounds && issued < kStages; issued++) issue(issued);
+  // pixel block of this warp: x in [bx0,bx1], y in [by0,by1]
+  const float bx0 = (float)((tile % gx) * kTile + ((warp & 1) << 3)), bx1 = bx0 + 7.f;
+  const float by0 = (float)((tile / gx) * kTile + ((warp >> 1) << 2)), by1 = by0 + 3.f;
 
   bool done = !inside;
+  bool wdone = __all_sync(0xFFFFFFFFu, done);
+  if (wdone && lane == 0) atomicAdd(&sb.done_warps, 1u);
   float Tr = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t last = 0;
-  uint32_t r = 0;
-  for (; r < rounds; r++) {
+  for (uint32_t r = 0; r < rounds; r++) {
     const int s = r % kStages;
-    mbar_wait(&sb.bar[s], (r / kStages) & 1);
-    const uint32_t cnt = min((uint32_t)kBatch, n - r * kBatch);
-    const float4 *rec = &sb.rec[s][0];
-    if (!__all_sync(0xFFFFFFFFu, done)) {
+    mbar_wait(&sb.full[s], (r / kStages) & 1);
+    if (r >= *(volatile uint32_t *)&sb.stop_round) break;
+    if (!wdone) {
+      const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
+      const float4 *rec = &sb.rec[s][0];
       for (uint32_t base = 0; base < cnt; base += 32) {
-        // each lane tests ONE instance's cull box against this warp's 8x4 pixel block
+        // each lane tests ONE instance's cull box against this warp's pixel block
         const uint32_t e = base + lane;
         bool hit = false;
         if (e < cnt) {
@@ -122,38 +157,50 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint2 *__re
         }
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
         while (mask) {
-          const uint32_t j = base + (uint32_t)__ffs(mask) - 1u;
-          mask &= mask - 1u;
-          if (done) continue;
-          float4 a = rec[3 * j], b = rec[3 * j + 1];
-          float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-          float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-          float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-          if (power > 0.0f) continue;
-          float alpha = fminf(0.99f, fmul(b.y, expf(power)));
-          if (alpha < kAlphaMin) continue;
-          float test_T = fmul(Tr, fsub(1.f, alpha));
-          if (test_T < 0.0001f) {
-            done = true;
-            continue;
+          // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
+          // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
+          // short T / colour update is serial.
+          uint32_t jj[kIlpF];
+          float al[kIlpF];
+          float4 col[kIlpF];
+#pragma unroll
+          for (int k = 0; k < kIlpF; k++) {
+            const bool ok = mask != 0;
+            jj[k] = ok ? base + (uint32_t)__ffs(mask) - 1u : jj[0];
+            mask &= mask - 1u;                      // 0 stays 0
+            float4 a = rec[3 * jj[k]], b = rec[3 * jj[k] + 1];
+            col[k] = rec[3 * jj[k] + 2];
+            float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+            float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
+            float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
+            float alpha = fminf(0.99f, fmul(b.y, expf(power)));
+            al[k] = (ok && power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;
           }
-          float4 c = rec[3 * j + 2];
-          C0 = ffma(fmul(c.x, alpha), Tr, C0);
-          C1 = ffma(fmul(c.y, alpha), Tr, C1);
-          C2 = ffma(fmul(c.z, alpha), Tr, C2);
-          Tr = test_T;
-          last = r * kBatch + j + 1;
+#pragma unroll
+          for (int k = 0; k < kIlpF; k++) {
+            if (done || al[k] == 0.f) continue;
+            float test_T = fmul(Tr, fsub(1.f, al[k]));
+            if (test_T < 0.0001f) {
+              done = true;
+              continue;
+            }
+            C0 = ffma(fmul(col[k].x, al[k]), Tr, C0);
+            C1 = ffma(fmul(col[k].y, al[k]), Tr, C1);
+            C2 = ffma(fmul(col[k].z, al[k]), Tr, C2);
+            Tr = test_T;
+            last = r * kStageN + jj[k] + 1;
+          }
         }
-        if (__all_sync(0xFFFFFFFFu, done)) break;
+        if (__all_sync(0xFFFFFFFFu, done)) {
+          wdone = true;
+          if (lane == 0) atomicAdd(&sb.done_warps, 1u);
+          break;
+        }
       }
     }
-    int ndone = __syncthreads_count(done);
-    if (ndone == 256) { r++; break; }
-    if (tid == 0 && issued < rounds) { issue(issued); issued++; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sb.empty[s]);
   }
-  // never leave the CTA with bulk copies in flight into its shared memory
-  if (tid == 0)
-    for (uint32_t q = r; q < issued; q++) mbar_wait(&sb.bar[q % kStages], (q / kStages) & 1);
 
   if (inside) {
     const float *bg = cam.bg + (size_t)cam.bg_stride * v;
@@ -166,7 +213,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint2 *__re
     o[2 * N] = ffma(Tr, bg[2], C2);
   }
   uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
-  if ((tid & 31) == 0 && wmax) atomicMax(&tilemax[(size_t)v * T + tile], wmax);
+  if (lane == 0 && wmax) atomicMax(&tilemax[vt], wmax);
 }
 
 // Reduce-scatter butterfly over the warp for 9 values held in v[0..8]; on return lane L with
@@ -204,47 +251,48 @@ __device__ __forceinline__ float warp_reduce_scatter9(const float (&v)[9], int l
   return f;
 }
 
-__global__ void __launch_bounds__(256)
-blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uint2 *__restrict__ ranges,
-                      const float4 *__restrict__ records, const float *__restrict__ final_T,
-                      const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tilemax,
-                      const float *__restrict__ dL_dout, float *__restrict__ acc) {
+__global__ void __launch_bounds__(kBlendThreads)
+blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uint32_t *__restrict__ order,
+                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
+                      const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+                      const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
+                      float *__restrict__ acc) {
   __shared__ StageBuf sb;
-  const int tile = blockIdx.x, v = blockIdx.y;
-  const uint32_t maxc = tilemax[(size_t)v * T + tile];
+  const uint32_t vt = order[blockIdx.x];
+  const uint32_t maxc = tilemax[vt];
   if (maxc == 0) return;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  const uint2 range = ranges[vt];
+  const uint32_t n = min(range.y - range.x, maxc);     // instances past the last contributor never matter
+  const uint32_t rounds = (n + kStageN - 1) / kStageN;
+  const float4 *src = records + 3 * (size_t)range.x;
+  stage_init(sb, tid);
+
+  if (warp == kConsumerWarps) {
+    // producer: step k streams round (rounds-1-k), back to front
+    if (lane == 0) {
+      for (uint32_t k = 0; k < rounds; k++) {
+        const int s = k % kStages;
+        if (k >= kStages) mbar_wait(&sb.empty[s], ((k / kStages) - 1) & 1);
+        const uint32_t rr = rounds - 1 - k;
+        const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
+        mbar_expect_tx(&sb.full[s], cnt * kRecBytes);
+        bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)rr * kStageN, cnt * kRecBytes, &sb.full[s]);
+      }
+    }
+    return;
+  }
+
   int lx, ly;
   pixel_of_thread(tid, lx, ly);
   const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  const float bx0 = (float)((tile % gx) * kTile + (((tid >> 5) & 1) << 3)), bx1 = bx0 + 7.f;
-  const float by0 = (float)((tile / gx) * kTile + ((tid >> 6) << 2)), by1 = by0 + 3.f;
-
-  const uint2 range = ranges[(size_t)v * T + tile];
-  const uint32_t n = min(range.y - range.x, maxc);     // instances past the last contributor never matter
-  const uint32_t rounds = (n + kBatch - 1) / kBatch;
-  const float4 *src = records + 3 * (size_t)range.x;
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; s++) mbar_init(&sb.bar[s], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  // rounds are consumed back to front: step k handles round (rounds-1-k)
-  uint32_t issued = 0;
-  auto issue = [&](uint32_t k) {
-    uint32_t rr = rounds - 1 - k;
-    uint32_t cnt = min((uint32_t)kBatch, n - rr * kBatch);
-    uint32_t bytes = cnt * kRecBytes;
-    int s = k % kStages;
-    mbar_expect_tx(&sb.bar[s], bytes);
-    bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)rr * kBatch, bytes, &sb.bar[s]);
-  };
-  if (tid == 0)
-    for (; issued < rounds && issued < kStages; issued++) issue(issued);
+  const float bx0 = (float)((tile % gx) * kTile + ((warp & 1) << 3)), bx1 = bx0 + 7.f;
+  const float by0 = (float)((tile / gx) * kTile + ((warp >> 1) << 2)), by1 = by0 + 3.f;
 
   float T_final = 0.f, dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
   uint32_t last = 0;
@@ -266,82 +314,133 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
   const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
   const bool owner = ((lane & 1) == 0) && slot < 9;
   float *accv = acc + (size_t)v * P * kAccStride + slot;
+  const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
 
   for (uint32_t k = 0; k < rounds; k++) {
     const int s = k % kStages;
-    mbar_wait(&sb.bar[s], (k / kStages) & 1);
+    mbar_wait(&sb.full[s], (k / kStages) & 1);
     const uint32_t rr = rounds - 1 - k;
-    const uint32_t cnt = min((uint32_t)kBatch, n - rr * kBatch);
-    const float4 *rec = &sb.rec[s][0];
-    const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
-    for (int base = (int)((cnt - 1) & ~31u); base >= 0; base -= 32) {
-      const uint32_t el = (uint32_t)base + lane;          // index inside the stage
-      bool hit = false;
-      if (el < cnt && rr * kBatch + el < wlast) {
-        const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * el]);
-        const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * el + 1].z);
-        hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
-      }
-      uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
-      while (mask) {
-        const int bit = 31 - __clz(mask);                 // back to front
-        mask &= ~(1u << bit);
-        const int j = base + bit;
-        const uint32_t e = rr * kBatch + (uint32_t)j;     // position in the tile list
-        float4 a = rec[3 * j], b = rec[3 * j + 1];
-        float vals[9];
+    if (rr * kStageN < wlast) {
+      const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
+      const float4 *rec = &sb.rec[s][0];
+      for (int base = (int)((cnt - 1) & ~31u); base >= 0; base -= 32) {
+        const uint32_t el = (uint32_t)base + lane;          // index inside the stage
+        bool hit = false;
+        if (el < cnt && rr * kStageN + el < wlast) {
+          const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * el]);
+          const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * el + 1].z);
+          hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
+        }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
+        while (mask) {
+          // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets
+          int jj[kIlpB];
+          float al[kIlpB], Gk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB];
+          float4 col[kIlpB];
 #pragma unroll
-        for (int t = 0; t < 9; t++) vals[t] = 0.f;
-        bool contrib = false;
-        if (e < last) {
-          float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-          float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-          float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-          if (power <= 0.0f) {
+          for (int k = 0; k < kIlpB; k++) {
+            const bool ok = mask != 0;
+            const int bit = ok ? 31 - __clz(mask) : 0;          // back to front
+            mask &= ~(1u << bit) & (ok ? 0xFFFFFFFFu : 0u);
+            jj[k] = ok ? base + bit : jj[0];
+            const uint32_t e = rr * kStageN + (uint32_t)jj[k];  // position in the tile list
+            float4 a = rec[3 * jj[k]], b = rec[3 * jj[k] + 1];
+            col[k] = rec[3 * jj[k] + 2];
+            float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+            float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
+            float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
             float G = expf(power);
             float alpha = fminf(0.99f, fmul(b.y, G));
-            if (alpha >= kAlphaMin) {
-              contrib = true;
-              float4 c = rec[3 * j + 2];
-              float rc = __frcp_rn(1.f - alpha);
-              Tr = Tr * rc;
+            const bool c = ok && e < last && power <= 0.0f && alpha >= kAlphaMin;
+            al[k] = c ? alpha : 0.f;
+            Gk[k] = G;
+            rck[k] = __frcp_rn(1.f - alpha);
+            dxk[k] = dx;
+            dyk[k] = dy;
+          }
+          // phase 2 (serial, short): transmittance / suffix-colour recursion -> 9 partials each
+          float vals[kIlpB][9];
+          bool contrib[kIlpB];
+#pragma unroll
+          for (int k = 0; k < kIlpB; k++) {
+#pragma unroll
+            for (int t = 0; t < 9; t++) vals[k][t] = 0.f;
+            contrib[k] = al[k] != 0.f;
+            if (contrib[k]) {
+              const float alpha = al[k];
+              Tr = Tr * rck[k];
               float wgt = alpha * Tr;
               acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
               acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
               acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-              lc0 = c.x; lc1 = c.y; lc2 = c.z;
-              float dL_dalpha = (c.x - acc0) * dLp0 + (c.y - acc1) * dLp1 + (c.z - acc2) * dLp2;
+              lc0 = col[k].x; lc1 = col[k].y; lc2 = col[k].z;
+              float dL_dalpha = (lc0 - acc0) * dLp0 + (lc1 - acc1) * dLp1 + (lc2 - acc2) * dLp2;
               dL_dalpha *= Tr;
               last_alpha = alpha;
-              dL_dalpha += (-T_final * rc) * bgdot;
-              float wG = G * dL_dalpha;
-              float m10 = wG * dx, m01 = wG * dy;
-              vals[0] = wgt * dLp0; vals[1] = wgt * dLp1; vals[2] = wgt * dLp2;
-              vals[3] = wG; vals[4] = m10; vals[5] = m01;
-              vals[6] = m10 * dx; vals[7] = m10 * dy; vals[8] = m01 * dy;
+              dL_dalpha += (-T_final * rck[k]) * bgdot;
+              float wG = Gk[k] * dL_dalpha;
+              float m10 = wG * dxk[k], m01 = wG * dyk[k];
+              vals[k][0] = wgt * dLp0; vals[k][1] = wgt * dLp1; vals[k][2] = wgt * dLp2;
+              vals[k][3] = wG; vals[k][4] = m10; vals[k][5] = m01;
+              vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
             }
           }
-        }
-        if (!__any_sync(0xFFFFFFFFu, contrib)) continue;
-        float tot = warp_reduce_scatter9(vals, lane);
-        if (owner) {
-          uint32_t id = __float_as_uint(rec[3 * j + 2].w);
-          atomicAdd(accv + (size_t)id * kAccStride, tot);
+          // phase 3 (independent): warp reduce-scatter + one RED per value
+#pragma unroll
+          for (int k = 0; k < kIlpB; k++) {
+            if (!__any_sync(0xFFFFFFFFu, contrib[k])) continue;
+            float tot = warp_reduce_scatter9(vals[k], lane);
+            if (owner) atomicAdd(accv + (size_t)__float_as_uint(col[k].w) * kAccStride, tot);
+          }
         }
       }
     }
-    __syncthreads();
-    if (tid == 0 && issued < rounds) { issue(issued); issued++; }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sb.empty[s]);
+  }
+}
+
+// Heaviest-first tile schedule: a counting sort of the V*T (view, tile) ids by the class
+// floor(log2(list length)) in descending order (single CTA; V*T is a few thousand).
+__global__ void __launch_bounds__(1024)
+tile_schedule_kernel(int VT, const uint2 *__restrict__ ranges, uint32_t *__restrict__ order) {
+  __shared__ uint32_t cnt[34], cur[34];
+  const int tid = threadIdx.x;
+  if (tid < 34) cnt[tid] = 0;
+  __syncthreads();
+  auto cls = [](uint2 r) -> int {
+    uint32_t n = r.y - r.x;
+    return n == 0 ? 33 : __clz(n);   // fewer leading zeros = longer list = earlier; 33 = empty tile
+  };
+  for (int t = tid; t < VT; t += blockDim.x) atomicAdd(&cnt[cls(ranges[t])], 1u);
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t sum = 0;
+    for (int c = 0; c < 34; c++) { cur[c] = sum; sum += cnt[c]; }
+  }
+  __syncthreads();
+  for (int t = tid; t < VT; t += blockDim.x) {
+    uint32_t pos = atomicAdd(&cur[cls(ranges[t])], 1u);
+    order[pos] = (uint32_t)t;
   }
 }
 
 }  // namespace
 
+cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s) {
+  int VT = d.V * L.T;
+  if (VT == 0) return cudaSuccess;
+  tile_schedule_kernel<<<1, 1024, 0, s>>>(VT, (const uint2 *)(state + L.pub.off_ranges),
+                                          (uint32_t *)(state + L.pub.off_order));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
                                  float *out_color, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
-  dim3 grid(L.T, d.V), block(256);
-  blend_forward_kernel<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint2 *)(state + L.pub.off_ranges),
+  dim3 grid(L.T * d.V), block(kBlendThreads);
+  blend_forward_kernel<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
+                                              (const uint2 *)(state + L.pub.off_ranges),
                                               (const float4 *)(state + L.pub.off_records),
                                               (float *)(state + L.pub.off_final_T),
                                               (uint32_t *)(state + L.pub.off_ncontrib),
@@ -352,11 +451,12 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
                                   const float *dL_dout, float *acc, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
-  dim3 grid(L.T, d.V), block(256);
+  dim3 grid(L.T * d.V), block(kBlendThreads);
   blend_backward_kernel<<<grid, block, 0, s>>>(
-      d.H, d.W, L.gx, L.T, d.P, cam, (const uint2 *)(state + L.pub.off_ranges),
-      (const float4 *)(state + L.pub.off_records), (const float *)(state + L.pub.off_final_T),
-      (const uint32_t *)(state + L.pub.off_ncontrib), (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, acc);
+      d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
+      (const uint2 *)(state + L.pub.off_ranges), (const float4 *)(state + L.pub.off_records),
+      (const float *)(state + L.pub.off_final_T), (const uint32_t *)(state + L.pub.off_ncontrib),
+      (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, acc);
   return cudaGetLastError();
 }
 

@@ -70,6 +70,7 @@ cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s);
 cudaError_t launch_tile_sort(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
 cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state, char *temp,
                                  uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s);
+cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s);
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
                                  float *out_color, cudaStream_t s);
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,

@@ -18,23 +18,30 @@ __constant__ float SHB_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.457
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;
 
+// A.2 step 3 in the canonical order (same bits as preprocess.cu), also returning R and s
 __device__ __forceinline__ void cov3d_of(const float *sc, float mod, float4 q, float *c3, float (*R)[3], float *s) {
-  s[0] = mod * sc[0]; s[1] = mod * sc[1]; s[2] = mod * sc[2];
+  s[0] = fmul(mod, sc[0]); s[1] = fmul(mod, sc[1]); s[2] = fmul(mod, sc[2]);
   float r = q.x, x = q.y, y = q.z, z = q.w;
-  R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
-  R[1][0] = 2.f * (x * y + r * z); R[1][1] = 1.f - 2.f * (x * x + z * z); R[1][2] = 2.f * (y * z - r * x);
-  R[2][0] = 2.f * (x * z - r * y); R[2][1] = 2.f * (y * z + r * x); R[2][2] = 1.f - 2.f * (x * x + y * y);
+  R[0][0] = ffma(-2.f, ffma(y, y, fmul(z, z)), 1.f);
+  R[0][1] = fmul(2.f, ffma(x, y, -fmul(r, z)));
+  R[0][2] = fmul(2.f, ffma(x, z, fmul(r, y)));
+  R[1][0] = fmul(2.f, ffma(x, y, fmul(r, z)));
+  R[1][1] = ffma(-2.f, ffma(x, x, fmul(z, z)), 1.f);
+  R[1][2] = fmul(2.f, ffma(y, z, -fmul(r, x)));
+  R[2][0] = fmul(2.f, ffma(x, z, -fmul(r, y)));
+  R[2][1] = fmul(2.f, ffma(y, z, fmul(r, x)));
+  R[2][2] = ffma(-2.f, ffma(x, x, fmul(y, y)), 1.f);
   float A[3][3];
 #pragma unroll
   for (int a = 0; a < 3; a++)
 #pragma unroll
-    for (int k = 0; k < 3; k++) A[a][k] = R[a][k] * s[k];
-  c3[0] = A[0][0] * A[0][0] + A[0][1] * A[0][1] + A[0][2] * A[0][2];
-  c3[1] = A[0][0] * A[1][0] + A[0][1] * A[1][1] + A[0][2] * A[1][2];
-  c3[2] = A[0][0] * A[2][0] + A[0][1] * A[2][1] + A[0][2] * A[2][2];
-  c3[3] = A[1][0] * A[1][0] + A[1][1] * A[1][1] + A[1][2] * A[1][2];
-  c3[4] = A[1][0] * A[2][0] + A[1][1] * A[2][1] + A[1][2] * A[2][2];
-  c3[5] = A[2][0] * A[2][0] + A[2][1] * A[2][1] + A[2][2] * A[2][2];
+    for (int k = 0; k < 3; k++) A[a][k] = fmul(R[a][k], s[k]);
+  c3[0] = dot3(A[0][0], A[0][0], A[0][1], A[0][1], A[0][2], A[0][2]);
+  c3[1] = dot3(A[0][0], A[1][0], A[0][1], A[1][1], A[0][2], A[1][2]);
+  c3[2] = dot3(A[0][0], A[2][0], A[0][1], A[2][1], A[0][2], A[2][2]);
+  c3[3] = dot3(A[1][0], A[1][0], A[1][1], A[1][1], A[1][2], A[1][2]);
+  c3[4] = dot3(A[1][0], A[2][0], A[1][1], A[2][1], A[1][2], A[2][2]);
+  c3[5] = dot3(A[2][0], A[2][0], A[2][1], A[2][1], A[2][2], A[2][2]);
 }
 
 template <bool HAS_SH>
@@ -90,35 +97,39 @@ preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale
       const float tanfovx = cam.tanfov ? cam.tanfov[2 * v] : cam.tanfovx;
       const float tanfovy = cam.tanfov ? cam.tanfov[2 * v + 1] : cam.tanfovy;
       // ---- A.7 ----
-      float tvx = Vm[0] * px + Vm[4] * py + Vm[8] * pz + Vm[12];
-      float tvy = Vm[1] * px + Vm[5] * py + Vm[9] * pz + Vm[13];
-      float tvz = Vm[2] * px + Vm[6] * py + Vm[10] * pz + Vm[14];
-      const float fx = (float)W / (2.0f * tanfovx), fy = (float)H / (2.0f * tanfovy);
-      const float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
-      const float txtz = tvx / tvz, tytz = tvy / tvz;
-      const float tx = fminf(limx, fmaxf(-limx, txtz)) * tvz;
-      const float ty = fminf(limy, fmaxf(-limy, tytz)) * tvz;
+      // recompute the forward quantities in the canonical order (bit-identical to preprocess.cu):
+      // denom = a*c - b*b cancels catastrophically for anisotropic splats, so its rounding must
+      // be the forward's, not whatever contraction the compiler picks here
+      const float tvx = dot3a(Vm[0], px, Vm[4], py, Vm[8], pz, Vm[12]);
+      const float tvy = dot3a(Vm[1], px, Vm[5], py, Vm[9], pz, Vm[13]);
+      const float tvz = dot3a(Vm[2], px, Vm[6], py, Vm[10], pz, Vm[14]);
+      const float fx = fdiv((float)W, fmul(2.0f, tanfovx)), fy = fdiv((float)H, fmul(2.0f, tanfovy));
+      const float limx = fmul(1.3f, tanfovx), limy = fmul(1.3f, tanfovy);
+      const float txtz = fdiv(tvx, tvz), tytz = fdiv(tvy, tvz);
+      const float tx = fmul(fminf(limx, fmaxf(-limx, txtz)), tvz);
+      const float ty = fmul(fminf(limy, fmaxf(-limy, tytz)), tvz);
       const float gxm = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
       const float gym = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
       const float itz = 1.f / tvz, itz2 = itz * itz, itz3 = itz2 * itz;
-      const float J00 = fx * itz, J02 = -fx * tx * itz2, J11 = fy * itz, J12 = -fy * ty * itz2;
+      const float J00 = fdiv(fx, tvz), J02 = fdiv(-fmul(fx, tx), fmul(tvz, tvz));
+      const float J11 = fdiv(fy, tvz), J12 = fdiv(-fmul(fy, ty), fmul(tvz, tvz));
       float T0[3], T1[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        T0[c] = J00 * Vm[4 * c + 0] + J02 * Vm[4 * c + 2];
-        T1[c] = J11 * Vm[4 * c + 1] + J12 * Vm[4 * c + 2];
+        T0[c] = dot2(J00, Vm[4 * c + 0], J02, Vm[4 * c + 2]);
+        T1[c] = dot2(J11, Vm[4 * c + 1], J12, Vm[4 * c + 2]);
       }
       const float S[3][3] = {{c3[0], c3[1], c3[2]}, {c3[1], c3[3], c3[4]}, {c3[2], c3[4], c3[5]}};
       float u0[3], u1[3];
 #pragma unroll
       for (int r = 0; r < 3; r++) {
-        u0[r] = S[r][0] * T0[0] + S[r][1] * T0[1] + S[r][2] * T0[2];
-        u1[r] = S[r][0] * T1[0] + S[r][1] * T1[1] + S[r][2] * T1[2];
+        u0[r] = dot3(S[r][0], T0[0], S[r][1], T0[1], S[r][2], T0[2]);
+        u1[r] = dot3(S[r][0], T1[0], S[r][1], T1[1], S[r][2], T1[2]);
       }
-      const float ca = T0[0] * u0[0] + T0[1] * u0[1] + T0[2] * u0[2] + 0.3f;
-      const float cb = T0[0] * u1[0] + T0[1] * u1[1] + T0[2] * u1[2];
-      const float cc = T1[0] * u1[0] + T1[1] * u1[1] + T1[2] * u1[2] + 0.3f;
-      const float denom = ca * cc - cb * cb;
+      const float ca = fadd(dot3(T0[0], u0[0], T0[1], u0[1], T0[2], u0[2]), 0.3f);
+      const float cb = dot3(T0[0], u1[0], T0[1], u1[1], T0[2], u1[2]);
+      const float cc = fadd(dot3(T1[0], u1[0], T1[1], u1[1], T1[2], u1[2]), 0.3f);
+      const float denom = ffma(ca, cc, -fmul(cb, cb));
       const float d2i = 1.0f / (denom * denom + 0.0000001f);
       if (d2i != 0.f) {
         const float dL_da = d2i * (-cc * cc * gA + 2.f * cb * cc * gB + (denom - ca * cc) * gC);

@@ -41,10 +41,10 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 2
+#define GHR_ABI_VERSION 3
 
 /* stage ids for the optional stage_events arrays */
-#define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges, 5 blend */
+#define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges+schedule, 5 blend */
 #define GHR_NSTAGES_BWD 2 /* 0 blend backward, 1 preprocess backward */
 
 /* Problem dimensions.  T = ceil(W/16)*ceil(H/16) tiles per view, N = H*W pixels per view. */
@@ -72,6 +72,7 @@ typedef struct GhrLayout {
                           {x,y,conic.x,conic.y} {conic.z,opacity,wx,wy} {r,g,b,id(uint bits)} */
   size_t off_final_T;  /* float per (view, pixel) */
   size_t off_ncontrib; /* uint32 per (view, pixel) */
+  size_t off_order;    /* uint32 per (view, tile): blend launch order, longest instance list first */
 } GhrLayout;
 
 typedef struct GhrStatus {

@@ -581,7 +581,7 @@ GSO_EXPORT int gso_backward(const gso_in *in, const gso_fwd *f, const float *dL_
     float a, b, c;
     cov2d_ctx cx;
     cov2d(V, in->tanfovx, in->tanfovy, W, H, pvx, pvy, pvz, c3, &a, &b, &c, &cx);
-    float denom = a * c - b * b;
+    float denom = fmaf(a, c, -(b * b));   /* same rounding as the forward's det */
     float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
     float dmx = 0.f, dmy = 0.f, dmz = 0.f;
     float dc3[6] = {0, 0, 0, 0, 0, 0};

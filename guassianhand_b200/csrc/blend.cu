@@ -46,16 +46,19 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware (no issue slots burnt
+// by a spin loop while other warps of the SM are blending), retried until the phase completes.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
+    if (!ok) __nanosleep(64);
   } while (!ok);
 }
 

@@ -168,7 +168,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from guassianhand_b200 import _native as NV, api, scenes
-    from guassianhand_b200.dist import PackedGrads, fit_step_grads
+    from guassianhand_b200.dist import GraphedFitStep, PackedGrads, fit_step_grads
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import util
 
@@ -235,17 +235,35 @@ def run_ours(args):
         step(i)
     sync_all()
 
-    fwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_FWD) for _ in range(K)]
-    bwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_BWD) for _ in range(K)]
+    # ---- timed region: K steps.  Default: the step is replayed from a CUDA graph (one launch per
+    # step); the cameras of the step's view group are copied into the graph's static buffers inside
+    # the timed region.  --no-graph launches the same kernels eagerly. ----
     ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stream = torch.cuda.current_stream()
+    gstep = None
+    if not args.no_graph:
+        static_views = util.gpu_views(group_cams(0), bg, dev)
+        gstep = GraphedFitStep(gauss, static_views, dL, grads, R_cap=R_cap)
+
+        def run_step(i):
+            vg = view_groups[i % n_groups]
+            static_views.viewmatrix.copy_(vg.viewmatrix)
+            static_views.projmatrix.copy_(vg.projmatrix)
+            static_views.campos.copy_(vg.campos)
+            static_views.tanfov.copy_(vg.tanfov)
+            return gstep.replay()
+    else:
+        def run_step(i):
+            return step(i)
+    for i in range(Wm):
+        run_step(i)
     sync_all()
     with ClockSampler(local) as clk:
         for i in range(K):
             flush.zero_()                                   # L2 flush, outside the timed events
             ev_s[i].record()
-            res = step(i, fwd_ev[i], bwd_ev[i])
+            res = run_step(i)
             ev_e[i].record()
             NV.check(NV.lib().ghr_read_status_async(res.state.data_ptr(), status_pin[i].data_ptr(),
                                                     stream.cuda_stream), "status")
@@ -258,6 +276,15 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms_max = float(tmax.item())
     value = world * B * K / (total_ms_max / 1000.0)
+
+    # ---- per-stage durations: the same K steps again, launched eagerly with the library's
+    # per-stage CUDA events (events cannot be timed from inside a replayed graph) ----
+    fwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_FWD) for _ in range(K)]
+    bwd_ev = [NV.StageEvents(NV.GHR_NSTAGES_BWD) for _ in range(K)]
+    for i in range(K):
+        flush.zero_()
+        step(i, fwd_ev[i], bwd_ev[i])
+    sync_all()
 
     stage_ms = {}
     for si, name in enumerate(NV.FWD_STAGES):
@@ -285,6 +312,20 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     single_ms = s1.elapsed_time(e1) / n1
+    single_graph_ms = None
+    if not args.no_graph and world == 1:
+        g1 = GraphedFitStep(gauss, v1, dL1, grads, R_cap=cap1)
+        for _ in range(5):
+            g1.replay()
+        torch.cuda.synchronize()
+        s1.record()
+        for _ in range(n1):
+            g1.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        single_graph_ms = s1.elapsed_time(e1) / n1
+        if g1.status()[1]:
+            raise RuntimeError("bench: overflow in the single-view graph")
 
     # ---- FP32 peak probe (dependent FMA chains) ----
     import ctypes as C
@@ -371,6 +412,7 @@ def run_ours(args):
             "config": {"workload": _workload(B), "views_per_rank_per_step": B, "gaussians": P, "image": [H, W],
                        "instances_per_step": R_mean, "blend_pairs_per_step": I_mean, "R_cap": R_cap,
                        "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"camera-sharded dp{world}",
+                       "launch": "eager" if args.no_graph else "CUDA graph replay (1 launch/step) + 4 camera copies",
                        "collective": "none (N=1)" if world == 1 else "NCCL all-reduce of packed grads (56 B x P)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                          "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
@@ -383,7 +425,10 @@ def run_ours(args):
                                      "frac": f / (stage_ms[k] * 1e-3) / 1e12 / fp32_peak}
                                  for k, f in blend_flops.items()}},
             "stage_ms": stage_ms,
-            "single_view": {"ms_per_view": single_ms, "views_per_s": 1000.0 / single_ms},
+            "single_view": {"ms_per_view_eager": single_ms, "views_per_s_eager": 1000.0 / single_ms,
+                            "ms_per_view_graph": single_graph_ms,
+                            "views_per_s_graph": (1000.0 / single_graph_ms) if single_graph_ms else None,
+                            "note": "1 view per call (the shape the reference runs), L2 warm"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "guassianhand_b200.rasterize_views + autograd, pinned host buffers, wall clock"},
             "gpu_launches": launches_per_step * K,
@@ -408,6 +453,7 @@ def main():
     ap.add_argument("--views", type=int, default=8, help="views per rank per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -92,3 +92,43 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
                      stage_events=bwd_events)
     grads.all_reduce_(group)
     return res
+
+
+class GraphedFitStep:
+    """The camera-sharded step (forward + backward [+ all-reduce]) captured once into a CUDA graph
+    and replayed: ~16 kernel launches, 2 memsets and the NCCL call become one graph launch, which is
+    what makes the single-view (latency-bound) case GPU-bound instead of host-bound.
+
+    All inputs are static device buffers: write new Gaussian attributes / cameras / dL_dout into
+    `gauss`, `views` tensors and `dL_dout` (in place) before `replay()`.  Capacity is fixed
+    (`R_cap`); check `status()` for overflow when the scene changes a lot."""
+
+    def __init__(self, gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
+                 R_cap: int, group=None, sh_degree: int = 0, scale_modifier: float = 1.0, warmup: int = 2):
+        self.gauss, self.views, self.dL_dout, self.grads, self.R_cap = gauss, views, dL_dout, grads, int(R_cap)
+        kw = dict(group=group, sh_degree=sh_degree, scale_modifier=scale_modifier, R_cap=self.R_cap, check="none")
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                fit_step_grads(gauss, views, dL_dout, grads, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fit_step_grads(gauss, views, dL_dout, grads, **kw)
+        self._pin = torch.zeros(4, dtype=torch.int64).pin_memory()
+
+    def replay(self):
+        self.graph.replay()
+        return self.result
+
+    def status(self):
+        """(R, overflow) of the last replay; synchronises the current stream."""
+        from . import _native as N
+        s = torch.cuda.current_stream()
+        N.check(N.lib().ghr_read_status_async(self.result.state.data_ptr(), self._pin.data_ptr(), s.cuda_stream),
+                "ghr_read_status_async")
+        s.synchronize()
+        return int(self._pin[0]), int(self._pin[1]) & 0xFFFFFFFF

@@ -83,6 +83,21 @@ __device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
   __syncthreads();
 }
 
+// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (ex2.approx: <= 2 ulp; argument rounding adds <= 3.3e-7
+// relative at |x| <= 5.6, the largest exponent that can still pass alpha >= 1/255).  libdevice expf
+// costs 9 more issue slots per pair in kernels that are issue-bound.  Forward and backward use the
+// same function, so every alpha / skip decision of the backward replays the forward's exactly.
+__device__ __forceinline__ float exp_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // thread -> pixel inside the tile: warp w covers the 8x4 block (w&1, w>>1)
 __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
   int w = tid >> 5, l = tid & 31;
@@ -176,7 +191,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
             float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
             float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
             float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-            float alpha = fminf(0.99f, fmul(b.y, expf(power)));
+            float alpha = fminf(0.99f, fmul(b.y, exp_fast(power)));
             al[k] = (ok && power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;
           }
 #pragma unroll
@@ -352,12 +367,12 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
             float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
             float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
             float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-            float G = expf(power);
+            float G = exp_fast(power);
             float alpha = fminf(0.99f, fmul(b.y, G));
             const bool c = ok && e < last && power <= 0.0f && alpha >= kAlphaMin;
             al[k] = c ? alpha : 0.f;
             Gk[k] = G;
-            rck[k] = __frcp_rn(1.f - alpha);
+            rck[k] = rcp_fast(1.f - alpha);
             dxk[k] = dx;
             dyk[k] = dy;
           }

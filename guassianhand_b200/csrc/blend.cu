@@ -10,8 +10,8 @@
 // barrier every round.  Inside a stage each warp first culls: lane l tests instance (base+l)'s
 // conservative alpha>=1/255 box against the warp's pixel block, a ballot compacts the survivors,
 // and only those are blended.  Backward: per-instance partial gradients are reduced across the warp
-// with a reduce-scatter butterfly (16 shuffles for 9 values) and leave the SM as one RED.ADD per
-// value per warp.
+// through a conflict-free shared-memory transpose (36 issue slots for 9 values) and leave the SM as
+// one RED.ADD per value per warp.
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -98,6 +98,21 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return y;
 }
 
+// Exact box-constrained minimum of q(d) = A dx^2 + 2 B dx dy + C dy^2 over the pixel block
+// [bx0,bx1] x [by0,by1] (d = pixel - centre) against the instance's threshold.  The minimiser of a
+// convex quadratic over a box is the centre itself (q = 0) or lies on an edge facing the centre; the
+// two candidates below cover every case.  Returns true if the instance may contribute to the block.
+__device__ __forceinline__ bool cull_hit(const float4 a, const float4 b, float bx0, float bx1, float by0, float by1) {
+  const float A = a.z, B = a.w, C = b.x, thr = b.z;
+  const float u0 = bx0 - a.x, u1 = bx1 - a.x, v0 = by0 - a.y, v1 = by1 - a.y;
+  const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
+  const float v_e = fminf(fmaxf(-B * uc * rcp_fast(C), v0), v1);   // best v on the edge u = uc
+  const float u_e = fminf(fmaxf(-B * vc * rcp_fast(A), u0), u1);   // best u on the edge v = vc
+  const float q1 = A * uc * uc + 2.f * B * uc * v_e + C * v_e * v_e;
+  const float q2 = A * u_e * u_e + 2.f * B * u_e * vc + C * vc * vc;
+  return !(fminf(q1, q2) > thr);   // NaN-safe: anything unordered counts as a hit
+}
+
 // thread -> pixel inside the tile: warp w covers the 8x4 block (w&1, w>>1)
 __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
   int w = tid >> 5, l = tid & 31;
@@ -168,11 +183,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         // each lane tests ONE instance's cull box against this warp's pixel block
         const uint32_t e = base + lane;
         bool hit = false;
-        if (e < cnt) {
-          const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * e]);
-          const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * e + 1].z);
-          hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
-        }
+        if (e < cnt) hit = cull_hit(rec[3 * e], rec[3 * e + 1], bx0, bx1, by0, by1);
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
         while (mask) {
           // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
@@ -234,39 +245,30 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
   if (lane == 0 && wmax) atomicMax(&tilemax[vt], wmax);
 }
 
-// Reduce-scatter butterfly over the warp for 9 values held in v[0..8]; on return lane L with
-// (L & 1) == 0 and slot(L) < 9 holds the warp total of value slot(L) in the return value,
-// slot(L) = ((L>>4)&1)*8 + ((L>>3)&1)*4 + ((L>>2)&1)*2 + ((L>>1)&1).
-__device__ __forceinline__ float warp_reduce_scatter9(const float (&v)[9], int lane) {
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-  float a[8];
-  // 16 -> 8 : lower half keeps v[0..7], upper half keeps v[8..15] (v[9..15] = 0)
+// Warp reduction of 9 values per lane through shared memory: lane L stores its 9 partials as row L
+// of a 32x9 tile (stride 9 is odd: conflict-free), then lane (g,c) = (L/9, L%9), L < 27, sums column
+// c over 12 (8 for g=2) rows and the three row groups are combined with two shuffles.  36 issue slots
+// per instance instead of 62 for a register reduce-scatter butterfly (16 SHFL + 16 FADD + 30 FSEL) or
+// 90 for five plain xor steps.  On return lanes 0..8 hold the warp totals of values 0..8.
+__device__ __forceinline__ void warp_store9(float *buf, const float (&v)[9], int lane) {
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    float mine_hi = (k == 0) ? v[8] : 0.f;
-    float send = b4 ? v[k] : mine_hi;
-    float recv = __shfl_xor_sync(0xFFFFFFFFu, send, 16);
-    a[k] = (b4 ? mine_hi : v[k]) + recv;
-  }
-  float c[4];
+  for (int t = 0; t < 9; t++) buf[lane * 9 + t] = v[t];
+}
+__device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
+  const int g = lane / 9, c = lane - 9 * g;
+  float sum = 0.f;
+  if (lane < 27) {
+    const float *col = buf + (g * 12) * 9 + c;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    float send = b3 ? a[k] : a[k + 4];
-    float recv = __shfl_xor_sync(0xFFFFFFFFu, send, 8);
-    c[k] = (b3 ? a[k + 4] : a[k]) + recv;
-  }
-  float e[2];
+    for (int i = 0; i < 8; i++) sum += col[i * 9];
+    if (g < 2) {
 #pragma unroll
-  for (int k = 0; k < 2; k++) {
-    float send = b2 ? c[k] : c[k + 2];
-    float recv = __shfl_xor_sync(0xFFFFFFFFu, send, 4);
-    e[k] = (b2 ? c[k + 2] : c[k]) + recv;
+      for (int i = 8; i < 12; i++) sum += col[i * 9];
+    }
   }
-  float send = b1 ? e[0] : e[1];
-  float recv = __shfl_xor_sync(0xFFFFFFFFu, send, 2);
-  float f = (b1 ? e[1] : e[0]) + recv;
-  f += __shfl_xor_sync(0xFFFFFFFFu, f, 1);
-  return f;
+  const float s1 = __shfl_down_sync(0xFFFFFFFFu, sum, 9);
+  const float s2 = __shfl_down_sync(0xFFFFFFFFu, sum, 18);
+  return sum + s1 + s2;
 }
 
 __global__ void __launch_bounds__(kBlendThreads)
@@ -276,6 +278,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
                       const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
                       float *__restrict__ acc) {
   __shared__ StageBuf sb;
+  __shared__ float s_red[kConsumerWarps][kIlpB][32 * 9];
   const uint32_t vt = order[blockIdx.x];
   const uint32_t maxc = tilemax[vt];
   if (maxc == 0) return;
@@ -328,10 +331,9 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
   float Tr = T_final;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
 
-  // which slot of the butterfly this lane ends up owning
-  const int slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  const bool owner = ((lane & 1) == 0) && slot < 9;
-  float *accv = acc + (size_t)v * P * kAccStride + slot;
+  // lanes 0..8 own the warp totals of the 9 accumulated values
+  const bool owner = lane < 9;
+  float *accv = acc + (size_t)v * P * kAccStride + lane;
   const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
 
   for (uint32_t k = 0; k < rounds; k++) {
@@ -344,11 +346,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
       for (int base = (int)((cnt - 1) & ~31u); base >= 0; base -= 32) {
         const uint32_t el = (uint32_t)base + lane;          // index inside the stage
         bool hit = false;
-        if (el < cnt && rr * kStageN + el < wlast) {
-          const float2 c = *reinterpret_cast<const float2 *>(&rec[3 * el]);
-          const float2 w = *reinterpret_cast<const float2 *>(&rec[3 * el + 1].z);
-          hit = (c.x + w.x >= bx0) && (c.x - w.x <= bx1) && (c.y + w.y >= by0) && (c.y - w.y <= by1);
-        }
+        if (el < cnt && rr * kStageN + el < wlast) hit = cull_hit(rec[3 * el], rec[3 * el + 1], bx0, bx1, by0, by1);
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
         while (mask) {
           // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets
@@ -403,13 +401,21 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
               vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
             }
           }
-          // phase 3 (independent): warp reduce-scatter + one RED per value
+          // phase 3 (independent): warp reduction through shared memory + one RED per value
+          bool any[kIlpB];
 #pragma unroll
           for (int k = 0; k < kIlpB; k++) {
-            if (!__any_sync(0xFFFFFFFFu, contrib[k])) continue;
-            float tot = warp_reduce_scatter9(vals[k], lane);
+            any[k] = __any_sync(0xFFFFFFFFu, contrib[k]);
+            if (any[k]) warp_store9(&s_red[warp][k][0], vals[k], lane);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < kIlpB; k++) {
+            if (!any[k]) continue;
+            float tot = warp_colsum9(&s_red[warp][k][0], lane);
             if (owner) atomicAdd(accv + (size_t)__float_as_uint(col[k].w) * kAccStride, tot);
           }
+          __syncwarp();
         }
       }
     }

@@ -110,7 +110,7 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     int radius = 0;
     uint32_t tiles = 0;
     float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
-    q1.z = -1.f; q1.w = -1.f;   // empty cull box
+    q1.z = -1.f;   // cull threshold: never contributes
     uint32_t cbits = 0;
 
     float pvx = dot3a(Vm[0], px, Vm[4], py, Vm[8], pz, Vm[12]);
@@ -188,23 +188,19 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
           radius = rad;
           tiles = (uint32_t)tt;
           key = __float_as_uint(pvz);
-          // Conservative half-extents of the region where alpha >= 1/255 can hold (blend kernels use
-          // them for warp-level culling only; never part of the canonical arithmetic):
-          // alpha = o*exp(power) >= 1/255  =>  d^T Q d <= 2 ln(255 o), bbox = sqrt(2 tau Q^-1_ii).
+          // Cull threshold for the blend kernels (never part of the canonical arithmetic):
+          // alpha = o*exp(power) >= 1/255  =>  d^T Q d <= 2 ln(255 o) =: thr.  A warp skips the
+          // instance when the minimum of d^T Q d over its pixel block exceeds thr (with margin).
+          // thr < 0: can never contribute; thr = 3e38: ill-conditioned conic, never cull.
           const float opac = g.opacities[i];
-          float wxh = -1.f, wyh = -1.f;
+          float thr = -1.f;
           if (opac >= 0.0039f) {
             float tau = fmaxf(logf(255.f * opac), 0.f) + 1e-3f;
             float detq = conx * conz - cony * cony;
-            if (detq > 0.f && detq > 1e-3f * conx * conz) {
-              wxh = sqrtf(2.f * tau * conz / detq) * 1.002f + 0.05f;
-              wyh = sqrtf(2.f * tau * conx / detq) * 1.002f + 0.05f;
-            } else {
-              wxh = wyh = 1e30f;   // ill-conditioned conic: never cull
-            }
+            thr = (conx > 0.f && conz > 0.f && detq > 1e-3f * conx * conz) ? 2.f * tau * 1.01f + 0.02f : 3e38f;
           }
           q0 = make_float4(pix_x, pix_y, conx, cony);
-          q1 = make_float4(conz, opac, wxh, wyh);
+          q1 = make_float4(conz, opac, thr, 0.f);
           q2 = make_float4(rgb[0], rgb[1], rgb[2], pvz);
           q3 = make_float4(__int_as_float(rad), __uint_as_float(tiles), 0.f, 0.f);
         }

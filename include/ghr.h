@@ -62,14 +62,14 @@ typedef struct GhrDims {
 typedef struct GhrLayout {
   size_t state_bytes, temp_bytes, temp_bwd_bytes;
   size_t off_status;   /* GhrStatus */
-  size_t off_geom;     /* float4[4] per (view, Gaussian): {x,y,conic.x,conic.y} {conic.z,opacity,wx,wy}
-                          {r,g,b,depth} {radius(int bits), tiles_touched(uint bits),0,0}; (wx,wy) =
-                          conservative half-extents of the alpha>=1/255 region (culling only) */
+  size_t off_geom;     /* float4[4] per (view, Gaussian): {x,y,conic.x,conic.y} {conic.z,opacity,thr,0}
+                          {r,g,b,depth} {radius(int bits), tiles_touched(uint bits),0,0}; thr = 2 ln(255
+                          opacity) + margin: bound on d^T Q d for alpha >= 1/255 (culling only) */
   size_t off_clamped;  /* uint8 per (view, Gaussian): bit c set if SH colour channel c was clamped */
   size_t off_ranges;   /* uint32[2] per (view, tile): [start,end) into the sorted instances */
   size_t off_tilemax;  /* uint32 per (view, tile): max n_contrib in the tile */
   size_t off_records;  /* 48-byte instance records in sorted order:
-                          {x,y,conic.x,conic.y} {conic.z,opacity,wx,wy} {r,g,b,id(uint bits)} */
+                          {x,y,conic.x,conic.y} {conic.z,opacity,thr,0} {r,g,b,id(uint bits)} */
   size_t off_final_T;  /* float per (view, pixel) */
   size_t off_ncontrib; /* uint32 per (view, pixel) */
   size_t off_order;    /* uint32 per (view, tile): blend launch order, longest instance list first */

@@ -40,7 +40,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->tile_bits = bits;
   L->npt = (bits + 7) / 8;
   L->items_d = (VP > (1u << 21)) ? 16 : 4;
-  L->items_t = ((uint64_t)d.R_cap > (1u << 22)) ? 16 : 4;
+  L->items_t = ((uint64_t)d.R_cap > (1u << 19)) ? 16 : 4;
   L->nblk_d = (int)((d.P + (uint64_t)kSortThreads * L->items_d - 1) / ((uint64_t)kSortThreads * L->items_d));
   L->nblk_t = (int)(((uint64_t)d.R_cap + (uint64_t)kSortThreads * L->items_t - 1) /
                     ((uint64_t)kSortThreads * L->items_t));

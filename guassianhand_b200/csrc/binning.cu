@@ -172,29 +172,33 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
   }
 }
 
-// One thread per sorted instance.
-__global__ void __launch_bounds__(256)
+// Three threads per sorted instance (one per float4 of the 48-byte record): consecutive lanes read
+// consecutive 16-byte chunks of a geometry record (one request per record instead of three) and
+// write consecutive 16-byte chunks of the sorted slab (fully coalesced 128-bit stores).
+__global__ void __launch_bounds__(384)
 gather_ranges_kernel(int P, int T, uint64_t R_cap, const GhrStatus *__restrict__ status,
                      const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tvals,
                      const float4 *__restrict__ geom, float4 *__restrict__ records, uint2 *__restrict__ ranges,
                      uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
   uint64_t R = status->R;
   if (R > R_cap) R = R_cap;
-  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t tk = tkeys[r];
-    uint32_t g = tvals[r];
-    float4 q0 = geom[4 * (size_t)g + 0];
-    float4 q1 = geom[4 * (size_t)g + 1];
-    float4 q2 = geom[4 * (size_t)g + 2];
-    uint32_t id = g % (uint32_t)P;
-    records[3 * r + 0] = q0;
-    records[3 * r + 1] = q1;
-    records[3 * r + 2] = make_float4(q2.x, q2.y, q2.z, __uint_as_float(id));
-    if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
-    if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
-    if (dbg_keys) dbg_keys[r] = ((uint64_t)(tk % (uint32_t)T) << 32) | __float_as_uint(q2.w);
-    if (dbg_plist) dbg_plist[r] = id;
+  const uint32_t part = threadIdx.x % 3u;
+  uint64_t r = (uint64_t)blockIdx.x * (blockDim.x / 3) + threadIdx.x / 3u;
+  for (; r < R; r += (uint64_t)gridDim.x * (blockDim.x / 3)) {
+    const uint32_t g = tvals[r];
+    float4 q = geom[4 * (size_t)g + part];
+    const uint32_t id = g % (uint32_t)P;
+    if (part == 2) {
+      if (dbg_keys) dbg_keys[r] = ((uint64_t)(tkeys[r] % (uint32_t)T) << 32) | __float_as_uint(q.w);
+      q.w = __uint_as_float(id);
+    }
+    records[3 * r + part] = q;
+    if (part == 0) {
+      const uint32_t tk = tkeys[r];
+      if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
+      if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
+      if (dbg_plist) dbg_plist[r] = id;
+    }
   }
 }
 
@@ -224,9 +228,9 @@ cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state,
                                  uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s) {
   if (d.R_cap <= 0) return cudaSuccess;
   int buf = tile_sorted_buf(L);
-  uint64_t want = ((uint64_t)d.R_cap + 255) / 256;
+  uint64_t want = ((uint64_t)d.R_cap + 127) / 128;
   int nb = (int)(want < (uint64_t)(148 * 16) ? want : (uint64_t)(148 * 16));
-  gather_ranges_kernel<<<nb, 256, 0, s>>>(d.P, L.T, (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
+  gather_ranges_kernel<<<nb, 384, 0, s>>>(d.P, L.T, (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
                                           (const uint32_t *)(temp + L.t_tkeys[buf]),
                                           (const uint32_t *)(temp + L.t_tvals[buf]),
                                           (const float4 *)(state + L.pub.off_geom),

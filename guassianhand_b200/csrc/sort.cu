@@ -108,14 +108,25 @@ radix_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
       st_volatile(&status[(size_t)blk * 256 + d], kFlagIncl | total);
     } else {
       st_volatile(&status[(size_t)blk * 256 + d], kFlagLocal | total);
+      // decoupled look-back, kWin predecessors per round trip: the loads of a window are issued
+      // back to back (independent), then consumed nearest-first until an inclusive prefix is met
+      constexpr int kWin = 8;
       int b = (int)blk - 1;
-      while (true) {
-        uint32_t sv = ld_volatile(&status[(size_t)b * 256 + d]);
-        uint32_t f = sv & ~kValMask;
-        if (f == 0) continue;
-        excl += sv & kValMask;
-        if (f == kFlagIncl) break;
-        b--;
+      bool found = false;
+      while (!found) {
+        uint32_t sv[kWin];
+#pragma unroll
+        for (int w = 0; w < kWin; w++)
+          sv[w] = (b - w >= 0) ? ld_volatile(&status[(size_t)(b - w) * 256 + d]) : kFlagIncl;
+#pragma unroll
+        for (int w = 0; w < kWin; w++) {
+          if (found) break;
+          uint32_t x = sv[w];
+          while ((x & ~kValMask) == 0) x = ld_volatile(&status[(size_t)(b - w) * 256 + d]);
+          excl += x & kValMask;
+          if ((x & ~kValMask) == kFlagIncl) found = true;
+        }
+        b -= kWin;
       }
       st_volatile(&status[(size_t)blk * 256 + d], kFlagIncl | (excl + total));
     }

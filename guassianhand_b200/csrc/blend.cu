@@ -12,6 +12,8 @@
 // and only those are blended.  Backward: per-instance partial gradients are reduced across the warp
 // through a conflict-free shared-memory transpose (36 issue slots for 9 values) and leave the SM as
 // one RED.ADD per value per warp.
+#include <cstdlib>
+
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -23,8 +25,7 @@ constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
-constexpr int kIlpF = 4;      // forward: instances blended per inner iteration
-constexpr int kIlpB = 2;      // backward
+constexpr int kMaxIlpB = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -120,7 +121,9 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
   ly = ((w >> 1) << 2) + (l >> 3);
 }
 
-__global__ void __launch_bounds__(kBlendThreads)
+// kIlpF = instances blended per inner iteration (ILP); fewer registers -> one more CTA per SM
+template <int kIlpF>
+__global__ void __launch_bounds__(kBlendThreads, kIlpF <= 2 ? 5 : (kIlpF <= 4 ? 4 : 3))
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
@@ -132,6 +135,25 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
 
   const uint2 range = ranges[vt];
   const uint32_t n = range.y - range.x;
+  if (n == 0) {
+    // empty tile (most of the frame): background only, no barriers, no staging
+    if (warp < kConsumerWarps) {
+      int lx, ly;
+      pixel_of_thread(tid, lx, ly);
+      const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
+      if (px < W && py < H) {
+        const size_t N = (size_t)H * W, pix = (size_t)py * W + px;
+        const float *bg = cam.bg + (size_t)cam.bg_stride * v;
+        final_T[(size_t)v * N + pix] = 1.0f;
+        n_contrib[(size_t)v * N + pix] = 0u;
+        float *o = out_color + (size_t)v * 3 * N + pix;
+        o[0] = ffma(1.0f, bg[0], 0.f);
+        o[N] = ffma(1.0f, bg[1], 0.f);
+        o[2 * N] = ffma(1.0f, bg[2], 0.f);
+      }
+    }
+    return;
+  }
   const uint32_t rounds = (n + kStageN - 1) / kStageN;
   const float4 *src = records + 3 * (size_t)range.x;
   stage_init(sb, tid);
@@ -271,14 +293,16 @@ __device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
   return sum + s1 + s2;
 }
 
-__global__ void __launch_bounds__(kBlendThreads)
+template <int kIlpB>
+__global__ void __launch_bounds__(kBlendThreads, kIlpB <= 1 ? 5 : (kIlpB <= 2 ? 4 : (kIlpB <= 3 ? 3 : 2)))
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uint32_t *__restrict__ order,
                       const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                       const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                       const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
                       float *__restrict__ acc) {
   __shared__ StageBuf sb;
-  __shared__ float s_red[kConsumerWarps][kIlpB][32 * 9];
+  constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
+  __shared__ float s_red[kConsumerWarps][kRedBufs][32 * 9];
   const uint32_t vt = order[blockIdx.x];
   const uint32_t maxc = tilemax[vt];
   if (maxc == 0) return;
@@ -402,20 +426,25 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
             }
           }
           // phase 3 (independent): warp reduction through shared memory + one RED per value
-          bool any[kIlpB];
 #pragma unroll
-          for (int k = 0; k < kIlpB; k++) {
-            any[k] = __any_sync(0xFFFFFFFFu, contrib[k]);
-            if (any[k]) warp_store9(&s_red[warp][k][0], vals[k], lane);
-          }
-          __syncwarp();
+          for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
+            bool any[kRedBufs];
 #pragma unroll
-          for (int k = 0; k < kIlpB; k++) {
-            if (!any[k]) continue;
-            float tot = warp_colsum9(&s_red[warp][k][0], lane);
-            if (owner) atomicAdd(accv + (size_t)__float_as_uint(col[k].w) * kAccStride, tot);
+            for (int q = 0; q < kRedBufs; q++) {
+              const int k = k0 + q;
+              any[q] = k < kIlpB && __any_sync(0xFFFFFFFFu, contrib[k < kIlpB ? k : 0]);
+              if (any[q]) warp_store9(&s_red[warp][q][0], vals[k < kIlpB ? k : 0], lane);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kRedBufs; q++) {
+              const int k = k0 + q;
+              if (!any[q]) continue;
+              float tot = warp_colsum9(&s_red[warp][q][0], lane);
+              if (owner) atomicAdd(accv + (size_t)__float_as_uint(col[k < kIlpB ? k : 0].w) * kAccStride, tot);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
@@ -449,6 +478,11 @@ tile_schedule_kernel(int VT, const uint2 *__restrict__ ranges, uint32_t *__restr
   }
 }
 
+int env_int(const char *name, int dflt) {
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 }  // namespace
 
 cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s) {
@@ -463,12 +497,18 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                  float *out_color, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
-  blend_forward_kernel<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
-                                              (const uint2 *)(state + L.pub.off_ranges),
-                                              (const float4 *)(state + L.pub.off_records),
-                                              (float *)(state + L.pub.off_final_T),
-                                              (uint32_t *)(state + L.pub.off_ncontrib),
-                                              (uint32_t *)(state + L.pub.off_tilemax), out_color);
+  static const int ilp = env_int("GHR_ILPF", 4);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
+                                (const uint2 *)(state + L.pub.off_ranges),
+                                (const float4 *)(state + L.pub.off_records), (float *)(state + L.pub.off_final_T),
+                                (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
+                                out_color);
+  };
+  if (ilp <= 2) launch(blend_forward_kernel<2>);
+  else if (ilp <= 4) launch(blend_forward_kernel<4>);
+  else launch(blend_forward_kernel<6>);
   return cudaGetLastError();
 }
 
@@ -476,11 +516,19 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                   const float *dL_dout, float *acc, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
-  blend_backward_kernel<<<grid, block, 0, s>>>(
-      d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
-      (const uint2 *)(state + L.pub.off_ranges), (const float4 *)(state + L.pub.off_records),
-      (const float *)(state + L.pub.off_final_T), (const uint32_t *)(state + L.pub.off_ncontrib),
-      (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, acc);
+  static const int ilp = env_int("GHR_ILPB", 2);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
+                                (const uint2 *)(state + L.pub.off_ranges),
+                                (const float4 *)(state + L.pub.off_records),
+                                (const float *)(state + L.pub.off_final_T),
+                                (const uint32_t *)(state + L.pub.off_ncontrib),
+                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, acc);
+  };
+  if (ilp <= 1) launch(blend_backward_kernel<1>);
+  else if (ilp <= 2) launch(blend_backward_kernel<2>);
+  else launch(blend_backward_kernel<3>);
   return cudaGetLastError();
 }
 

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 3
+GHR_ABI_VERSION = 4
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 6, 2
 FWD_STAGES = ["preprocess", "depth_sort", "scan_duplicate", "tile_sort", "gather_ranges", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
@@ -47,7 +47,7 @@ class GhrForwardArgs(C.Structure):
         ("bg_stride", C.c_int32),
         ("means3D", _vp), ("opacities", _vp), ("scales", _vp), ("rotations", _vp), ("cov3D_precomp", _vp),
         ("shs", _vp), ("colors_precomp", _vp),
-        ("out_color", _vp), ("radii", _vp),
+        ("out_color", _vp), ("radii", _vp), ("out_mask", _vp),
         ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
         ("dbg_keys_sorted", _vp), ("dbg_point_list", _vp),
         ("host_status", _vp), ("seq", C.c_uint64), ("stage_events", _vp),
@@ -62,7 +62,7 @@ class GhrBackwardArgs(C.Structure):
         ("bg_stride", C.c_int32),
         ("means3D", _vp), ("opacities", _vp), ("scales", _vp), ("rotations", _vp), ("cov3D_precomp", _vp),
         ("shs", _vp), ("colors_precomp", _vp),
-        ("dL_dout_color", _vp),
+        ("dL_dout_color", _vp), ("dL_dout_mask", _vp),
         ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
         ("accumulate", C.c_int32),
         ("dL_dmeans3D", _vp), ("dL_dmeans2D", _vp), ("dL_dcolors", _vp), ("dL_dopacity", _vp),

@@ -139,6 +139,7 @@ def _fill_common(a, cams: _Cams, P, M, sh_degree, R_cap, scale_modifier, flags, 
 
 class ForwardResult(NamedTuple):
     color: torch.Tensor       # [V,3,H,W]
+    mask: Optional[torch.Tensor]   # [V,H,W] coverage 1 - T_final (want_mask) or None
     radii: torch.Tensor       # [V,P] int32
     state: torch.Tensor       # uint8 blob (geometry, sorted instances, ranges, final_T, n_contrib)
     R_cap: int
@@ -148,7 +149,7 @@ class ForwardResult(NamedTuple):
 
 def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
                 scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
-                R_cap: Optional[int] = None, stage_events=None) -> ForwardResult:
+                R_cap: Optional[int] = None, stage_events=None, want_mask: bool = False) -> ForwardResult:
     """Enqueue one libghr forward (V views).  check: "poll" (exact, re-runs on overflow),
     "none" (caller checks GhrStatus later; needed under CUDA-graph capture)."""
     L = N.lib()
@@ -165,11 +166,13 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
         temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
         color = torch.empty(cams.V, 3, cams.H, cams.W, dtype=torch.float32, device=dev)
         radii = torch.empty(cams.V, max(P, 1), dtype=torch.int32, device=dev)
+        mask = torch.empty(cams.V, cams.H, cams.W, dtype=torch.float32, device=dev) if want_mask else None
         dbg = None
         a = N.GhrForwardArgs()
         _fill_common(a, cams, P, M, sh_degree, cap, scale_modifier, flags, means3D, opacities, scales, rotations,
                      cov3D, shs, colors)
         a.out_color, a.radii = color.data_ptr(), radii.data_ptr()
+        a.out_mask = _ptr(mask)
         a.state, a.state_bytes = state.data_ptr(), lay.state_bytes
         a.temp, a.temp_bytes = temp.data_ptr(), temp.numel()
         if want_debug:
@@ -202,12 +205,12 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
                     raise RuntimeError(f"ghr_forward: {R} instances exceed the fixed capacity R_cap={cap}")
                 cap = ws.cap[key]
                 continue
-        return ForwardResult(color, radii[:, :P], state, cap, R, dbg)
+        return ForwardResult(color, mask, radii[:, :P], state, cap, R, dbg)
 
 
 def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, scales, rotations, cov3D, shs,
                  colors, sh_degree, scale_modifier, flags=0, want_means2D=True, accumulate_into=None,
-                 want_conic=False, accumulate=True, stage_events=None):
+                 want_conic=False, accumulate=True, stage_events=None, dL_dmask=None):
     """Enqueue one libghr backward.  Returns dict of gradient tensors (summed over views, except
     dL_dmeans2D which is per view)."""
     L = N.lib()
@@ -223,6 +226,9 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
                  shs, colors)
     dL_dout = _f32c(dL_dout)
     a.dL_dout_color = dL_dout.data_ptr()
+    if dL_dmask is not None:
+        dL_dmask = _f32c(dL_dmask)
+        a.dL_dout_mask = dL_dmask.data_ptr()
     a.state, a.state_bytes = fwd_state.data_ptr(), fwd_state.numel()
     a.temp, a.temp_bytes = temp.data_ptr(), temp.numel()
     g = None if accumulate_into is None else dict(accumulate_into)
@@ -271,7 +277,7 @@ class _RasterizeGaussians(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, want_mask=False):
         _require_cuda(means3D, opacities)
         if means3D.dim() != 2 or means3D.shape[1] != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -284,14 +290,15 @@ class _RasterizeGaussians(torch.autograd.Function):
             cpu_args = [None if t is None or not torch.is_tensor(t) else t.detach().cpu().clone()
                         for t in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)]
             try:
-                res = forward_raw(*args, flags=_flags(rs))
+                res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask)
             except Exception:
                 torch.save(cpu_args, "snapshot_fw.dump")
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
         else:
-            res = forward_raw(*args, flags=_flags(rs))
+            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask)
         ctx.raster_settings = rs
+        ctx.want_mask = want_mask
         ctx.cams = cams
         ctx.R_cap = res.R_cap
         ctx.num_rendered = res.R
@@ -302,16 +309,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                               col_c if col_c is not None else torch.empty(0), res.state)
         radii = res.radii[0]
         ctx.mark_non_differentiable(radii)
+        if want_mask:
+            return res.color[0], radii, res.mask[0]
         return res.color[0], radii
 
     @staticmethod
-    def backward(ctx, grad_out_color, _grad_radii):
+    def backward(ctx, grad_out_color, _grad_radii, grad_mask=None):
         rs = ctx.raster_settings
         means3D, opac, sc, rot, cov, sh, col, state = ctx.saved_tensors
         none_if_empty = lambda t: None if t.numel() == 0 else t
         sc, rot, cov, sh, col = map(none_if_empty, (sc, rot, cov, sh, col))
         call = lambda: backward_raw(ctx.cams, state, ctx.R_cap, grad_out_color.unsqueeze(0), means3D, opac, sc, rot,
-                                    cov, sh, col, int(rs.sh_degree), float(rs.scale_modifier), flags=_flags(rs))
+                                    cov, sh, col, int(rs.sh_degree), float(rs.scale_modifier), flags=_flags(rs),
+                                    dL_dmask=grad_mask.unsqueeze(0) if (ctx.want_mask and grad_mask is not None) else None)
         if rs.debug:
             try:
                 g = call()
@@ -334,13 +344,14 @@ class _RasterizeGaussians(torch.autograd.Function):
             g.get("dL_drotations") if need[6] else None,
             g["dL_dcov3D"] if need[7] else None,
             None,
+            None,
         )
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, want_mask=False):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, want_mask)
 
 
 class GaussianRasterizer(nn.Module):
@@ -361,8 +372,16 @@ class GaussianRasterizer(nn.Module):
                     "ghr_mark_visible")
         return out
 
+    def forward_with_mask(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                          rotations=None, cov3D_precomp=None):
+        """forward() plus the coverage mask [H,W] = 1 - T_final of the same pass: replaces the second
+        rasterizer call of renderer_one_shot.py:353-380 (colors = 1, bg = 0).  Returns
+        (color [3,H,W], radii [P], mask [H,W]); all three renders' gradients flow through ONE backward."""
+        return self.forward(means3D, means2D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp,
+                            _want_mask=True)
+
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
-                cov3D_precomp=None):
+                cov3D_precomp=None, _want_mask=False):
         rs = self.raster_settings
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
             raise Exception('Please provide excatly one of either SHs or precomputed colors!')
@@ -371,7 +390,7 @@ class GaussianRasterizer(nn.Module):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         e = lambda t: torch.Tensor([]) if t is None else t
         return rasterize_gaussians(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
-                                   e(cov3D_precomp), rs)
+                                   e(cov3D_precomp), rs, _want_mask)
 
 
 # ------------------------------------------------------------------ multi-view batched entry
@@ -400,47 +419,55 @@ class ViewBatch(NamedTuple):
 
 class _RasterizeViews(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, views: ViewBatch):
+    def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, views: ViewBatch,
+                want_mask: bool):
         _require_cuda(means3D, opacities, views.viewmatrix)
         cams = views.cams()
         means3D_c, opac_c = _f32c(means3D), _f32c(opacities)
         sh_c, col_c, sc_c, rot_c, cov_c = _opt(sh), _opt(colors_precomp), _opt(scales), _opt(rotations), _opt(cov3Ds_precomp)
         res = forward_raw(cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(views.sh_degree),
-                          float(views.scale_modifier))
-        ctx.cams, ctx.views, ctx.R_cap = cams, views, res.R_cap
+                          float(views.scale_modifier), want_mask=want_mask)
+        ctx.cams, ctx.views, ctx.R_cap, ctx.want_mask = cams, views, res.R_cap, want_mask
         z = torch.empty(0)
         ctx.save_for_backward(means3D_c, opac_c, sc_c if sc_c is not None else z, rot_c if rot_c is not None else z,
                               cov_c if cov_c is not None else z, sh_c if sh_c is not None else z,
                               col_c if col_c is not None else z, res.state)
         ctx.mark_non_differentiable(res.radii)
-        return res.color, res.radii
+        mask = res.mask if want_mask else torch.empty(0, device=means3D.device)
+        return res.color, mask, res.radii
 
     @staticmethod
-    def backward(ctx, grad_color, _):
+    def backward(ctx, grad_color, grad_mask, _):
         means3D, opac, sc, rot, cov, sh, col, state = ctx.saved_tensors
         nz = lambda t: None if t.numel() == 0 else t
         sc, rot, cov, sh, col = map(nz, (sc, rot, cov, sh, col))
         v = ctx.views
         g = backward_raw(ctx.cams, state, ctx.R_cap, grad_color, means3D, opac, sc, rot, cov, sh, col,
-                         int(v.sh_degree), float(v.scale_modifier), want_means2D=False)
+                         int(v.sh_degree), float(v.scale_modifier), want_means2D=False,
+                         dL_dmask=grad_mask if ctx.want_mask else None)
         need = ctx.needs_input_grad
         P = means3D.shape[0]
         return (g["dL_dmeans3D"] if need[0] else None, g.get("dL_dsh") if need[1] else None,
                 g.get("dL_dcolors") if need[2] else None, g["dL_dopacity"].view(P, -1) if need[3] else None,
                 g.get("dL_dscales") if need[4] else None, g.get("dL_drotations") if need[5] else None,
-                g["dL_dcov3D"] if need[6] else None, None)
+                g["dL_dcov3D"] if need[6] else None, None, None)
 
 
 def rasterize_views(means3D, opacities, views: ViewBatch, shs=None, colors_precomp=None, scales=None,
-                    rotations=None, cov3D_precomp=None):
+                    rotations=None, cov3D_precomp=None, return_mask: bool = False):
     """Render V views of one Gaussian set in a single launch chain.
-    Returns (color [V,3,H,W], radii [V,P]); differentiable w.r.t. the Gaussian attributes with the
-    gradient summed over views (what the per-view Python loop + autograd of the reference yields)."""
+    Returns (color [V,3,H,W], radii [V,P]) -- or (color, mask [V,H,W], radii) with return_mask --
+    differentiable w.r.t. the Gaussian attributes with the gradient summed over views (what the
+    per-view Python loop + autograd of the reference yields).
+
+    `mask` is the coverage 1 - T_final of the SAME pass: what the reference obtains from a second
+    rasterizer call with colors = 1 and bg = 0 (renderer_one_shot.py:353-380), at no extra render."""
     if (shs is None) == (colors_precomp is None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
     e = lambda t: torch.Tensor([]) if t is None else t
-    return _RasterizeViews.apply(means3D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
-                                 e(cov3D_precomp), views)
+    color, mask, radii = _RasterizeViews.apply(means3D, e(shs), e(colors_precomp), opacities, e(scales),
+                                               e(rotations), e(cov3D_precomp), views, bool(return_mask))
+    return (color, mask, radii) if return_mask else (color, radii)

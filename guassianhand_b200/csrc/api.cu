@@ -224,7 +224,7 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   if (a->host_status && d.P == 0)
     GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
             "ghr_forward: status copy");
-  GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, s), "ghr_forward: blend");
+  GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, a->out_mask, s), "ghr_forward: blend");
   tm.stop(5);
   return GHR_OK;
 }
@@ -260,7 +260,7 @@ int ghr_backward(const GhrBackwardArgs *a, void *cuda_stream) {
   StageTimer tm{a->stage_events, s};
   tm.start(0);
   GHR_TRY(cudaMemsetAsync(acc, 0, (size_t)d.V * d.P * kAccStride * sizeof(float), s), "ghr_backward: memset(acc)");
-  GHR_TRY(launch_blend_backward(d, L, cam, state, a->dL_dout_color, acc, s), "ghr_backward: blend");
+  GHR_TRY(launch_blend_backward(d, L, cam, state, a->dL_dout_color, a->dL_dout_mask, acc, s), "ghr_backward: blend");
   tm.stop(0);
   tm.start(1);
   GHR_TRY(launch_preprocess_backward(d, L, cam, g, a->scale_modifier, state, acc, go, s),

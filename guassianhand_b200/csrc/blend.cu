@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kBlendThreads, kIlpF <= 2 ? 5 : (kIlpF <= 4 ? 
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
-                     uint32_t *__restrict__ tilemax, float *__restrict__ out_color) {
+                     uint32_t *__restrict__ tilemax, float *__restrict__ out_color,
+                     float *__restrict__ out_mask) {
   __shared__ StageBuf sb;
   const uint32_t vt = order[blockIdx.x];
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
@@ -150,6 +151,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         o[0] = ffma(1.0f, bg[0], 0.f);
         o[N] = ffma(1.0f, bg[1], 0.f);
         o[2 * N] = ffma(1.0f, bg[2], 0.f);
+        if (out_mask) out_mask[(size_t)v * N + pix] = 0.f;
       }
     }
     return;
@@ -262,6 +264,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     o[0] = ffma(Tr, bg[0], C0);
     o[N] = ffma(Tr, bg[1], C1);
     o[2 * N] = ffma(Tr, bg[2], C2);
+    if (out_mask) out_mask[(size_t)v * N + pix] = 1.0f - Tr;   // = sum_j alpha_j T_j
   }
   uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
   if (lane == 0 && wmax) atomicMax(&tilemax[vt], wmax);
@@ -299,7 +302,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
                       const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                       const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                       const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
-                      float *__restrict__ acc) {
+                      const float *__restrict__ dL_dmask, float *__restrict__ acc) {
   __shared__ StageBuf sb;
   constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
   __shared__ float s_red[kConsumerWarps][kRedBufs][32 * 9];
@@ -351,7 +354,10 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
     dLp2 = g[2 * N];
   }
   const float *bg = cam.bg + (size_t)cam.bg_stride * v;
-  const float bgdot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  float bgdot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
+  // coverage output m = 1 - T_final: dm/dalpha_j = +T_final/(1-alpha_j), the background term with
+  // the opposite sign, so its gradient folds into bgdot
+  if (dL_dmask && inside) bgdot -= dL_dmask[(size_t)v * N + (size_t)py * W + px];
   float Tr = T_final;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
 
@@ -494,7 +500,7 @@ cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state,
 }
 
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
-                                 float *out_color, cudaStream_t s) {
+                                 float *out_color, float *out_mask, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
   static const int ilp = env_int("GHR_ILPF", 4);
@@ -504,7 +510,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                 (const uint2 *)(state + L.pub.off_ranges),
                                 (const float4 *)(state + L.pub.off_records), (float *)(state + L.pub.off_final_T),
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
-                                out_color);
+                                out_color, out_mask);
   };
   if (ilp <= 2) launch(blend_forward_kernel<2>);
   else if (ilp <= 4) launch(blend_forward_kernel<4>);
@@ -513,7 +519,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
 }
 
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
-                                  const float *dL_dout, float *acc, cudaStream_t s) {
+                                  const float *dL_dout, const float *dL_dmask, float *acc, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
   static const int ilp = env_int("GHR_ILPB", 2);
@@ -524,7 +530,7 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                 (const float4 *)(state + L.pub.off_records),
                                 (const float *)(state + L.pub.off_final_T),
                                 (const uint32_t *)(state + L.pub.off_ncontrib),
-                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, acc);
+                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc);
   };
   if (ilp <= 1) launch(blend_backward_kernel<1>);
   else if (ilp <= 2) launch(blend_backward_kernel<2>);

@@ -72,9 +72,9 @@ cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state,
                                  uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s);
 cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s);
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
-                                 float *out_color, cudaStream_t s);
+                                 float *out_color, float *out_mask, cudaStream_t s);
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
-                                  const float *dL_dout, float *acc, cudaStream_t s);
+                                  const float *dL_dout, const float *dL_dmask, float *acc, cudaStream_t s);
 struct GradOut {
   int accumulate;
   float *dmeans3D, *dmeans2D, *dcolors, *dopacity, *dcov3D, *dsh, *dscales, *drots, *dconic;

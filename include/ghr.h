@@ -41,7 +41,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 3
+#define GHR_ABI_VERSION 4
 
 /* stage ids for the optional stage_events arrays */
 #define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges+schedule, 5 blend */
@@ -105,6 +105,9 @@ typedef struct GhrForwardArgs {
   /* outputs */
   float *out_color;            /* [V,3,H,W] */
   int32_t *radii;              /* [V,P] */
+  float *out_mask;             /* [V,H,W] or NULL: coverage 1 - T_final of the same pass.  Equals the
+                                  reference's second "mask" render (colors = 1, bg = 0,
+                                  renderer_one_shot.py:353-380) without rendering twice */
   /* workspaces */
   void *state; size_t state_bytes;
   void *temp;  size_t temp_bytes;
@@ -131,6 +134,7 @@ typedef struct GhrBackwardArgs {
   int32_t bg_stride;
   const float *means3D, *opacities, *scales, *rotations, *cov3D_precomp, *shs, *colors_precomp;
   const float *dL_dout_color;  /* [V,3,H,W] */
+  const float *dL_dout_mask;   /* [V,H,W] or NULL: gradient w.r.t. out_mask, folded into the same pass */
   const void *state; size_t state_bytes;   /* as written by ghr_forward */
   void *temp; size_t temp_bytes;           /* >= layout.temp_bwd_bytes */
   /* Gradient outputs.  Summed over the V views.  accumulate != 0: "+=" into the buffers

@@ -126,3 +126,53 @@ def test_batched_views_autograd_equals_view_loop(cuda_device):
     assert util.rel_err(xyz.grad.cpu().numpy(), tot["dL_dmeans3D"]) <= 1e-4
     assert util.rel_err(colors.grad.cpu().numpy(), tot["dL_dcolors"]) <= 1e-4
     assert util.rel_err(rotation.grad.cpu().numpy(), tot["dL_drots"]) <= 1e-4
+
+
+def test_fused_mask_equals_second_render(cuda_device):
+    """the coverage mask of the SAME pass (1 - T_final) must equal the
+    reference's second render (colors = 1, bg = 0, renderer_one_shot.py:353-380) to 1e-5, and one
+    backward must deliver the sum of both renders' gradients to 1e-4."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from guassianhand_b200 import rasterize_views
+    dev = cuda_device
+    sc = scenes.two_hand_scene(4000, seed=19)
+    cams = scenes.fibonacci_cameras(3, 96, 80, seed=19)
+    bg = np.array([0.2, 0.3, 0.4], np.float32)
+    rng = np.random.default_rng(5)
+    w_img = (rng.normal(size=(3, 3, 96, 80)) / 7680).astype(np.float32)
+    w_msk = (rng.normal(size=(3, 96, 80)) / 7680).astype(np.float32)
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    # single-view drop-in object
+    xyz, opacity, scaling, rotation, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+    m2d = torch.zeros_like(xyz, requires_grad=True)
+    r = GaussianRasterizer(raster_settings=_settings(cams[0], bg, dev))
+    img, radii, mask = r.forward_with_mask(means3D=xyz, means2D=m2d, colors_precomp=colors, opacities=opacity,
+                                           scales=scaling, rotations=rotation)
+    ((img * torch.from_numpy(w_img[0]).to(dev)).sum() + (mask * torch.from_numpy(w_msk[0]).to(dev)).sum()).backward()
+    f1, g1 = util.run_oracle(sc, cams[0], bg, w_img[0])
+    ones = scenes.GaussianScene(**{**sc.__dict__})
+    ones.colors = np.ones_like(sc.colors)
+    # the mask render's three channels are identical; dL/dmask spreads to one channel of the oracle call
+    dLm = np.stack([w_msk[0], np.zeros_like(w_msk[0]), np.zeros_like(w_msk[0])])
+    f2, g2 = util.run_oracle(ones, cams[0], np.zeros(3, np.float32), dLm)
+    assert np.abs(mask.detach().cpu().numpy() - f2["out_color"][0]).max() <= 1e-5
+    assert np.abs(img.detach().cpu().numpy() - f1["out_color"]).max() <= 1e-5
+    for t, k in ((xyz, "dL_dmeans3D"), (scaling, "dL_dscales"), (rotation, "dL_drots")):
+        assert util.rel_err(t.grad.cpu().numpy(), g1[k].astype(np.float64) + g2[k]) <= 1e-4, k
+    assert util.rel_err(opacity.grad.cpu().numpy().reshape(-1), g1["dL_dopacity"].astype(np.float64) + g2["dL_dopacity"]) <= 1e-4
+    assert util.rel_err(m2d.grad.cpu().numpy(), g1["dL_dmeans2D"].astype(np.float64) + g2["dL_dmeans2D"]) <= 1e-4
+    assert util.rel_err(colors.grad.cpu().numpy(), g1["dL_dcolors"]) <= 1e-4
+    # batched entry
+    xyz2, opacity2, scaling2, rotation2, colors2 = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+    views = util.gpu_views(cams, bg, dev)
+    imgs, masks, _ = rasterize_views(xyz2, opacity2, views, colors_precomp=colors2, scales=scaling2,
+                                     rotations=rotation2, return_mask=True)
+    ((imgs * torch.from_numpy(w_img).to(dev)).sum() + (masks * torch.from_numpy(w_msk).to(dev)).sum()).backward()
+    tot = 0
+    for v, cam in enumerate(cams):
+        _, ga = util.run_oracle(sc, cam, bg, w_img[v])
+        fb, gb = util.run_oracle(ones, cam, np.zeros(3, np.float32),
+                                 np.stack([w_msk[v], np.zeros_like(w_msk[v]), np.zeros_like(w_msk[v])]))
+        assert np.abs(masks[v].detach().cpu().numpy() - fb["out_color"][0]).max() <= 1e-5
+        tot = tot + ga["dL_dmeans3D"].astype(np.float64) + gb["dL_dmeans3D"]
+    assert util.rel_err(xyz2.grad.cpu().numpy(), tot) <= 1e-4

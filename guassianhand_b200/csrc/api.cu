@@ -2,6 +2,7 @@
 // No allocation, no synchronisation (unless GHR_FLAG_DEBUG), everything on the caller's stream.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ghr_internal.cuh"
@@ -41,6 +42,12 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->npt = (bits + 7) / 8;
   L->items_d = (VP > (1u << 21)) ? 16 : 4;
   L->items_t = ((uint64_t)d.R_cap > (1u << 19)) ? 16 : 4;
+  {
+    // tuning overrides (A/B runs): GHR_ITEMS_D / GHR_ITEMS_T in {4, 16}
+    static const char *ed = getenv("GHR_ITEMS_D"), *et = getenv("GHR_ITEMS_T");
+    if (ed) L->items_d = atoi(ed) >= 16 ? 16 : 4;
+    if (et) L->items_t = atoi(et) >= 16 ? 16 : 4;
+  }
   L->nblk_d = (int)((d.P + (uint64_t)kSortThreads * L->items_d - 1) / ((uint64_t)kSortThreads * L->items_d));
   L->nblk_t = (int)(((uint64_t)d.R_cap + (uint64_t)kSortThreads * L->items_t - 1) /
                     ((uint64_t)kSortThreads * L->items_t));

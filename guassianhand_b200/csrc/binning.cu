@@ -29,14 +29,15 @@ __device__ __forceinline__ void st_volatile64(uint64_t *p, uint64_t v) {
 __device__ __forceinline__ void rect_of(float px, float py, int radius, int gx, int gy, int &minx, int &miny,
                                         int &maxx, int &maxy) {
   float rf = (float)radius;
-  minx = min(gx, max(0, (int)fdiv(fsub(px, rf), 16.0f)));
-  miny = min(gy, max(0, (int)fdiv(fsub(py, rf), 16.0f)));
-  maxx = min(gx, max(0, (int)fdiv(fsub(fadd(fadd(px, rf), 16.0f), 1.0f), 16.0f)));
-  maxy = min(gy, max(0, (int)fdiv(fsub(fadd(fadd(py, rf), 16.0f), 1.0f), 16.0f)));
+  // x / 16 == x * 0.0625 bit for bit (power of two)
+  minx = min(gx, max(0, (int)fmul(fsub(px, rf), 0.0625f)));
+  miny = min(gy, max(0, (int)fmul(fsub(py, rf), 0.0625f)));
+  maxx = min(gx, max(0, (int)fmul(fsub(fadd(fadd(px, rf), 16.0f), 1.0f), 0.0625f)));
+  maxy = min(gy, max(0, (int)fmul(fsub(fadd(fadd(py, rf), 16.0f), 1.0f), 0.0625f)));
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_cap,
+scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, uint64_t R_cap,
                       const float4 *__restrict__ geom, const uint32_t *__restrict__ order /*[V,P] depth-sorted ids*/,
                       uint64_t *__restrict__ scan_status, uint32_t *__restrict__ ticket,
                       uint32_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint32_t *__restrict__ thist,
@@ -69,7 +70,7 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
     rad[k] = 0;
     xy[k] = make_float2(0.f, 0.f);
     if (e < total_elems) {
-      uint32_t v = (uint32_t)(e / P);
+      uint32_t v = dP.div((uint32_t)e);
       uint32_t id = order[e];
       uint32_t g = v * (uint32_t)P + id;
       float4 q3 = geom[4 * (size_t)g + 3];
@@ -145,13 +146,22 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
   __syncthreads();
   uint64_t off = s_prefix + wbase + (incl - sum);
 
-  // emission: row-major over the tile rectangle (A.4), in depth-sorted Gaussian order
+  // emission: row-major over the tile rectangle (A.4), in depth-sorted Gaussian order.  Histogram
+  // of the tile key's digits for the tile sort: the low digit per instance; the upper digits change
+  // rarely along a thread's emissions (same view, neighbouring tiles), so they are counted as runs
+  // and flushed once per change instead of one (warp-wide conflicting) shared atomic per instance.
+  uint32_t run_hi = 0xFFFFFFFFu, run_cnt = 0;
+  auto flush = [&]() {
+    if (run_cnt)
+      for (int p = 1; p < npt; p++) atomicAdd(&s_hist[p][(run_hi >> (8 * (p - 1))) & 255u], run_cnt);
+    run_cnt = 0;
+  };
 #pragma unroll
   for (int k = 0; k < kItems; k++) {
     if (tt[k]) {
       int minx, miny, maxx, maxy;
       rect_of(xy[k].x, xy[k].y, rad[k], gx, gy, minx, miny, maxx, maxy);
-      uint32_t v = gid[k] / (uint32_t)P;
+      uint32_t v = dP.div(gid[k]);
       uint32_t tbase = v * (uint32_t)T;
       for (int y = miny; y < maxy; y++)
         for (int x = minx; x < maxx; x++) {
@@ -159,12 +169,18 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
           if (off < R_cap) {
             tkeys[off] = tk;
             tvals[off] = gid[k];
-            for (int p = 0; p < npt; p++) atomicAdd(&s_hist[p][(tk >> (8 * p)) & 255u], 1u);
+            atomicAdd(&s_hist[0][tk & 255u], 1u);
+            if ((tk >> 8) != run_hi) {
+              flush();
+              run_hi = tk >> 8;
+            }
+            run_cnt++;
           }
           off++;
         }
     }
   }
+  flush();
   __syncthreads();
   for (int k = tid; k < npt * 256; k += kScanThreads) {
     uint32_t c = (&s_hist[0][0])[k];
@@ -172,33 +188,68 @@ scan_duplicate_kernel(int P, int V, int gx, int gy, int T, int npt, uint64_t R_c
   }
 }
 
-// Three threads per sorted instance (one per float4 of the 48-byte record): consecutive lanes read
-// consecutive 16-byte chunks of a geometry record (one request per record instead of three) and
-// write consecutive 16-byte chunks of the sorted slab (fully coalesced 128-bit stores).
-__global__ void __launch_bounds__(384)
-gather_ranges_kernel(int P, int T, uint64_t R_cap, const GhrStatus *__restrict__ status,
+// 64 sorted instances per block iteration.  Phase 1: four threads per instance test two 8x4
+// sub-blocks each of the instance's tile against its alpha >= 1/255 ellipse (exact box minimum,
+// cull_hit) and combine the 8-bit mask with two shuffles.  Phase 2: three threads per instance (one
+// per float4 of the 48-byte record) copy the geometry record into sorted order: consecutive lanes
+// read consecutive 16-byte chunks of a record and write consecutive chunks of the sorted slab
+// (coalesced 128-bit stores); the mask rides in record[1].w.
+constexpr int kGatherInst = 64;
+__global__ void __launch_bounds__(4 * kGatherInst)
+gather_ranges_kernel(FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap, const GhrStatus *__restrict__ status,
                      const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tvals,
                      const float4 *__restrict__ geom, float4 *__restrict__ records, uint2 *__restrict__ ranges,
                      uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
+  __shared__ uint32_t s_mask[kGatherInst];
   uint64_t R = status->R;
   if (R > R_cap) R = R_cap;
-  const uint32_t part = threadIdx.x % 3u;
-  uint64_t r = (uint64_t)blockIdx.x * (blockDim.x / 3) + threadIdx.x / 3u;
-  for (; r < R; r += (uint64_t)gridDim.x * (blockDim.x / 3)) {
-    const uint32_t g = tvals[r];
-    float4 q = geom[4 * (size_t)g + part];
-    const uint32_t id = g % (uint32_t)P;
-    if (part == 2) {
-      if (dbg_keys) dbg_keys[r] = ((uint64_t)(tkeys[r] % (uint32_t)T) << 32) | __float_as_uint(q.w);
-      q.w = __uint_as_float(id);
+  const uint32_t tid = threadIdx.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * kGatherInst; base < R; base += (uint64_t)gridDim.x * kGatherInst) {
+    {
+      const uint64_t r = base + (tid >> 2);
+      const uint32_t sub = tid & 3u;
+      uint32_t m = 0;
+      if (r < R) {
+        const uint32_t g = tvals[r];
+        const uint32_t tile = dT.mod(tkeys[r]);
+        const float4 q0 = geom[4 * (size_t)g], q1 = geom[4 * (size_t)g + 1];
+        const uint32_t ty = dgx.div(tile);
+        const int x0 = (int)(tile - ty * dgx.d) * kTile, y0 = (int)ty * kTile;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const uint32_t w = 2 * sub + k;
+          const float bx0 = (float)(x0 + (int)((w & 1u) << 3)), by0 = (float)(y0 + (int)((w >> 1) << 2));
+          if (cull_hit(q0, q1, bx0, bx0 + 7.f, by0, by0 + 3.f)) m |= 1u << w;
+        }
+      }
+      m |= __shfl_xor_sync(0xFFFFFFFFu, m, 1);
+      m |= __shfl_xor_sync(0xFFFFFFFFu, m, 2);
+      if (sub == 0) s_mask[tid >> 2] = m;
     }
-    records[3 * r + part] = q;
-    if (part == 0) {
-      const uint32_t tk = tkeys[r];
-      if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
-      if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
-      if (dbg_plist) dbg_plist[r] = id;
+    __syncthreads();
+    if (tid < 3 * kGatherInst) {
+      const uint32_t li = tid / 3u, part = tid % 3u;
+      const uint64_t r = base + li;
+      if (r < R) {
+        const uint32_t g = tvals[r];
+        float4 q = geom[4 * (size_t)g + part];
+        const uint32_t id = dP.mod(g);
+        if (part == 2) {
+          if (dbg_keys) dbg_keys[r] = ((uint64_t)dT.mod(tkeys[r]) << 32) | __float_as_uint(q.w);
+          q.w = __uint_as_float(id);
+        } else if (part == 1) {
+          q.w = __uint_as_float(s_mask[li]);
+        }
+        records[3 * r + part] = q;
+        if (part == 0) {
+          const uint32_t tk = tkeys[r];
+          if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
+          if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
+          if (dbg_plist) dbg_plist[r] = id;
+        }
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -216,7 +267,7 @@ cudaError_t launch_scan_duplicate(const GhrDims &d, const Layout &L, char *state
   (void)seq;
   if (L.nblk_scan == 0) return cudaSuccess;
   scan_duplicate_kernel<<<L.nblk_scan, kScanThreads, 0, s>>>(
-      d.P, d.V, L.gx, L.gy, L.T, L.npt, (uint64_t)d.R_cap, (const float4 *)(state + L.pub.off_geom),
+      d.P, make_fastdiv((uint32_t)d.P), d.V, L.gx, L.gy, L.T, L.npt, (uint64_t)d.R_cap, (const float4 *)(state + L.pub.off_geom),
       (const uint32_t *)(temp + L.t_dvals[depth_sorted_buf()]), (uint64_t *)(temp + L.t_scan_status),
       (uint32_t *)(temp + L.t_tickets) + 4 * (size_t)d.V + 4, (uint32_t *)(temp + L.t_tkeys[0]),
       (uint32_t *)(temp + L.t_tvals[0]), (uint32_t *)(temp + L.t_thist), (GhrStatus *)(state + L.pub.off_status),
@@ -228,9 +279,9 @@ cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state,
                                  uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s) {
   if (d.R_cap <= 0) return cudaSuccess;
   int buf = tile_sorted_buf(L);
-  uint64_t want = ((uint64_t)d.R_cap + 127) / 128;
+  uint64_t want = ((uint64_t)d.R_cap + kGatherInst - 1) / kGatherInst;
   int nb = (int)(want < (uint64_t)(148 * 16) ? want : (uint64_t)(148 * 16));
-  gather_ranges_kernel<<<nb, 384, 0, s>>>(d.P, L.T, (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
+  gather_ranges_kernel<<<nb, 4 * kGatherInst, 0, s>>>(make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
                                           (const uint32_t *)(temp + L.t_tkeys[buf]),
                                           (const uint32_t *)(temp + L.t_tvals[buf]),
                                           (const float4 *)(state + L.pub.off_geom),

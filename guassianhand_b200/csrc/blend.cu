@@ -26,6 +26,8 @@ constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr int kMaxIlpB = 2;
+constexpr int kDirectMax = 3;    // <= this many contributing lanes: no warp reduction, direct REDs
+constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -47,9 +49,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware (no issue slots burnt
-// by a spin loop while other warps of the SM are blending), retried until the phase completes.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Blocking wait: try_wait with a suspend-time hint parks the warp in hardware; between retries the
+// warp sleeps `backoff_ns` (warps that only keep the ring turning -- all their pixels terminated --
+// pass a long backoff so their polling does not take issue slots from warps that still blend).
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t backoff_ns = 32u) {
   uint32_t ok;
   do {
     asm volatile(
@@ -59,7 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
-    if (!ok) __nanosleep(64);
+    if (!ok) __nanosleep(backoff_ns);
   } while (!ok);
 }
 
@@ -93,26 +96,6 @@ __device__ __forceinline__ float exp_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
   return y;
 }
-__device__ __forceinline__ float rcp_fast(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Exact box-constrained minimum of q(d) = A dx^2 + 2 B dx dy + C dy^2 over the pixel block
-// [bx0,bx1] x [by0,by1] (d = pixel - centre) against the instance's threshold.  The minimiser of a
-// convex quadratic over a box is the centre itself (q = 0) or lies on an edge facing the centre; the
-// two candidates below cover every case.  Returns true if the instance may contribute to the block.
-__device__ __forceinline__ bool cull_hit(const float4 a, const float4 b, float bx0, float bx1, float by0, float by1) {
-  const float A = a.z, B = a.w, C = b.x, thr = b.z;
-  const float u0 = bx0 - a.x, u1 = bx1 - a.x, v0 = by0 - a.y, v1 = by1 - a.y;
-  const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
-  const float v_e = fminf(fmaxf(-B * uc * rcp_fast(C), v0), v1);   // best v on the edge u = uc
-  const float u_e = fminf(fmaxf(-B * vc * rcp_fast(A), u0), u1);   // best u on the edge v = vc
-  const float q1 = A * uc * uc + 2.f * B * uc * v_e + C * v_e * v_e;
-  const float q2 = A * u_e * u_e + 2.f * B * u_e * vc + C * vc * vc;
-  return !(fminf(q1, q2) > thr);   // NaN-safe: anything unordered counts as a hit
-}
 
 // thread -> pixel inside the tile: warp w covers the 8x4 block (w&1, w>>1)
 __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
@@ -121,15 +104,39 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
   ly = ((w >> 1) << 2) + (l >> 3);
 }
 
-// kIlpF = instances blended per inner iteration (ILP); fewer registers -> one more CTA per SM
+// Survivor queue of one warp for one stage: the indices (inside the stage, ascending) of the
+// instances whose sub-block mask (record[1].w, written by gather_ranges) has this warp's bit set.
+// Each lane tests 4 instances (one 32-bit LDS each), 4 ballots compact them; the blend loop then
+// takes kIlp indices per iteration from one broadcast LDS instead of peeling bits off a mask.
+// Survivor i is q[kQPad + i]; kQPad entries of index 0 pad both ends.  Returns the survivor count.
+__device__ __forceinline__ uint32_t build_queue(const float4 *rec, uint32_t cnt, uint32_t limit, int warp, int lane,
+                                                uint8_t *q) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kStageN / 32; w++) {
+    const uint32_t e = w * 32 + lane;
+    bool hit = false;
+    if (e < cnt && e < limit) hit = (__float_as_uint(rec[3 * e + 1].w) >> warp) & 1u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) q[kQPad + total + __popc(m & lt)] = (uint8_t)e;
+    total += __popc(m);
+  }
+  if (lane < kQPad) q[kQPad + total + lane] = 0;     // q[0, kQPad) stays 0 from the kernel prologue
+  __syncwarp();
+  return total;
+}
+
+// kIlpF = instances blended per inner iteration (ILP): 4 or 8
 template <int kIlpF>
-__global__ void __launch_bounds__(kBlendThreads, kIlpF <= 2 ? 5 : (kIlpF <= 4 ? 4 : 3))
+__global__ void __launch_bounds__(kBlendThreads, kIlpF <= 4 ? 4 : 3)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float *__restrict__ out_color,
                      float *__restrict__ out_mask) {
   __shared__ StageBuf sb;
+  __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
   const uint32_t vt = order[blockIdx.x];
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -187,9 +194,8 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  // pixel block of this warp: x in [bx0,bx1], y in [by0,by1]
-  const float bx0 = (float)((tile % gx) * kTile + ((warp & 1) << 3)), bx1 = bx0 + 7.f;
-  const float by0 = (float)((tile / gx) * kTile + ((warp >> 1) << 2)), by1 = by0 + 3.f;
+  uint8_t *q = &s_q[warp][0];
+  if (lane < kQPad) q[lane] = 0;
 
   bool done = !inside;
   bool wdone = __all_sync(0xFFFFFFFFu, done);
@@ -198,51 +204,45 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
   uint32_t last = 0;
   for (uint32_t r = 0; r < rounds; r++) {
     const int s = r % kStages;
-    mbar_wait(&sb.full[s], (r / kStages) & 1);
+    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 512u : 32u);
     if (r >= *(volatile uint32_t *)&sb.stop_round) break;
     if (!wdone) {
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const float4 *rec = &sb.rec[s][0];
-      for (uint32_t base = 0; base < cnt; base += 32) {
-        // each lane tests ONE instance's cull box against this warp's pixel block
-        const uint32_t e = base + lane;
-        bool hit = false;
-        if (e < cnt) hit = cull_hit(rec[3 * e], rec[3 * e + 1], bx0, bx1, by0, by1);
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
-        while (mask) {
-          // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
-          // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
-          // short T / colour update is serial.
-          uint32_t jj[kIlpF];
-          float al[kIlpF];
-          float4 col[kIlpF];
+      const uint32_t total = build_queue(rec, cnt, kStageN, warp, lane, q);
+      for (uint32_t b = 0; b < total; b += kIlpF) {
+        // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
+        // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
+        // short T / colour update is serial (and branch-free: a rejected pair blends alpha = 0).
+        uint32_t jj[kIlpF];
+        float al[kIlpF];
+        float4 col[kIlpF];
+        uint32_t packed[kIlpF / 4];
 #pragma unroll
-          for (int k = 0; k < kIlpF; k++) {
-            const bool ok = mask != 0;
-            jj[k] = ok ? base + (uint32_t)__ffs(mask) - 1u : jj[0];
-            mask &= mask - 1u;                      // 0 stays 0
-            float4 a = rec[3 * jj[k]], b = rec[3 * jj[k] + 1];
-            col[k] = rec[3 * jj[k] + 2];
-            float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-            float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-            float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
-            float alpha = fminf(0.99f, fmul(b.y, exp_fast(power)));
-            al[k] = (ok && power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;
-          }
+        for (int w = 0; w < kIlpF / 4; w++) packed[w] = *reinterpret_cast<const uint32_t *>(q + kQPad + b + 4 * w);
 #pragma unroll
-          for (int k = 0; k < kIlpF; k++) {
-            if (done || al[k] == 0.f) continue;
-            float test_T = fmul(Tr, fsub(1.f, al[k]));
-            if (test_T < 0.0001f) {
-              done = true;
-              continue;
-            }
-            C0 = ffma(fmul(col[k].x, al[k]), Tr, C0);
-            C1 = ffma(fmul(col[k].y, al[k]), Tr, C1);
-            C2 = ffma(fmul(col[k].z, al[k]), Tr, C2);
-            Tr = test_T;
-            last = r * kStageN + jj[k] + 1;
-          }
+        for (int k = 0; k < kIlpF; k++) {
+          jj[k] = (packed[k >> 2] >> (8 * (k & 3))) & 255u;
+          const float4 a = rec[3 * jj[k]], bq = rec[3 * jj[k] + 1];
+          col[k] = rec[3 * jj[k] + 2];
+          const float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+          const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
+          const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
+          const float alpha = fminf(0.99f, fmul(bq.y, exp_fast(power)));
+          al[k] = (b + k < total && power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kIlpF; k++) {
+          float a = done ? 0.f : al[k];
+          const float test_T = fmul(Tr, fsub(1.f, a));          // a == 0: test_T == Tr exactly
+          const bool term = a != 0.f && test_T < 0.0001f;        // the stopping Gaussian is not blended
+          done = done || term;
+          a = term ? 0.f : a;
+          C0 = ffma(fmul(col[k].x, a), Tr, C0);
+          C1 = ffma(fmul(col[k].y, a), Tr, C1);
+          C2 = ffma(fmul(col[k].z, a), Tr, C2);
+          Tr = term ? Tr : test_T;
+          last = a != 0.f ? r * kStageN + jj[k] + 1 : last;
         }
         if (__all_sync(0xFFFFFFFFu, done)) {
           wdone = true;
@@ -302,10 +302,11 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
                       const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                       const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
                       const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
-                      const float *__restrict__ dL_dmask, float *__restrict__ acc) {
+                      const float *__restrict__ dL_dmask, float *__restrict__ acc, int direct_max) {
   __shared__ StageBuf sb;
   constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
   __shared__ float s_red[kConsumerWarps][kRedBufs][32 * 9];
+  __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
   const uint32_t vt = order[blockIdx.x];
   const uint32_t maxc = tilemax[vt];
   if (maxc == 0) return;
@@ -339,8 +340,8 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  const float bx0 = (float)((tile % gx) * kTile + ((warp & 1) << 3)), bx1 = bx0 + 7.f;
-  const float by0 = (float)((tile / gx) * kTile + ((warp >> 1) << 2)), by1 = by0 + 3.f;
+  uint8_t *q = &s_q[warp][0];
+  if (lane < kQPad) q[lane] = 0;
 
   float T_final = 0.f, dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
   uint32_t last = 0;
@@ -363,40 +364,36 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
 
   // lanes 0..8 own the warp totals of the 9 accumulated values
   const bool owner = lane < 9;
-  float *accv = acc + (size_t)v * P * kAccStride + lane;
+  float *accb = acc + (size_t)v * P * kAccStride;
   const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
 
   for (uint32_t k = 0; k < rounds; k++) {
     const int s = k % kStages;
-    mbar_wait(&sb.full[s], (k / kStages) & 1);
     const uint32_t rr = rounds - 1 - k;
+    mbar_wait(&sb.full[s], (k / kStages) & 1, rr * kStageN < wlast ? 32u : 512u);
     if (rr * kStageN < wlast) {
       const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
       const float4 *rec = &sb.rec[s][0];
-      for (int base = (int)((cnt - 1) & ~31u); base >= 0; base -= 32) {
-        const uint32_t el = (uint32_t)base + lane;          // index inside the stage
-        bool hit = false;
-        if (el < cnt && rr * kStageN + el < wlast) hit = cull_hit(rec[3 * el], rec[3 * el + 1], bx0, bx1, by0, by1);
-        uint32_t mask = __ballot_sync(0xFFFFFFFFu, hit);
-        while (mask) {
-          // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets
+      // survivors of this warp's sub-block among the instances that precede the warp's last contributor
+      const uint32_t total = build_queue(rec, cnt, wlast - rr * kStageN, warp, lane, q);
+      {
+        for (int b = (int)total; b > 0; b -= kIlpB) {
+          // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets; back to front
           int jj[kIlpB];
           float al[kIlpB], Gk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB];
           float4 col[kIlpB];
 #pragma unroll
           for (int k = 0; k < kIlpB; k++) {
-            const bool ok = mask != 0;
-            const int bit = ok ? 31 - __clz(mask) : 0;          // back to front
-            mask &= ~(1u << bit) & (ok ? 0xFFFFFFFFu : 0u);
-            jj[k] = ok ? base + bit : jj[0];
+            const bool ok = b - 1 - k >= 0;
+            jj[k] = q[kQPad + b - 1 - k];                       // front pad (index 0) when !ok
             const uint32_t e = rr * kStageN + (uint32_t)jj[k];  // position in the tile list
-            float4 a = rec[3 * jj[k]], b = rec[3 * jj[k] + 1];
+            const float4 a = rec[3 * jj[k]], bq = rec[3 * jj[k] + 1];
             col[k] = rec[3 * jj[k] + 2];
             float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-            float q = ffma(fmul(a.z, dx), dx, fmul(fmul(b.x, dy), dy));
-            float power = ffma(-0.5f, q, -fmul(fmul(a.w, dx), dy));
+            float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
+            float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
             float G = exp_fast(power);
-            float alpha = fminf(0.99f, fmul(b.y, G));
+            float alpha = fminf(0.99f, fmul(bq.y, G));
             const bool c = ok && e < last && power <= 0.0f && alpha >= kAlphaMin;
             al[k] = c ? alpha : 0.f;
             Gk[k] = G;
@@ -431,23 +428,31 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
               vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
             }
           }
-          // phase 3 (independent): warp reduction through shared memory + one RED per value
+          // phase 3 (independent): slots with few contributing lanes send their partials straight
+          // to L2 (9 REDs for the warp); the others are reduced through shared memory first and
+          // leave as one RED per value
 #pragma unroll
           for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
-            bool any[kRedBufs];
+            int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
 #pragma unroll
-            for (int q = 0; q < kRedBufs; q++) {
-              const int k = k0 + q;
-              any[q] = k < kIlpB && __any_sync(0xFFFFFFFFu, contrib[k < kIlpB ? k : 0]);
-              if (any[q]) warp_store9(&s_red[warp][q][0], vals[k < kIlpB ? k : 0], lane);
+            for (int qi = 0; qi < kRedBufs; qi++) {
+              const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+              const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
+              mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
+              if (mode[qi] == 2) warp_store9(&s_red[warp][qi][0], vals[k], lane);
+              if (mode[qi] == 1 && contrib[k]) {
+                float *dst = accb + (size_t)__float_as_uint(col[k].w) * kAccStride;
+#pragma unroll
+                for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
+              }
             }
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < kRedBufs; q++) {
-              const int k = k0 + q;
-              if (!any[q]) continue;
-              float tot = warp_colsum9(&s_red[warp][q][0], lane);
-              if (owner) atomicAdd(accv + (size_t)__float_as_uint(col[k < kIlpB ? k : 0].w) * kAccStride, tot);
+            for (int qi = 0; qi < kRedBufs; qi++) {
+              const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+              if (mode[qi] != 2) continue;
+              float tot = warp_colsum9(&s_red[warp][qi][0], lane);
+              if (owner) atomicAdd(accb + (size_t)__float_as_uint(col[k].w) * kAccStride + lane, tot);
             }
             __syncwarp();
           }
@@ -512,9 +517,8 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
                                 out_color, out_mask);
   };
-  if (ilp <= 2) launch(blend_forward_kernel<2>);
-  else if (ilp <= 4) launch(blend_forward_kernel<4>);
-  else launch(blend_forward_kernel<6>);
+  if (ilp <= 4) launch(blend_forward_kernel<4>);
+  else launch(blend_forward_kernel<8>);
   return cudaGetLastError();
 }
 
@@ -523,6 +527,7 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
   static const int ilp = env_int("GHR_ILPB", 2);
+  static const int direct = env_int("GHR_DIRECT", kDirectMax);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
@@ -530,7 +535,7 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                 (const float4 *)(state + L.pub.off_records),
                                 (const float *)(state + L.pub.off_final_T),
                                 (const uint32_t *)(state + L.pub.off_ncontrib),
-                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc);
+                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc, direct);
   };
   if (ilp <= 1) launch(blend_backward_kernel<1>);
   else if (ilp <= 2) launch(blend_backward_kernel<2>);

@@ -33,6 +33,63 @@ __device__ __forceinline__ float dot3a(float a0, float b0, float a1, float b1, f
   return fadd(dot3(a0, b0, a1, b1, a2, b2), c);
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Sub-block culling (never part of the canonical arithmetic).
+// Exact box-constrained minimum of q(d) = A dx^2 + 2 B dx dy + C dy^2 over the pixel block
+// [bx0,bx1] x [by0,by1] (d = pixel - centre) against the instance's threshold.  The minimiser of a
+// convex quadratic over a box is the centre itself (q = 0) or lies on an edge facing the centre; the
+// two candidates below cover every case.  Returns true if the instance may contribute to the block.
+__device__ __forceinline__ bool cull_hit(const float4 a, const float4 b, float bx0, float bx1, float by0, float by1) {
+  const float A = a.z, B = a.w, C = b.x, thr = b.z;
+  const float u0 = bx0 - a.x, u1 = bx1 - a.x, v0 = by0 - a.y, v1 = by1 - a.y;
+  const float uc = fminf(fmaxf(0.f, u0), u1), vc = fminf(fmaxf(0.f, v0), v1);
+  const float v_e = fminf(fmaxf(-B * uc * rcp_fast(C), v0), v1);   // best v on the edge u = uc
+  const float u_e = fminf(fmaxf(-B * vc * rcp_fast(A), u0), u1);   // best u on the edge v = vc
+  const float q1 = A * uc * uc + 2.f * B * uc * v_e + C * v_e * v_e;
+  const float q2 = A * u_e * u_e + 2.f * B * u_e * vc + C * vc * vc;
+  return !(fminf(q1, q2) > thr);   // NaN-safe: anything unordered counts as a hit
+}
+
+
+// 8-bit mask of the 8x4-pixel sub-blocks of a 16x16 tile an instance may contribute to (bit w =
+// sub-block (w&1, w>>1), the pixel block blend warp w owns).  Computed once per instance by
+// gather_ranges and stored in record[1].w; the blend kernels only test a bit.
+__device__ __forceinline__ uint32_t subblock_mask(const float4 a, const float4 b, int tile_x0, int tile_y0) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const float bx0 = (float)(tile_x0 + ((w & 1) << 3)), by0 = (float)(tile_y0 + ((w >> 1) << 2));
+    if (cull_hit(a, b, bx0, bx0 + 7.f, by0, by0 + 3.f)) m |= 1u << w;
+  }
+  return m;
+}
+
+// Exact division of n < 2^31 by a run-time constant: q = (n * m) >> s with a host-made magic
+// (m = floor(2^(31+k)/d) + 1, k = ceil(log2 d), s = 31 + k); two integer instructions instead of
+// the ~25-instruction emulated 32-bit divide.
+struct FastDiv {
+  uint32_t m, s, d;
+  __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    return (uint32_t)(((uint64_t)n * m) >> s);
+  }
+  __host__ __device__ __forceinline__ uint32_t mod(uint32_t n) const { return n - div(n) * d; }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  if (d == 0) d = 1;
+  uint32_t k = 0;
+  while ((1ull << k) < d) k++;
+  FastDiv f;
+  f.m = (uint32_t)(((1ull << (31 + k)) / d) + 1ull);
+  f.s = 31 + k;
+  f.d = d;
+  return f;
+}
+
 struct Cameras {
   const float *view, *proj, *campos, *tanfov, *bg;
   float tanfovx, tanfovy;

@@ -171,10 +171,11 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
         float pix_x = fmul(ffma(fadd(ppx, 1.0f), (float)W, -1.0f), 0.5f);
         float pix_y = fmul(ffma(fadd(ppy, 1.0f), (float)H, -1.0f), 0.5f);
         float rf = (float)rad;
-        int minx = min(gx, max(0, (int)fdiv(fsub(pix_x, rf), 16.0f)));
-        int miny = min(gy, max(0, (int)fdiv(fsub(pix_y, rf), 16.0f)));
-        int maxx = min(gx, max(0, (int)fdiv(fsub(fadd(fadd(pix_x, rf), 16.0f), 1.0f), 16.0f)));
-        int maxy = min(gy, max(0, (int)fdiv(fsub(fadd(fadd(pix_y, rf), 16.0f), 1.0f), 16.0f)));
+        // x / 16 == x * 0.0625 bit for bit (power of two)
+        int minx = min(gx, max(0, (int)fmul(fsub(pix_x, rf), 0.0625f)));
+        int miny = min(gy, max(0, (int)fmul(fsub(pix_y, rf), 0.0625f)));
+        int maxx = min(gx, max(0, (int)fmul(fsub(fadd(fadd(pix_x, rf), 16.0f), 1.0f), 0.0625f)));
+        int maxy = min(gy, max(0, (int)fmul(fsub(fadd(fadd(pix_y, rf), 16.0f), 1.0f), 0.0625f)));
         int tt = (maxx - minx) * (maxy - miny);
         if (tt != 0) {
           float rgb[3];
@@ -216,8 +217,19 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     if (clamped) clamped[e] = (uint8_t)cbits;
     radii[e] = radius;
     depth_keys[e] = key;
+  }
+  // digit histograms of the depth key: lanes of a warp that share a digit (nearly all of them for
+  // the high bytes: depths of a scene span one or two binades) add once per distinct digit
+  {
+    const uint32_t act = __ballot_sync(0xFFFFFFFFu, i < P);
+    if (i < P) {
 #pragma unroll
-    for (int p = 0; p < 4; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & 255u], 1u);
+      for (int p = 0; p < 4; p++) {
+        const uint32_t dgt = (key >> (8 * p)) & 255u;
+        const uint32_t peers = __match_any_sync(act, dgt);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[p][dgt], (uint32_t)__popc(peers));
+      }
+    }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) {

@@ -58,6 +58,7 @@ class _Workspace:
         self.cap = {}          # (P, V, H, W) -> entries
         self.pinned = torch.zeros(64, 4, dtype=torch.int64).pin_memory()   # 64 slots of GhrStatus
         self.slot = 0
+        self.pending = []      # deferred checks: (row, seq, key, cap, fixed_cap)
 
     def get_temp(self, nbytes: int) -> torch.Tensor:
         if self.temp.numel() < nbytes:
@@ -74,8 +75,32 @@ class _Workspace:
     def next_slot(self):
         self.slot = (self.slot + 1) % self.pinned.shape[0]
         row = self.pinned[self.slot]
+        if any(p[0] is row or p[0].data_ptr() == row.data_ptr() for p in self.pending):
+            self.verify_pending(wait=True)          # the ring wrapped around an unverified report
         row.zero_()
         return row
+
+    def verify_pending(self, wait: bool = False):
+        """check="deferred": look at the status reports of earlier forwards that have arrived (all of
+        them when `wait`); raises if one overflowed its capacity (its outputs were invalid)."""
+        keep = []
+        for row, seq, key, cap, fixed in self.pending:
+            if int(row[2]) != seq:
+                if not wait:
+                    keep.append((row, seq, key, cap, fixed))
+                    continue
+                torch.cuda.synchronize(self.device)
+                if int(row[2]) != seq:
+                    raise RuntimeError("ghr_forward: status report never arrived")
+            R, overflow = int(row[0]), int(row[1]) & 0xFFFFFFFF
+            if not fixed and key in self.cap:
+                self.cap[key] = max(self.cap[key], int(R * 1.5) + (1 << 14))
+            if overflow:
+                self.pending = []
+                raise RuntimeError(f"ghr_forward (deferred check): an earlier forward produced {R} instances, more "
+                                   f"than its capacity {cap}; its outputs were invalid. Re-run it (the capacity "
+                                   f"has been raised) or use check='poll'.")
+        self.pending = keep
 
 
 _ws_lock = threading.Lock()
@@ -150,8 +175,11 @@ class ForwardResult(NamedTuple):
 def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
                 scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
                 R_cap: Optional[int] = None, stage_events=None, want_mask: bool = False) -> ForwardResult:
-    """Enqueue one libghr forward (V views).  check: "poll" (exact, re-runs on overflow),
-    "none" (caller checks GhrStatus later; needed under CUDA-graph capture)."""
+    """Enqueue one libghr forward (V views).  check: "poll" (exact: the host waits for the instance
+    count, which arrives while the GPU is still sorting/blending, and re-runs on overflow),
+    "deferred" (no host wait: the report is verified at the next call on this stream or by
+    check_deferred(); an overflow raises there), "none" (caller checks GhrStatus itself; needed
+    under CUDA-graph capture)."""
     L = N.lib()
     dev = means3D.device
     stream = torch.cuda.current_stream(dev)
@@ -159,6 +187,8 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
     P = means3D.shape[0]
     M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
     key = (P, cams.V, cams.H, cams.W)
+    if ws.pending:
+        ws.verify_pending()
     cap = int(R_cap) if R_cap is not None else ws.capacity(key, P, cams.V)
     while True:
         lay = N.layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
@@ -184,11 +214,13 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
         row = None
         seq = next(_seq)
         a.seq = seq
-        if check == "poll":
+        if check in ("poll", "deferred"):
             row = ws.next_slot()
             a.host_status = row.data_ptr()
         N.check(L.ghr_forward(C.byref(a), stream.cuda_stream), "ghr_forward")
         R = None
+        if check == "deferred":
+            ws.pending.append((row, seq, key, cap, R_cap is not None))
         if check == "poll":
             t0 = time.perf_counter()
             while int(row[2]) != seq:           # reserved[0]
@@ -206,6 +238,15 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
                 cap = ws.cap[key]
                 continue
         return ForwardResult(color, mask, radii[:, :P], state, cap, R, dbg)
+
+
+def check_deferred(device=None):
+    """Verify every outstanding check="deferred" forward on `device` (synchronises it)."""
+    with _ws_lock:
+        wss = list(_workspaces.items())
+    for (dev_index, _), ws in wss:
+        if device is None or torch.device(device).index in (None, dev_index):
+            ws.verify_pending(wait=True)
 
 
 def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, scales, rotations, cov3D, shs,
@@ -420,13 +461,13 @@ class ViewBatch(NamedTuple):
 class _RasterizeViews(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, views: ViewBatch,
-                want_mask: bool):
+                want_mask: bool, check: str = "poll"):
         _require_cuda(means3D, opacities, views.viewmatrix)
         cams = views.cams()
         means3D_c, opac_c = _f32c(means3D), _f32c(opacities)
         sh_c, col_c, sc_c, rot_c, cov_c = _opt(sh), _opt(colors_precomp), _opt(scales), _opt(rotations), _opt(cov3Ds_precomp)
         res = forward_raw(cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(views.sh_degree),
-                          float(views.scale_modifier), want_mask=want_mask)
+                          float(views.scale_modifier), want_mask=want_mask, check=check)
         ctx.cams, ctx.views, ctx.R_cap, ctx.want_mask = cams, views, res.R_cap, want_mask
         z = torch.empty(0)
         ctx.save_for_backward(means3D_c, opac_c, sc_c if sc_c is not None else z, rot_c if rot_c is not None else z,
@@ -450,18 +491,21 @@ class _RasterizeViews(torch.autograd.Function):
         return (g["dL_dmeans3D"] if need[0] else None, g.get("dL_dsh") if need[1] else None,
                 g.get("dL_dcolors") if need[2] else None, g["dL_dopacity"].view(P, -1) if need[3] else None,
                 g.get("dL_dscales") if need[4] else None, g.get("dL_drotations") if need[5] else None,
-                g["dL_dcov3D"] if need[6] else None, None, None)
+                g["dL_dcov3D"] if need[6] else None, None, None, None)
 
 
 def rasterize_views(means3D, opacities, views: ViewBatch, shs=None, colors_precomp=None, scales=None,
-                    rotations=None, cov3D_precomp=None, return_mask: bool = False):
+                    rotations=None, cov3D_precomp=None, return_mask: bool = False, check: str = "poll"):
     """Render V views of one Gaussian set in a single launch chain.
     Returns (color [V,3,H,W], radii [V,P]) -- or (color, mask [V,H,W], radii) with return_mask --
     differentiable w.r.t. the Gaussian attributes with the gradient summed over views (what the
     per-view Python loop + autograd of the reference yields).
 
     `mask` is the coverage 1 - T_final of the SAME pass: what the reference obtains from a second
-    rasterizer call with colors = 1 and bg = 0 (renderer_one_shot.py:353-380), at no extra render."""
+    rasterizer call with colors = 1 and bg = 0 (renderer_one_shot.py:353-380), at no extra render.
+
+    check="deferred" removes the one host wait of a call (for pipelined loops that keep several steps
+    in flight): the instance-capacity report is verified at the next call / by check_deferred()."""
     if (shs is None) == (colors_precomp is None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
@@ -469,5 +513,5 @@ def rasterize_views(means3D, opacities, views: ViewBatch, shs=None, colors_preco
         raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
     e = lambda t: torch.Tensor([]) if t is None else t
     color, mask, radii = _RasterizeViews.apply(means3D, e(shs), e(colors_precomp), opacities, e(scales),
-                                               e(rotations), e(cov3D_precomp), views, bool(return_mask))
+                                               e(rotations), e(cov3D_precomp), views, bool(return_mask), check)
     return (color, mask, radii) if return_mask else (color, radii)

@@ -64,6 +64,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->pub.off_final_T = o;  o = align_up(o + VN * 4);
   L->pub.off_ncontrib = o; o = align_up(o + VN * 4);
   L->pub.off_order = o;    o = align_up(o + VT * 4);
+  L->pub.off_masks = o;    o = align_up(o + (size_t)d.R_cap + 64);
   L->pub.state_bytes = o;
 
   // ---- temp (forward): zeroed prefix first ----

@@ -188,68 +188,50 @@ scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, 
   }
 }
 
-// 64 sorted instances per block iteration.  Phase 1: four threads per instance test two 8x4
-// sub-blocks each of the instance's tile against its alpha >= 1/255 ellipse (exact box minimum,
-// cull_hit) and combine the 8-bit mask with two shuffles.  Phase 2: three threads per instance (one
-// per float4 of the 48-byte record) copy the geometry record into sorted order: consecutive lanes
-// read consecutive 16-byte chunks of a record and write consecutive chunks of the sorted slab
-// (coalesced 128-bit stores); the mask rides in record[1].w.
-constexpr int kGatherInst = 64;
-__global__ void __launch_bounds__(4 * kGatherInst)
-gather_ranges_kernel(FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap, const GhrStatus *__restrict__ status,
-                     const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tvals,
-                     const float4 *__restrict__ geom, float4 *__restrict__ records, uint2 *__restrict__ ranges,
+// One launch, two kinds of blocks, no block-level synchronisation:
+//   copy blocks (blockIdx.x < nb_copy): three threads per sorted instance, one per float4 of the
+//     48-byte record: consecutive lanes read consecutive 16-byte chunks of a geometry record and
+//     write consecutive chunks of the sorted slab (coalesced stores); they also mark tile ranges.
+//   mask blocks: one thread per sorted instance computes the 8-bit mask of 8x4 sub-blocks of its
+//     tile the alpha >= 1/255 ellipse reaches (subblock_mask) into the compact byte array the blend
+//     kernels stage next to the records (coalesced 1-byte stores).
+constexpr int kGatherThreads = 384;
+__global__ void __launch_bounds__(kGatherThreads)
+gather_ranges_kernel(int nb_copy, FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap,
+                     const GhrStatus *__restrict__ status, const uint32_t *__restrict__ tkeys,
+                     const uint32_t *__restrict__ tvals, const float4 *__restrict__ geom,
+                     float4 *__restrict__ records, uint8_t *__restrict__ masks, uint2 *__restrict__ ranges,
                      uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
-  __shared__ uint32_t s_mask[kGatherInst];
   uint64_t R = status->R;
   if (R > R_cap) R = R_cap;
-  const uint32_t tid = threadIdx.x;
-  for (uint64_t base = (uint64_t)blockIdx.x * kGatherInst; base < R; base += (uint64_t)gridDim.x * kGatherInst) {
-    {
-      const uint64_t r = base + (tid >> 2);
-      const uint32_t sub = tid & 3u;
-      uint32_t m = 0;
-      if (r < R) {
-        const uint32_t g = tvals[r];
-        const uint32_t tile = dT.mod(tkeys[r]);
-        const float4 q0 = geom[4 * (size_t)g], q1 = geom[4 * (size_t)g + 1];
-        const uint32_t ty = dgx.div(tile);
-        const int x0 = (int)(tile - ty * dgx.d) * kTile, y0 = (int)ty * kTile;
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-          const uint32_t w = 2 * sub + k;
-          const float bx0 = (float)(x0 + (int)((w & 1u) << 3)), by0 = (float)(y0 + (int)((w >> 1) << 2));
-          if (cull_hit(q0, q1, bx0, bx0 + 7.f, by0, by0 + 3.f)) m |= 1u << w;
-        }
-      }
-      m |= __shfl_xor_sync(0xFFFFFFFFu, m, 1);
-      m |= __shfl_xor_sync(0xFFFFFFFFu, m, 2);
-      if (sub == 0) s_mask[tid >> 2] = m;
+  if ((int)blockIdx.x >= nb_copy) {
+    const uint64_t stride = (uint64_t)(gridDim.x - nb_copy) * kGatherThreads;
+    for (uint64_t r = (uint64_t)(blockIdx.x - nb_copy) * kGatherThreads + threadIdx.x; r < R; r += stride) {
+      const uint32_t g = tvals[r];
+      const uint32_t tile = dT.mod(tkeys[r]);
+      const uint32_t ty = dgx.div(tile);
+      masks[r] = (uint8_t)subblock_mask(geom[4 * (size_t)g], geom[4 * (size_t)g + 1],
+                                        (int)(tile - ty * dgx.d) * kTile, (int)ty * kTile);
     }
-    __syncthreads();
-    if (tid < 3 * kGatherInst) {
-      const uint32_t li = tid / 3u, part = tid % 3u;
-      const uint64_t r = base + li;
-      if (r < R) {
-        const uint32_t g = tvals[r];
-        float4 q = geom[4 * (size_t)g + part];
-        const uint32_t id = dP.mod(g);
-        if (part == 2) {
-          if (dbg_keys) dbg_keys[r] = ((uint64_t)dT.mod(tkeys[r]) << 32) | __float_as_uint(q.w);
-          q.w = __uint_as_float(id);
-        } else if (part == 1) {
-          q.w = __uint_as_float(s_mask[li]);
-        }
-        records[3 * r + part] = q;
-        if (part == 0) {
-          const uint32_t tk = tkeys[r];
-          if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
-          if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
-          if (dbg_plist) dbg_plist[r] = id;
-        }
-      }
+    return;
+  }
+  const uint32_t li = threadIdx.x / 3u, part = threadIdx.x - 3u * li;
+  const uint64_t stride = (uint64_t)nb_copy * (kGatherThreads / 3);
+  for (uint64_t r = (uint64_t)blockIdx.x * (kGatherThreads / 3) + li; r < R; r += stride) {
+    const uint32_t g = tvals[r];
+    float4 q = geom[4 * (size_t)g + part];
+    const uint32_t id = dP.mod(g);
+    if (part == 2) {
+      if (dbg_keys) dbg_keys[r] = ((uint64_t)dT.mod(tkeys[r]) << 32) | __float_as_uint(q.w);
+      q.w = __uint_as_float(id);
     }
-    __syncthreads();
+    records[3 * r + part] = q;
+    if (part == 0) {
+      const uint32_t tk = tkeys[r];
+      if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
+      if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
+      if (dbg_plist) dbg_plist[r] = id;
+    }
   }
 }
 
@@ -279,13 +261,16 @@ cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state,
                                  uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s) {
   if (d.R_cap <= 0) return cudaSuccess;
   int buf = tile_sorted_buf(L);
-  uint64_t want = ((uint64_t)d.R_cap + kGatherInst - 1) / kGatherInst;
-  int nb = (int)(want < (uint64_t)(148 * 16) ? want : (uint64_t)(148 * 16));
-  gather_ranges_kernel<<<nb, 4 * kGatherInst, 0, s>>>(make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
+  const uint64_t kMax = 148 * 8;
+  uint64_t want_c = ((uint64_t)d.R_cap + kGatherThreads / 3 - 1) / (kGatherThreads / 3);
+  uint64_t want_m = ((uint64_t)d.R_cap + kGatherThreads - 1) / kGatherThreads;
+  int nb_copy = (int)(want_c < kMax ? want_c : kMax), nb_mask = (int)(want_m < kMax ? want_m : kMax);
+  gather_ranges_kernel<<<nb_copy + nb_mask, kGatherThreads, 0, s>>>(nb_copy, make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
                                           (const uint32_t *)(temp + L.t_tkeys[buf]),
                                           (const uint32_t *)(temp + L.t_tvals[buf]),
                                           (const float4 *)(state + L.pub.off_geom),
                                           (float4 *)(state + L.pub.off_records),
+                                          (uint8_t *)(state + L.pub.off_masks),
                                           (uint2 *)(state + L.pub.off_ranges), dbg_keys, dbg_plist);
   return cudaGetLastError();
 }

@@ -26,7 +26,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr int kMaxIlpB = 2;
-constexpr int kDirectMax = 3;    // <= this many contributing lanes: no warp reduction, direct REDs
+constexpr int kDirectMax = 8;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,13 +66,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
   } while (!ok);
 }
 
+constexpr int kMaskBytes = kStageN + 16;   // a stage's mask bytes start at a 16-byte boundary at or before it
 struct __align__(128) StageBuf {
   float4 rec[kStages][kStageN * 3];
+  uint8_t msk[kStages][kMaskBytes];
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint32_t done_warps;
   uint32_t stop_round;
 };
+
+// Producer side of one stage: the contiguous record slab plus the 16-byte-aligned window of the
+// mask byte array that covers the same instances, both completing on the stage's full barrier.
+__device__ __forceinline__ void stage_load(StageBuf &sb, int s, const float4 *records, const uint8_t *masks,
+                                           size_t first, uint32_t cnt) {
+  const size_t m0 = first & ~(size_t)15;
+  const uint32_t mbytes = (uint32_t)(((first + cnt + 15) & ~(size_t)15) - m0);
+  mbar_expect_tx(&sb.full[s], cnt * kRecBytes + mbytes);
+  bulk_g2s(&sb.rec[s][0], records + 3 * first, cnt * kRecBytes, &sb.full[s]);
+  bulk_g2s(&sb.msk[s][0], masks + m0, mbytes, &sb.full[s]);
+}
 
 __device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
   if (tid == 0) {
@@ -105,11 +118,11 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
 }
 
 // Survivor queue of one warp for one stage: the indices (inside the stage, ascending) of the
-// instances whose sub-block mask (record[1].w, written by gather_ranges) has this warp's bit set.
-// Each lane tests 4 instances (one 32-bit LDS each), 4 ballots compact them; the blend loop then
+// instances whose sub-block mask (one byte per instance, written by gather_ranges) has this warp's
+// bit set.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the blend loop then
 // takes kIlp indices per iteration from one broadcast LDS instead of peeling bits off a mask.
 // Survivor i is q[kQPad + i]; kQPad entries of index 0 pad both ends.  Returns the survivor count.
-__device__ __forceinline__ uint32_t build_queue(const float4 *rec, uint32_t cnt, uint32_t limit, int warp, int lane,
+__device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt, uint32_t limit, int warp, int lane,
                                                 uint8_t *q) {
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t total = 0;
@@ -117,7 +130,7 @@ __device__ __forceinline__ uint32_t build_queue(const float4 *rec, uint32_t cnt,
   for (int w = 0; w < kStageN / 32; w++) {
     const uint32_t e = w * 32 + lane;
     bool hit = false;
-    if (e < cnt && e < limit) hit = (__float_as_uint(rec[3 * e + 1].w) >> warp) & 1u;
+    if (e < cnt && e < limit) hit = (msk[e] >> warp) & 1u;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
     if (hit) q[kQPad + total + __popc(m & lt)] = (uint8_t)e;
     total += __popc(m);
@@ -132,7 +145,7 @@ template <int kIlpF>
 __global__ void __launch_bounds__(kBlendThreads, kIlpF <= 4 ? 4 : 3)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
-                     float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+                     const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float *__restrict__ out_color,
                      float *__restrict__ out_mask) {
   __shared__ StageBuf sb;
@@ -164,7 +177,6 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     return;
   }
   const uint32_t rounds = (n + kStageN - 1) / kStageN;
-  const float4 *src = records + 3 * (size_t)range.x;
   stage_init(sb, tid);
 
   if (warp == kConsumerWarps) {
@@ -180,8 +192,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
           break;
         }
         const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
-        mbar_expect_tx(&sb.full[s], cnt * kRecBytes);
-        bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)r * kStageN, cnt * kRecBytes, &sb.full[s]);
+        stage_load(sb, s, records, masks, (size_t)range.x + (size_t)r * kStageN, cnt);
       }
     }
     return;
@@ -209,7 +220,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     if (!wdone) {
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const float4 *rec = &sb.rec[s][0];
-      const uint32_t total = build_queue(rec, cnt, kStageN, warp, lane, q);
+      const uint32_t total = build_queue(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, kStageN, warp, lane, q);
       for (uint32_t b = 0; b < total; b += kIlpF) {
         // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
         // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
@@ -300,7 +311,8 @@ template <int kIlpB>
 __global__ void __launch_bounds__(kBlendThreads, kIlpB <= 1 ? 5 : (kIlpB <= 2 ? 4 : (kIlpB <= 3 ? 3 : 2)))
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uint32_t *__restrict__ order,
                       const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
-                      const float *__restrict__ final_T, const uint32_t *__restrict__ n_contrib,
+                      const uint8_t *__restrict__ masks, const float *__restrict__ final_T,
+                      const uint32_t *__restrict__ n_contrib,
                       const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
                       const float *__restrict__ dL_dmask, float *__restrict__ acc, int direct_max) {
   __shared__ StageBuf sb;
@@ -316,7 +328,6 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
   const uint2 range = ranges[vt];
   const uint32_t n = min(range.y - range.x, maxc);     // instances past the last contributor never matter
   const uint32_t rounds = (n + kStageN - 1) / kStageN;
-  const float4 *src = records + 3 * (size_t)range.x;
   stage_init(sb, tid);
 
   if (warp == kConsumerWarps) {
@@ -327,8 +338,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
         if (k >= kStages) mbar_wait(&sb.empty[s], ((k / kStages) - 1) & 1);
         const uint32_t rr = rounds - 1 - k;
         const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
-        mbar_expect_tx(&sb.full[s], cnt * kRecBytes);
-        bulk_g2s(&sb.rec[s][0], src + 3 * (size_t)rr * kStageN, cnt * kRecBytes, &sb.full[s]);
+        stage_load(sb, s, records, masks, (size_t)range.x + (size_t)rr * kStageN, cnt);
       }
     }
     return;
@@ -375,7 +385,8 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uin
       const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
       const float4 *rec = &sb.rec[s][0];
       // survivors of this warp's sub-block among the instances that precede the warp's last contributor
-      const uint32_t total = build_queue(rec, cnt, wlast - rr * kStageN, warp, lane, q);
+      const uint32_t total =
+          build_queue(&sb.msk[s][(range.x + rr * kStageN) & 15u], cnt, wlast - rr * kStageN, warp, lane, q);
       {
         for (int b = (int)total; b > 0; b -= kIlpB) {
           // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets; back to front
@@ -508,12 +519,13 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                  float *out_color, float *out_mask, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
-  static const int ilp = env_int("GHR_ILPF", 4);
+  static const int ilp = env_int("GHR_ILPF", 8);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
                                 (const uint2 *)(state + L.pub.off_ranges),
-                                (const float4 *)(state + L.pub.off_records), (float *)(state + L.pub.off_final_T),
+                                (const float4 *)(state + L.pub.off_records),
+                                (const uint8_t *)(state + L.pub.off_masks), (float *)(state + L.pub.off_final_T),
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
                                 out_color, out_mask);
   };
@@ -533,6 +545,7 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
                                 (const uint2 *)(state + L.pub.off_ranges),
                                 (const float4 *)(state + L.pub.off_records),
+                                (const uint8_t *)(state + L.pub.off_masks),
                                 (const float *)(state + L.pub.off_final_T),
                                 (const uint32_t *)(state + L.pub.off_ncontrib),
                                 (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc, direct);

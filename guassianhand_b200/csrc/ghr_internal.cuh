@@ -58,13 +58,38 @@ __device__ __forceinline__ bool cull_hit(const float4 a, const float4 b, float b
 
 // 8-bit mask of the 8x4-pixel sub-blocks of a 16x16 tile an instance may contribute to (bit w =
 // sub-block (w&1, w>>1), the pixel block blend warp w owns).  Computed once per instance by
-// gather_ranges and stored in record[1].w; the blend kernels only test a bit.
+// gather_ranges and stored in record[1].w; the blend kernels only test a bit.  Same test as
+// cull_hit for each of the 8 sub-blocks, with the per-column / per-row parts shared (2 columns x 4
+// rows): ~11 instructions per sub-block.
 __device__ __forceinline__ uint32_t subblock_mask(const float4 a, const float4 b, int tile_x0, int tile_y0) {
+  const float A = a.z, B = a.w, C = b.x, thr = b.z;
+  if (!(thr >= 0.f)) return 0u;          // opacity < 1/255: never contributes
+  if (thr > 1e37f) return 0xFFu;         // ill-conditioned conic: never culled
+  const float k1 = -B * rcp_fast(C), k2 = -B * rcp_fast(A), B2 = 2.f * B;
+  float u0[2], u1[2], Auc2[2], Buc[2], vun[2];
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    u0[c] = (float)(tile_x0 + 8 * c) - a.x;
+    u1[c] = u0[c] + 7.f;
+    const float uc = fminf(fmaxf(0.f, u0[c]), u1[c]);
+    Auc2[c] = A * uc * uc;
+    Buc[c] = B2 * uc;
+    vun[c] = k1 * uc;                    // unconstrained best v on the edge u = uc
+  }
   uint32_t m = 0;
 #pragma unroll
-  for (int w = 0; w < 8; w++) {
-    const float bx0 = (float)(tile_x0 + ((w & 1) << 3)), by0 = (float)(tile_y0 + ((w >> 1) << 2));
-    if (cull_hit(a, b, bx0, bx0 + 7.f, by0, by0 + 3.f)) m |= 1u << w;
+  for (int j = 0; j < 4; j++) {
+    const float v0 = (float)(tile_y0 + 4 * j) - a.y, v1 = v0 + 3.f;
+    const float vc = fminf(fmaxf(0.f, v0), v1);
+    const float Cvc2 = C * vc * vc, Bvc = B2 * vc, uun = k2 * vc;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const float v_e = fminf(fmaxf(vun[c], v0), v1);
+      const float u_e = fminf(fmaxf(uun, u0[c]), u1[c]);
+      const float q1 = fmaf(fmaf(C, v_e, Buc[c]), v_e, Auc2[c]);
+      const float q2 = fmaf(fmaf(A, u_e, Bvc), u_e, Cvc2);
+      if (!(fminf(q1, q2) > thr)) m |= 1u << (2 * j + c);
+    }
   }
   return m;
 }

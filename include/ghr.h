@@ -41,7 +41,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 4
+#define GHR_ABI_VERSION 5
 
 /* stage ids for the optional stage_events arrays */
 #define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges+schedule, 5 blend */
@@ -73,6 +73,8 @@ typedef struct GhrLayout {
   size_t off_final_T;  /* float per (view, pixel) */
   size_t off_ncontrib; /* uint32 per (view, pixel) */
   size_t off_order;    /* uint32 per (view, tile): blend launch order, longest instance list first */
+  size_t off_masks;    /* uint8 per sorted instance: bit w set if the instance can reach alpha >= 1/255
+                          inside the 8x4-pixel sub-block w = 2*(row/4) + (col/8) of its tile (culling only) */
 } GhrLayout;
 
 typedef struct GhrStatus {

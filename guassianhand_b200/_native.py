@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 5
+GHR_ABI_VERSION = 6
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 6, 2
 FWD_STAGES = ["preprocess", "depth_sort", "scan_duplicate", "tile_sort", "gather_ranges", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
@@ -31,7 +31,8 @@ class GhrDims(C.Structure):
 class GhrLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "state_bytes", "temp_bytes", "temp_bwd_bytes", "off_status", "off_geom", "off_clamped", "off_ranges",
-        "off_tilemax", "off_records", "off_final_T", "off_ncontrib", "off_order", "off_masks")]
+        "off_tilemax", "off_records", "off_final_T", "off_ncontrib", "off_order", "off_masks", "off_tilefinal",
+        "off_ckpt", "off_units")]
 
 
 class GhrStatus(C.Structure):

@@ -74,6 +74,7 @@ struct __align__(128) StageBuf {
   uint64_t empty[kStages];
   uint32_t done_warps;
   uint32_t stop_round;
+  uint32_t tmax;          // max n_contrib of the tile (forward)
 };
 
 // Producer side of one stage: the contiguous record slab plus the 16-byte-aligned window of the
@@ -95,6 +96,7 @@ __device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
     }
     sb.done_warps = 0;
     sb.stop_round = 0xFFFFFFFFu;
+    sb.tmax = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -146,7 +148,8 @@ __global__ void __launch_bounds__(kBlendThreads, kIlpF <= 4 ? 4 : 3)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
-                     uint32_t *__restrict__ tilemax, float *__restrict__ out_color,
+                     uint32_t *__restrict__ tilemax, float4 *__restrict__ tilefinal, float4 *__restrict__ ckpt,
+                     uint2 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
                      float *__restrict__ out_mask) {
   __shared__ StageBuf sb;
   __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
@@ -218,6 +221,10 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 512u : 32u);
     if (r >= *(volatile uint32_t *)&sb.stop_round) break;
     if (!wdone) {
+      // running state at every kSeg-instance boundary: the backward restarts from it (one work unit per
+      // segment).  A warp whose pixels have all terminated writes nothing: no later unit reads it.
+      if (r > 0 && (r * kStageN) % kSeg == 0)
+        ckpt[((size_t)(range.x / kSeg) + vt + (r * kStageN) / kSeg) * 256 + tid] = make_float4(Tr, C0, C1, C2);
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const float4 *rec = &sb.rec[s][0];
       const uint32_t total = build_queue(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, kStageN, warp, lane, q);
@@ -277,8 +284,23 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     o[2 * N] = ffma(Tr, bg[2], C2);
     if (out_mask) out_mask[(size_t)v * N + pix] = 1.0f - Tr;   // = sum_j alpha_j T_j
   }
-  uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
-  if (lane == 0 && wmax) atomicMax(&tilemax[vt], wmax);
+  tilefinal[(size_t)vt * 256 + tid] = make_float4(C0, C1, C2, Tr);
+  // backward work units of this tile: one per kSeg instances up to the tile's last contributor
+  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
+  if (lane == 0 && wmax) atomicMax(&sb.tmax, wmax);
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+  if (warp == 0) {
+    const uint32_t tmax = sb.tmax, nseg = (tmax + kSeg - 1) / kSeg;
+    if (nseg) {
+      uint32_t base = 0;
+      if (lane == 0) {
+        tilemax[vt] = tmax;
+        base = (uint32_t)atomicAdd((unsigned long long *)&status->reserved[1], (unsigned long long)nseg);
+      }
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      for (uint32_t i = lane; i < nseg; i += 32) units[base + i] = make_uint2(vt, i);
+    }
+  }
 }
 
 // Warp reduction of 9 values per lane through shared memory: lane L stores its 9 partials as row L
@@ -307,171 +329,165 @@ __device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
   return sum + s1 + s2;
 }
 
+// Backward blend: one CTA per work unit = (view, tile, segment of kSeg instances), emitted by the
+// forward.  Each unit restarts the per-pixel recursion from the forward's checkpoint at the segment
+// start and walks the segment FRONT TO BACK, so units of one tile are independent: the launch has
+// R/kSeg uniform units instead of one CTA per tile (no heavy-tile tail, and a single view fills the
+// GPU).  With T_j the transmittance in front of contributor j, w_j = alpha_j T_j and
+//   D_j = sum_{k>j} (c_k . dL/dpix) w_k          (colour still to come behind j, from C_total - C_prefix)
+// upstream's  dL/dalpha_j = T_j (c_j - A_j).dL/dpix - T_final/(1-alpha_j) bg.dL/dpix  (A_j = suffix colour
+// normalised by T_{j+1}) becomes  T_j (c_j.dL/dpix) - (D_j + T_final bg.dL/dpix) / (1-alpha_j):  two scalar
+// recurrences (T, D) instead of the back-to-front vector one, and T replays the forward's products exactly.
+constexpr int kUnitThreads = kConsumerWarps * 32;
 template <int kIlpB>
-__global__ void __launch_bounds__(kBlendThreads, kIlpB <= 1 ? 5 : (kIlpB <= 2 ? 4 : (kIlpB <= 3 ? 3 : 2)))
-blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const uint32_t *__restrict__ order,
-                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
-                      const uint8_t *__restrict__ masks, const float *__restrict__ final_T,
-                      const uint32_t *__restrict__ n_contrib,
-                      const uint32_t *__restrict__ tilemax, const float *__restrict__ dL_dout,
-                      const float *__restrict__ dL_dmask, float *__restrict__ acc, int direct_max) {
-  __shared__ StageBuf sb;
+__global__ void __launch_bounds__(kUnitThreads, 4)
+blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const GhrStatus *__restrict__ status,
+                      const uint2 *__restrict__ units, const uint2 *__restrict__ ranges,
+                      const float4 *__restrict__ records, const uint8_t *__restrict__ masks,
+                      const float4 *__restrict__ tilefinal, const float4 *__restrict__ ckpt,
+                      const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tilemax,
+                      const float *__restrict__ dL_dout, const float *__restrict__ dL_dmask,
+                      float *__restrict__ acc, int direct_max) {
   constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
+  __shared__ __align__(128) float4 s_rec[kSeg * 3];
+  __shared__ __align__(16) uint8_t s_msk[kSeg + 16];
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ float s_red[kConsumerWarps][kRedBufs][32 * 9];
   __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
-  const uint32_t vt = order[blockIdx.x];
-  const uint32_t maxc = tilemax[vt];
-  if (maxc == 0) return;
+  if (blockIdx.x >= (uint32_t)status->reserved[1]) return;
+  const uint2 unit = units[blockIdx.x];
+  const uint32_t vt = unit.x, first = unit.y * kSeg;      // first = position of the segment in the tile list
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
   const uint2 range = ranges[vt];
-  const uint32_t n = min(range.y - range.x, maxc);     // instances past the last contributor never matter
-  const uint32_t rounds = (n + kStageN - 1) / kStageN;
-  stage_init(sb, tid);
+  const uint32_t n = min(range.y - range.x, tilemax[vt]);  // instances past the last contributor never matter
+  const uint32_t cnt = min((uint32_t)kSeg, n - first);
+  const size_t g0 = (size_t)range.x + first;
 
-  if (warp == kConsumerWarps) {
-    // producer: step k streams round (rounds-1-k), back to front
-    if (lane == 0) {
-      for (uint32_t k = 0; k < rounds; k++) {
-        const int s = k % kStages;
-        if (k >= kStages) mbar_wait(&sb.empty[s], ((k / kStages) - 1) & 1);
-        const uint32_t rr = rounds - 1 - k;
-        const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
-        stage_load(sb, s, records, masks, (size_t)range.x + (size_t)rr * kStageN, cnt);
-      }
-    }
-    return;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+    const size_t m0 = g0 & ~(size_t)15;
+    const uint32_t mbytes = (uint32_t)(((g0 + cnt + 15) & ~(size_t)15) - m0);
+    mbar_expect_tx(&s_bar, cnt * kRecBytes + mbytes);
+    bulk_g2s(s_rec, records + 3 * g0, cnt * kRecBytes, &s_bar);
+    bulk_g2s(s_msk, masks + m0, mbytes, &s_bar);
   }
+  uint8_t *q = &s_q[warp][0];
+  if (lane < kQPad) q[lane] = 0;
 
+  // per-pixel state while the segment is in flight
   int lx, ly;
   pixel_of_thread(tid, lx, ly);
   const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  uint8_t *q = &s_q[warp][0];
-  if (lane < kQPad) q[lane] = 0;
-
-  float T_final = 0.f, dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f;
+  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLm = 0.f;
   uint32_t last = 0;
   if (inside) {
-    size_t pix = (size_t)py * W + px;
-    T_final = final_T[(size_t)v * N + pix];
+    const size_t pix = (size_t)py * W + px;
     last = n_contrib[(size_t)v * N + pix];
     const float *g = dL_dout + (size_t)v * 3 * N + pix;
     dLp0 = g[0];
     dLp1 = g[N];
     dLp2 = g[2 * N];
+    if (dL_dmask) dLm = dL_dmask[(size_t)v * N + pix];
   }
-  const float *bg = cam.bg + (size_t)cam.bg_stride * v;
-  float bgdot = bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2;
-  // coverage output m = 1 - T_final: dm/dalpha_j = +T_final/(1-alpha_j), the background term with
-  // the opposite sign, so its gradient folds into bgdot
-  if (dL_dmask && inside) bgdot -= dL_dmask[(size_t)v * N + (size_t)py * W + px];
-  float Tr = T_final;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
-
-  // lanes 0..8 own the warp totals of the 9 accumulated values
-  const bool owner = lane < 9;
+  float Tr = 0.f, Drem = 0.f, Tb = 0.f;
+  if (last > first) {
+    const float4 fin = tilefinal[(size_t)vt * 256 + tid];
+    float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+    if (first) c = ckpt[((size_t)(range.x / kSeg) + vt + unit.y) * 256 + tid];
+    Tr = c.x;
+    Drem = (fin.x - c.y) * dLp0 + (fin.y - c.z) * dLp1 + (fin.z - c.w) * dLp2;
+    const float *bg = cam.bg + (size_t)cam.bg_stride * v;
+    // coverage output m = 1 - T_final: dm/dalpha_j = +T_final/(1-alpha_j), the background term with
+    // the opposite sign, so its gradient folds into the same product
+    Tb = fin.w * (bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2 - dLm);
+  }
+  const bool owner = lane < 9;      // lanes 0..8 own the warp totals of the 9 accumulated values
   float *accb = acc + (size_t)v * P * kAccStride;
   const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
+  __syncthreads();                  // barrier initialised before anyone polls it
+  if (wlast <= first) return;
+  mbar_wait(&s_bar, 0);
 
-  for (uint32_t k = 0; k < rounds; k++) {
-    const int s = k % kStages;
-    const uint32_t rr = rounds - 1 - k;
-    mbar_wait(&sb.full[s], (k / kStages) & 1, rr * kStageN < wlast ? 32u : 512u);
-    if (rr * kStageN < wlast) {
-      const uint32_t cnt = min((uint32_t)kStageN, n - rr * kStageN);
-      const float4 *rec = &sb.rec[s][0];
-      // survivors of this warp's sub-block among the instances that precede the warp's last contributor
-      const uint32_t total =
-          build_queue(&sb.msk[s][(range.x + rr * kStageN) & 15u], cnt, wlast - rr * kStageN, warp, lane, q);
-      {
-        for (int b = (int)total; b > 0; b -= kIlpB) {
-          // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets; back to front
-          int jj[kIlpB];
-          float al[kIlpB], Gk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB];
-          float4 col[kIlpB];
+  for (uint32_t sub = 0; sub * kStageN < cnt; sub++) {
+    const uint32_t pos0 = first + sub * kStageN;
+    if (pos0 >= wlast) break;
+    const uint32_t scnt = min((uint32_t)kStageN, cnt - sub * kStageN);
+    const float4 *rec = s_rec + 3 * sub * kStageN;
+    // survivors of this warp's sub-block among the instances that precede the warp's last contributor
+    const uint32_t total = build_queue(&s_msk[(g0 & 15u) + sub * kStageN], scnt, wlast - pos0, warp, lane, q);
+    for (uint32_t b = 0; b < total; b += kIlpB) {
+      // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
+      float al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB], cdk[kIlpB];
+      uint32_t idk[kIlpB];
 #pragma unroll
-          for (int k = 0; k < kIlpB; k++) {
-            const bool ok = b - 1 - k >= 0;
-            jj[k] = q[kQPad + b - 1 - k];                       // front pad (index 0) when !ok
-            const uint32_t e = rr * kStageN + (uint32_t)jj[k];  // position in the tile list
-            const float4 a = rec[3 * jj[k]], bq = rec[3 * jj[k] + 1];
-            col[k] = rec[3 * jj[k] + 2];
-            float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-            float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
-            float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
-            float G = exp_fast(power);
-            float alpha = fminf(0.99f, fmul(bq.y, G));
-            const bool c = ok && e < last && power <= 0.0f && alpha >= kAlphaMin;
-            al[k] = c ? alpha : 0.f;
-            Gk[k] = G;
-            rck[k] = rcp_fast(1.f - alpha);
-            dxk[k] = dx;
-            dyk[k] = dy;
-          }
-          // phase 2 (serial, short): transmittance / suffix-colour recursion -> 9 partials each
-          float vals[kIlpB][9];
-          bool contrib[kIlpB];
+      for (int k = 0; k < kIlpB; k++) {
+        const uint32_t jj = q[kQPad + b + k];                // tail pad (index 0) when b + k >= total
+        const float4 a = rec[3 * jj], bq = rec[3 * jj + 1], col = rec[3 * jj + 2];
+        const float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
+        const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
+        const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
+        const float G = exp_fast(power);
+        const float alpha = fminf(0.99f, fmul(bq.y, G));
+        const bool c = b + k < total && pos0 + jj < last && power <= 0.0f && alpha >= kAlphaMin;
+        al[k] = c ? alpha : 0.f;
+        Gk[k] = c ? G : 0.f;
+        omk[k] = fsub(1.f, al[k]);
+        rck[k] = rcp_fast(omk[k]);
+        dxk[k] = dx;
+        dyk[k] = dy;
+        cdk[k] = col.x * dLp0 + col.y * dLp1 + col.z * dLp2;
+        idk[k] = __float_as_uint(col.w);
+      }
+      // phase 2 (serial, short, branch-free: a rejected pair has alpha = G = 0 and adds zeros)
+      float vals[kIlpB][9];
+      bool contrib[kIlpB];
 #pragma unroll
-          for (int k = 0; k < kIlpB; k++) {
+      for (int k = 0; k < kIlpB; k++) {
+        contrib[k] = al[k] != 0.f;
+        const float wgt = al[k] * Tr;
+        Drem = fmaf(-cdk[k], wgt, Drem);
+        const float dL_dalpha = fmaf(Tr, cdk[k], -(Drem + Tb) * rck[k]);
+        Tr = fmul(Tr, omk[k]);                                 // the forward's own product
+        const float wG = Gk[k] * dL_dalpha;
+        const float m10 = wG * dxk[k], m01 = wG * dyk[k];
+        vals[k][0] = wgt * dLp0; vals[k][1] = wgt * dLp1; vals[k][2] = wgt * dLp2;
+        vals[k][3] = wG; vals[k][4] = m10; vals[k][5] = m01;
+        vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
+      }
+      // phase 3 (independent): slots with few contributing lanes send their partials straight
+      // to L2 (9 REDs for the warp); the others are reduced through shared memory first and
+      // leave as one RED per value
 #pragma unroll
-            for (int t = 0; t < 9; t++) vals[k][t] = 0.f;
-            contrib[k] = al[k] != 0.f;
-            if (contrib[k]) {
-              const float alpha = al[k];
-              Tr = Tr * rck[k];
-              float wgt = alpha * Tr;
-              acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0;
-              acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1;
-              acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2;
-              lc0 = col[k].x; lc1 = col[k].y; lc2 = col[k].z;
-              float dL_dalpha = (lc0 - acc0) * dLp0 + (lc1 - acc1) * dLp1 + (lc2 - acc2) * dLp2;
-              dL_dalpha *= Tr;
-              last_alpha = alpha;
-              dL_dalpha += (-T_final * rck[k]) * bgdot;
-              float wG = Gk[k] * dL_dalpha;
-              float m10 = wG * dxk[k], m01 = wG * dyk[k];
-              vals[k][0] = wgt * dLp0; vals[k][1] = wgt * dLp1; vals[k][2] = wgt * dLp2;
-              vals[k][3] = wG; vals[k][4] = m10; vals[k][5] = m01;
-              vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
-            }
-          }
-          // phase 3 (independent): slots with few contributing lanes send their partials straight
-          // to L2 (9 REDs for the warp); the others are reduced through shared memory first and
-          // leave as one RED per value
+      for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
+        int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
 #pragma unroll
-          for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
-            int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
+        for (int qi = 0; qi < kRedBufs; qi++) {
+          const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+          const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
+          mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
+          if (mode[qi] == 2) warp_store9(&s_red[warp][qi][0], vals[k], lane);
+          if (mode[qi] == 1 && contrib[k]) {
+            float *dst = accb + (size_t)idk[k] * kAccStride;
 #pragma unroll
-            for (int qi = 0; qi < kRedBufs; qi++) {
-              const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-              const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
-              mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
-              if (mode[qi] == 2) warp_store9(&s_red[warp][qi][0], vals[k], lane);
-              if (mode[qi] == 1 && contrib[k]) {
-                float *dst = accb + (size_t)__float_as_uint(col[k].w) * kAccStride;
-#pragma unroll
-                for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
-              }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int qi = 0; qi < kRedBufs; qi++) {
-              const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-              if (mode[qi] != 2) continue;
-              float tot = warp_colsum9(&s_red[warp][qi][0], lane);
-              if (owner) atomicAdd(accb + (size_t)__float_as_uint(col[k].w) * kAccStride + lane, tot);
-            }
-            __syncwarp();
+            for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
           }
         }
+        __syncwarp();
+#pragma unroll
+        for (int qi = 0; qi < kRedBufs; qi++) {
+          const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+          if (mode[qi] != 2) continue;
+          float tot = warp_colsum9(&s_red[warp][qi][0], lane);
+          if (owner) atomicAdd(accb + (size_t)idk[k] * kAccStride + lane, tot);
+        }
+        __syncwarp();
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sb.empty[s]);
   }
 }
 
@@ -527,6 +543,8 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                 (const float4 *)(state + L.pub.off_records),
                                 (const uint8_t *)(state + L.pub.off_masks), (float *)(state + L.pub.off_final_T),
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
+                                (float4 *)(state + L.pub.off_tilefinal), (float4 *)(state + L.pub.off_ckpt),
+                                (uint2 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
                                 out_color, out_mask);
   };
   if (ilp <= 4) launch(blend_forward_kernel<4>);
@@ -536,17 +554,21 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
 
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
                                   const float *dL_dout, const float *dL_dmask, float *acc, cudaStream_t s) {
-  if (L.T == 0 || d.V == 0) return cudaSuccess;
-  dim3 grid(L.T * d.V), block(kBlendThreads);
+  if (L.T == 0 || d.V == 0 || d.R_cap <= 0) return cudaSuccess;
+  // upper bound of the unit count (the forward wrote the exact one to GhrStatus.reserved[1]); surplus
+  // CTAs exit on their first instruction
+  dim3 grid((unsigned)(L.n_slots - 1)), block(kUnitThreads);
   static const int ilp = env_int("GHR_ILPB", 2);
   static const int direct = env_int("GHR_DIRECT", kDirectMax);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const uint32_t *)(state + L.pub.off_order),
+    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const GhrStatus *)(state + L.pub.off_status),
+                                (const uint2 *)(state + L.pub.off_units),
                                 (const uint2 *)(state + L.pub.off_ranges),
                                 (const float4 *)(state + L.pub.off_records),
                                 (const uint8_t *)(state + L.pub.off_masks),
-                                (const float *)(state + L.pub.off_final_T),
+                                (const float4 *)(state + L.pub.off_tilefinal),
+                                (const float4 *)(state + L.pub.off_ckpt),
                                 (const uint32_t *)(state + L.pub.off_ncontrib),
                                 (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc, direct);
   };

@@ -12,6 +12,7 @@ constexpr int kRecBytes = 48;        // sorted instance record: 3 x float4
 constexpr int kSortThreads = 256;
 constexpr int kScanItems = 4;        // Gaussians per thread in scan_duplicate
 constexpr int kScanThreads = 256;
+constexpr int kSeg = GHR_SEGMENT;     // instances per backward work unit
 constexpr int kAccStride = 12;       // floats per (view,Gaussian) backward accumulator
 
 // ---- canonical fp32 order: explicit rn intrinsics are never re-contracted ----
@@ -132,6 +133,7 @@ struct Layout {
   int tile_bits, npt;          // bits / 8-bit passes of the (view,tile) key
   int items_d, items_t;        // radix items per thread (depth / tile sorts)
   int nblk_d, nblk_t, nblk_scan;
+  size_t n_slots;              // checkpoint slots = upper bound of backward work units
   // temp (forward)
   size_t t_zero_bytes;         // prefix of temp that must be zeroed before a forward
   size_t t_dhist, t_thist, t_tickets, t_scan_status, t_dstatus, t_tstatus;

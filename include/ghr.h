@@ -41,7 +41,8 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 5
+#define GHR_ABI_VERSION 6
+#define GHR_SEGMENT 256 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
 #define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges+schedule, 5 blend */
@@ -75,13 +76,20 @@ typedef struct GhrLayout {
   size_t off_order;    /* uint32 per (view, tile): blend launch order, longest instance list first */
   size_t off_masks;    /* uint8 per sorted instance: bit w set if the instance can reach alpha >= 1/255
                           inside the 8x4-pixel sub-block w = 2*(row/4) + (col/8) of its tile (culling only) */
+  size_t off_tilefinal; /* float4 per (view, tile, pixel-in-tile): {C.r, C.g, C.b, T_final} of the forward
+                          blend before the background term (the backward's suffix sums start from it) */
+  size_t off_ckpt;     /* float4 {T, C.r, C.g, C.b} per (slot, pixel-in-tile): the forward's running state at
+                          every GHR_SEGMENT-instance boundary of a tile list; slot(tile, s) =
+                          ranges[tile].start / GHR_SEGMENT + tile + s, s >= 1 */
+  size_t off_units;    /* uint32[2] (view*T + tile, segment) per backward work unit, GhrStatus.reserved[1] of them */
 } GhrLayout;
 
 typedef struct GhrStatus {
   uint64_t R;          /* number of (tile, Gaussian) instances the forward produced (all views) */
   uint32_t overflow;   /* 1 if R > R_cap: the forward output is invalid, retry with larger R_cap */
   uint32_t n_visible;  /* Gaussians (summed over views) with radius > 0 */
-  uint64_t reserved[2]; /* [0] = GhrForwardArgs.seq of the forward that wrote this status */
+  uint64_t reserved[2]; /* [0] = GhrForwardArgs.seq of the forward that wrote this status;
+                           [1] = number of backward work units (tile, segment) the forward blend emitted */
 } GhrStatus;
 
 typedef struct GhrForwardArgs {

@@ -77,8 +77,8 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->t_thist = t;        t = align_up(t + (size_t)4 * 256 * 4);
   L->t_tickets = t;      t = align_up(t + ((size_t)4 * d.V + 4 + 1) * 4);
   L->t_scan_status = t;  t = align_up(t + (size_t)(L->nblk_scan + 1) * 8);
-  L->t_dstatus = t;      t = align_up(t + (size_t)4 * d.V * L->nblk_d * 256 * 4);
-  L->t_tstatus = t;      t = align_up(t + (size_t)L->npt * L->nblk_t * 256 * 4);
+  L->t_dstatus = t;      t = align_up(t + (size_t)4 * d.V * status_words(L->nblk_d) * 4);
+  L->t_tstatus = t;      t = align_up(t + (size_t)L->npt * status_words(L->nblk_t) * 4);
   L->t_zero_bytes = t;
   for (int b = 0; b < 2; b++) { L->t_dkeys[b] = t; t = align_up(t + VP * 4); }
   for (int b = 0; b < 2; b++) { L->t_dvals[b] = t; t = align_up(t + VP * 4); }

@@ -111,6 +111,20 @@ scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, 
       if (lane == 0) st_volatile64(&scan_status[0], kScanIncl | block_total);
     } else {
       if (lane == 0) st_volatile64(&scan_status[blk], kScanLocal | block_total);
+      if (nblk <= 2048u) {
+        // every block is resident at once: a look-back would be a serial chain over the blocks, so the
+        // warp sums the local totals of ALL predecessors directly (blk/32 independent loads per lane;
+        // they only wait for the predecessors' block sums, never for their look-back)
+        uint64_t part = 0;
+        for (int64_t j = (int64_t)blk - 1 - lane; j >= 0; j -= 32) {
+          uint64_t sv;
+          do { sv = ld_volatile64(&scan_status[j]); } while ((sv >> 62) == 0);
+          part += sv & kScanMask;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+        excl = part;
+      } else {
       int64_t b = (int64_t)blk - 1;
       while (true) {
         int64_t mine = b - lane;
@@ -130,6 +144,7 @@ scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, 
         b -= 32;
       }
       if (lane == 0) st_volatile64(&scan_status[blk], kScanIncl | (excl + block_total));
+      }
     }
     if (lane == 0) {
       s_prefix = excl;
@@ -188,50 +203,46 @@ scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, 
   }
 }
 
-// One launch, two kinds of blocks, no block-level synchronisation:
-//   copy blocks (blockIdx.x < nb_copy): three threads per sorted instance, one per float4 of the
-//     48-byte record: consecutive lanes read consecutive 16-byte chunks of a geometry record and
-//     write consecutive chunks of the sorted slab (coalesced stores); they also mark tile ranges.
-//   mask blocks: one thread per sorted instance computes the 8-bit mask of 8x4 sub-blocks of its
-//     tile the alpha >= 1/255 ellipse reaches (subblock_mask) into the compact byte array the blend
-//     kernels stage next to the records (coalesced 1-byte stores).
-constexpr int kGatherThreads = 384;
+// One thread per sorted instance: loads the instance's 48-byte geometry record (3 independent
+// 128-bit loads), computes the 8-bit mask of 8x4 sub-blocks of its tile the alpha >= 1/255 ellipse
+// reaches (subblock_mask; compact byte array staged by the blend kernels next to the records),
+// marks tile range boundaries, and stages the record in shared memory so that the block writes the
+// sorted slab with fully coalesced 128-bit stores.
+constexpr int kGatherThreads = 256;
 __global__ void __launch_bounds__(kGatherThreads)
-gather_ranges_kernel(int nb_copy, FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap,
+gather_ranges_kernel(FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap,
                      const GhrStatus *__restrict__ status, const uint32_t *__restrict__ tkeys,
                      const uint32_t *__restrict__ tvals, const float4 *__restrict__ geom,
                      float4 *__restrict__ records, uint8_t *__restrict__ masks, uint2 *__restrict__ ranges,
                      uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
+  __shared__ float4 s_rec[kGatherThreads * 3];
   uint64_t R = status->R;
   if (R > R_cap) R = R_cap;
-  if ((int)blockIdx.x >= nb_copy) {
-    const uint64_t stride = (uint64_t)(gridDim.x - nb_copy) * kGatherThreads;
-    for (uint64_t r = (uint64_t)(blockIdx.x - nb_copy) * kGatherThreads + threadIdx.x; r < R; r += stride) {
-      const uint32_t g = tvals[r];
-      const uint32_t tile = dT.mod(tkeys[r]);
-      const uint32_t ty = dgx.div(tile);
-      masks[r] = (uint8_t)subblock_mask(geom[4 * (size_t)g], geom[4 * (size_t)g + 1],
-                                        (int)(tile - ty * dgx.d) * kTile, (int)ty * kTile);
-    }
-    return;
-  }
-  const uint32_t li = threadIdx.x / 3u, part = threadIdx.x - 3u * li;
-  const uint64_t stride = (uint64_t)nb_copy * (kGatherThreads / 3);
-  for (uint64_t r = (uint64_t)blockIdx.x * (kGatherThreads / 3) + li; r < R; r += stride) {
-    const uint32_t g = tvals[r];
-    float4 q = geom[4 * (size_t)g + part];
-    const uint32_t id = dP.mod(g);
-    if (part == 2) {
-      if (dbg_keys) dbg_keys[r] = ((uint64_t)dT.mod(tkeys[r]) << 32) | __float_as_uint(q.w);
-      q.w = __uint_as_float(id);
-    }
-    records[3 * r + part] = q;
-    if (part == 0) {
-      const uint32_t tk = tkeys[r];
-      if (r == 0 || tkeys[r - 1] != tk) ranges[tk].x = (uint32_t)r;
-      if (r == R - 1 || tkeys[r + 1] != tk) ranges[tk].y = (uint32_t)(r + 1);
+  const int tid = threadIdx.x;
+  for (uint64_t base = (uint64_t)blockIdx.x * kGatherThreads; base < R; base += (uint64_t)gridDim.x * kGatherThreads) {
+    const uint64_t r = base + tid;
+    if (r < R) {
+      const uint32_t g = tvals[r], tk = tkeys[r];
+      const uint32_t tk_prev = r ? tkeys[r - 1] : 0xFFFFFFFFu, tk_next = r + 1 < R ? tkeys[r + 1] : 0xFFFFFFFFu;
+      const float4 q0 = geom[4 * (size_t)g], q1 = geom[4 * (size_t)g + 1];
+      float4 q2 = geom[4 * (size_t)g + 2];
+      const uint32_t tile = dT.mod(tk), ty = dgx.div(tile), id = dP.mod(g);
+      masks[r] = (uint8_t)subblock_mask(q0, q1, (int)(tile - ty * dgx.d) * kTile, (int)ty * kTile);
+      if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | __float_as_uint(q2.w);
       if (dbg_plist) dbg_plist[r] = id;
+      q2.w = __uint_as_float(id);
+      s_rec[3 * tid] = q0;
+      s_rec[3 * tid + 1] = q1;
+      s_rec[3 * tid + 2] = q2;
+      if (tk_prev != tk) ranges[tk].x = (uint32_t)r;
+      if (tk_next != tk) ranges[tk].y = (uint32_t)(r + 1);
     }
+    __syncthreads();
+    const uint64_t left = R - base;
+    const int nrec = left < (uint64_t)kGatherThreads ? (int)left : kGatherThreads;
+    float4 *dst = records + 3 * base;
+    for (int k = tid; k < 3 * nrec; k += kGatherThreads) dst[k] = s_rec[k];
+    __syncthreads();
   }
 }
 
@@ -262,16 +273,14 @@ cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state,
   if (d.R_cap <= 0) return cudaSuccess;
   int buf = tile_sorted_buf(L);
   const uint64_t kMax = 148 * 8;
-  uint64_t want_c = ((uint64_t)d.R_cap + kGatherThreads / 3 - 1) / (kGatherThreads / 3);
-  uint64_t want_m = ((uint64_t)d.R_cap + kGatherThreads - 1) / kGatherThreads;
-  int nb_copy = (int)(want_c < kMax ? want_c : kMax), nb_mask = (int)(want_m < kMax ? want_m : kMax);
-  gather_ranges_kernel<<<nb_copy + nb_mask, kGatherThreads, 0, s>>>(nb_copy, make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap, (const GhrStatus *)(state + L.pub.off_status),
-                                          (const uint32_t *)(temp + L.t_tkeys[buf]),
-                                          (const uint32_t *)(temp + L.t_tvals[buf]),
-                                          (const float4 *)(state + L.pub.off_geom),
-                                          (float4 *)(state + L.pub.off_records),
-                                          (uint8_t *)(state + L.pub.off_masks),
-                                          (uint2 *)(state + L.pub.off_ranges), dbg_keys, dbg_plist);
+  uint64_t want = ((uint64_t)d.R_cap + kGatherThreads - 1) / kGatherThreads;
+  int nb = (int)(want < kMax ? want : kMax);
+  gather_ranges_kernel<<<nb, kGatherThreads, 0, s>>>(
+      make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap,
+      (const GhrStatus *)(state + L.pub.off_status), (const uint32_t *)(temp + L.t_tkeys[buf]),
+      (const uint32_t *)(temp + L.t_tvals[buf]), (const float4 *)(state + L.pub.off_geom),
+      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks),
+      (uint2 *)(state + L.pub.off_ranges), dbg_keys, dbg_plist);
   return cudaGetLastError();
 }
 

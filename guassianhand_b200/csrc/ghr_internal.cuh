@@ -169,6 +169,9 @@ cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const 
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present,
                                 cudaStream_t s);
 
+// status words of one (pass, segment) of a radix sort: 256 per block + 256 per group of 32 blocks
+inline size_t status_words(int nblk) { return ((size_t)nblk + ((size_t)nblk + 31) / 32) * 256; }
+
 // which final sorted buffers hold the results (ping-pong parity)
 inline int depth_sorted_buf() { return 0; }                 // 4 passes: ends in buffer 0
 inline int tile_sorted_buf(const Layout &L) { return L.npt & 1; }  // input in buffer 0

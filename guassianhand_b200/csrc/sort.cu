@@ -16,6 +16,8 @@ namespace {
 constexpr uint32_t kFlagLocal = 1u << 30;
 constexpr uint32_t kFlagIncl = 2u << 30;
 constexpr uint32_t kValMask = (1u << 30) - 1;
+constexpr uint32_t kGroup = 32;                 // blocks per group of the two-level prefix
+constexpr uint32_t kTwoLevelMaxBlocks = 2048;   // above: classic decoupled look-back
 
 __device__ __forceinline__ uint32_t ld_volatile(const uint32_t *p) {
   uint32_t v;
@@ -26,6 +28,25 @@ __device__ __forceinline__ void st_volatile(uint32_t *p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// One look-back window: W predecessors b, b-1, ... loaded back to back (independent loads), then
+// consumed nearest-first until an inclusive prefix is met.  Returns true when one was found.
+template <int W>
+__device__ __forceinline__ bool lookback_window(const uint32_t *status, int b, int d, uint32_t &excl) {
+  uint32_t sv[W];
+#pragma unroll
+  for (int w = 0; w < W; w++) sv[w] = (b - w >= 0) ? ld_volatile(&status[(size_t)(b - w) * 256 + d]) : kFlagIncl;
+  bool found = false;
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    if (found) break;
+    uint32_t x = sv[w];
+    while ((x & ~kValMask) == 0) x = ld_volatile(&status[(size_t)(b - w) * 256 + d]);
+    excl += x & kValMask;
+    if ((x & ~kValMask) == kFlagIncl) found = true;
+  }
+  return found;
+}
+
 // One digit pass over one segment (blockIdx.y).  Items are taken in warp-striped order so that
 // (warp, iteration, lane) is the stable order.
 template <int ITEMS, bool IDENTITY_VALS, bool WRITE_KEYS>
@@ -34,7 +55,7 @@ radix_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                   const uint64_t *__restrict__ n_ptr, uint32_t n_fixed, uint64_t n_cap, size_t seg_stride,
                   int shift, const uint32_t *__restrict__ hist, uint32_t *__restrict__ status,
-                  size_t status_seg_stride, uint32_t *__restrict__ tickets) {
+                  size_t status_seg_stride, uint32_t *__restrict__ tickets, uint32_t nblk_cap) {
   constexpr int kWarps = kSortThreads / 32;
   constexpr int kBlockItems = kSortThreads * ITEMS;
   __shared__ uint32_t warp_cnt[kWarps][256];
@@ -104,31 +125,58 @@ radix_pass_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restri
       total += c;
     }
     uint32_t excl = 0;
+    const bool two_level = nblk <= kTwoLevelMaxBlocks;
     if (blk == 0) {
       st_volatile(&status[(size_t)blk * 256 + d], kFlagIncl | total);
+      if (two_level) atomicAdd(&status[(size_t)nblk_cap * 256 + d], (1u << 24) | total);
     } else {
       st_volatile(&status[(size_t)blk * 256 + d], kFlagLocal | total);
-      // decoupled look-back, kWin predecessors per round trip: the loads of a window are issued
-      // back to back (independent), then consumed nearest-first until an inclusive prefix is met
-      constexpr int kWin = 8;
-      int b = (int)blk - 1;
-      bool found = false;
-      while (!found) {
-        uint32_t sv[kWin];
+      if (two_level) {
+        // At these sizes every block of the pass is resident at once, so a classic decoupled look-back
+        // degenerates into a serial chain (a block cannot count on its predecessor being finished).
+        // Two-level sum instead, free of any chain: every block adds its count to its group's word
+        // ((arrivals << 24) | sum, one RED) right after ranking; a block needs the local counts of the
+        // earlier blocks of its own group and the words of the earlier, complete groups -- all of
+        // which only wait for ranking, never for another block's look-back.
+        uint32_t *grp = status + (size_t)nblk_cap * 256;
+        const uint32_t g = blk / kGroup;
+        atomicAdd(&grp[(size_t)g * 256 + d], (1u << 24) | total);
+#pragma unroll 1
+        for (uint32_t b0 = g * kGroup; b0 < blk; b0 += 8) {
+          uint32_t sv[8];
 #pragma unroll
-        for (int w = 0; w < kWin; w++)
-          sv[w] = (b - w >= 0) ? ld_volatile(&status[(size_t)(b - w) * 256 + d]) : kFlagIncl;
+          for (int w = 0; w < 8; w++) sv[w] = (b0 + w < blk) ? ld_volatile(&status[(size_t)(b0 + w) * 256 + d]) : kFlagLocal;
 #pragma unroll
-        for (int w = 0; w < kWin; w++) {
-          if (found) break;
-          uint32_t x = sv[w];
-          while ((x & ~kValMask) == 0) x = ld_volatile(&status[(size_t)(b - w) * 256 + d]);
-          excl += x & kValMask;
-          if ((x & ~kValMask) == kFlagIncl) found = true;
+          for (int w = 0; w < 8; w++) {
+            uint32_t x = sv[w];
+            while ((x & ~kValMask) == 0) x = ld_volatile(&status[(size_t)(b0 + w) * 256 + d]);
+            excl += x & kValMask;
+          }
         }
-        b -= kWin;
+#pragma unroll 1
+        for (uint32_t g0 = 0; g0 < g; g0 += 8) {
+          uint32_t sv[8];
+#pragma unroll
+          for (int w = 0; w < 8; w++) sv[w] = (g0 + w < g) ? ld_volatile(&grp[(size_t)(g0 + w) * 256 + d]) : (kGroup << 24);
+#pragma unroll
+          for (int w = 0; w < 8; w++) {
+            uint32_t x = sv[w];
+            while ((x >> 24) != kGroup) x = ld_volatile(&grp[(size_t)(g0 + w) * 256 + d]);
+            excl += x & 0xFFFFFFu;
+          }
+        }
+      } else {
+        // classic decoupled look-back (multi-wave grids: predecessors are mostly finished), windows
+        // of 8 independent loads consumed nearest-first until an inclusive prefix is met
+        int b = (int)blk - 1;
+        bool found = false;
+#pragma unroll 1
+        while (!found) {
+          found = lookback_window<8>(status, b, d, excl);
+          b -= 8;
+        }
+        st_volatile(&status[(size_t)blk * 256 + d], kFlagIncl | (excl + total));
       }
-      st_volatile(&status[(size_t)blk * 256 + d], kFlagIncl | (excl + total));
     }
     // exclusive scan of the global histogram over digits
     uint32_t h = hist[d];
@@ -179,15 +227,15 @@ cudaError_t run_passes(int npass, int first_shift, bool identity_first, bool dro
     if (ident)
       radix_pass_kernel<ITEMS, true, true><<<grid, block, 0, s>>>(keys[in], nullptr, keys[out], vals[out], n_ptr,
                                                                    n_fixed, n_cap, seg_stride, shift, h, st,
-                                                                   status_seg_stride, tk);
+                                                                   status_seg_stride, tk, (uint32_t)nblk);
     else if (wk)
       radix_pass_kernel<ITEMS, false, true><<<grid, block, 0, s>>>(keys[in], vals[in], keys[out], vals[out],
                                                                     n_ptr, n_fixed, n_cap, seg_stride, shift, h, st,
-                                                                    status_seg_stride, tk);
+                                                                    status_seg_stride, tk, (uint32_t)nblk);
     else
       radix_pass_kernel<ITEMS, false, false><<<grid, block, 0, s>>>(keys[in], vals[in], keys[out], vals[out],
                                                                      n_ptr, n_fixed, n_cap, seg_stride, shift, h,
-                                                                     st, status_seg_stride, tk);
+                                                                     st, status_seg_stride, tk, (uint32_t)nblk);
   }
   return cudaGetLastError();
 }
@@ -201,7 +249,7 @@ cudaError_t launch_depth_sort(const GhrDims &d, const Layout &L, char *temp, cud
   const uint32_t *hist = (const uint32_t *)(temp + L.t_dhist);
   uint32_t *status = (uint32_t *)(temp + L.t_dstatus);
   uint32_t *tickets = (uint32_t *)(temp + L.t_tickets);
-  size_t seg_status = (size_t)L.nblk_d * 256;
+  size_t seg_status = status_words(L.nblk_d);
   size_t pass_status = seg_status * d.V;
   if (L.items_d == 4)
     return run_passes<4>(4, 0, true, true, keys, vals, nullptr, (uint32_t)d.P, 0, d.V, (size_t)d.P, hist, status,
@@ -218,7 +266,7 @@ cudaError_t launch_tile_sort(const GhrDims &d, const Layout &L, char *state, cha
   uint32_t *status = (uint32_t *)(temp + L.t_tstatus);
   uint32_t *tickets = (uint32_t *)(temp + L.t_tickets) + 4 * (size_t)d.V;
   const uint64_t *n_ptr = &((const GhrStatus *)(state + L.pub.off_status))->R;
-  size_t seg_status = (size_t)L.nblk_t * 256;
+  size_t seg_status = status_words(L.nblk_t);
   if (L.items_t == 4)
     return run_passes<4>(L.npt, 0, false, false, keys, vals, n_ptr, 0, (uint64_t)d.R_cap, 1, 0, hist, status,
                          seg_status, seg_status, tickets, L.nblk_t, s);

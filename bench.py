@@ -154,10 +154,9 @@ def algorithmic_bytes(stage, P, V, N, T, R, M=0):
     sh_b = (24 * M + 3) * P * V if M else 0
     return {
         "preprocess": 80 * P * V + sh_f,
-        "depth_sort": 8 * P * V,           # compulsory: 4B key + 4B index in, sorted index out
-        "scan_duplicate": (8 + 20) * P * V + 12 * R,
-        "tile_sort": 24 * R,
-        "gather_ranges": 8 * R + 8 * T * V,
+        "tile_scan": (8 * P + 8 * T) * V,              # K2 (scan; here over tiles) + range table of K5
+        "duplicate": 20 * P * V + 12 * R,              # K3
+        "sort_gather": 24 * R + 8 * R,                 # K4 (one compulsory read+write of 12-B pairs) + K5
         "blend_forward": 40 * R + 20 * N * V,
         "blend_backward": 40 * R + (20 * N + 36 * P) * V,
         "preprocess_backward": 120 * P * V + sh_b,
@@ -215,8 +214,7 @@ def run_ours(args):
         pairs.append(int(nc.sum(dtype=torch.int64).item()))
     R_cap = int(max(Rs) * 1.25) + (1 << 14)
     lay = NV.layout(P, B, H, W, 0, 0, R_cap)
-    npt = (max(1, int(np.ceil(np.log2(max(B * T, 2))))) + 7) // 8
-    launches_per_step = 1 + 1 + 4 + 1 + npt + 1 + 1 + 1 + 2       # init, preprocess, 4 depth passes, scan, tile passes, gather, schedule, blend | 2 bwd
+    launches_per_step = 1 + 1 + 1 + 1 + 2 + 1 + 2     # init, preprocess, tile scan, duplicate, chunk sort, merge+gather, blend | 2 bwd
 
     status_pin = torch.zeros(K + Wm, 4, dtype=torch.int64).pin_memory()
 

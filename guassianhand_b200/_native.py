@@ -11,9 +11,9 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 6
-GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 6, 2
-FWD_STAGES = ["preprocess", "depth_sort", "scan_duplicate", "tile_sort", "gather_ranges", "blend_forward"]
+GHR_ABI_VERSION = 7
+GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
+FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
 
 EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",

@@ -36,23 +36,6 @@ int compute_layout(const GhrDims &d, Layout *L) {
               (unsigned long long)VP, (unsigned long long)VT, (long long)d.R_cap);
     return GHR_EINVAL;
   }
-  int bits = 1;
-  while ((1ull << bits) < VT) bits++;
-  L->tile_bits = bits;
-  L->npt = (bits + 7) / 8;
-  L->items_d = (VP > (1u << 21)) ? 16 : 4;
-  L->items_t = ((uint64_t)d.R_cap > (1u << 19)) ? 16 : 4;
-  {
-    // tuning overrides (A/B runs): GHR_ITEMS_D / GHR_ITEMS_T in {4, 16}
-    static const char *ed = getenv("GHR_ITEMS_D"), *et = getenv("GHR_ITEMS_T");
-    if (ed) L->items_d = atoi(ed) >= 16 ? 16 : 4;
-    if (et) L->items_t = atoi(et) >= 16 ? 16 : 4;
-  }
-  L->nblk_d = (int)((d.P + (uint64_t)kSortThreads * L->items_d - 1) / ((uint64_t)kSortThreads * L->items_d));
-  L->nblk_t = (int)(((uint64_t)d.R_cap + (uint64_t)kSortThreads * L->items_t - 1) /
-                    ((uint64_t)kSortThreads * L->items_t));
-  L->nblk_scan = (int)((VP + kScanThreads * kScanItems - 1) / (kScanThreads * kScanItems));
-
   // ---- state ----
   size_t o = 0;
   L->pub.off_status = o;   o = align_up(o + sizeof(GhrStatus));
@@ -73,17 +56,13 @@ int compute_layout(const GhrDims &d, Layout *L) {
 
   // ---- temp (forward): zeroed prefix first ----
   size_t t = 0;
-  L->t_dhist = t;        t = align_up(t + (size_t)4 * d.V * 256 * 4);
-  L->t_thist = t;        t = align_up(t + (size_t)4 * 256 * 4);
-  L->t_tickets = t;      t = align_up(t + ((size_t)4 * d.V + 4 + 1) * 4);
-  L->t_scan_status = t;  t = align_up(t + (size_t)(L->nblk_scan + 1) * 8);
-  L->t_dstatus = t;      t = align_up(t + (size_t)4 * d.V * status_words(L->nblk_d) * 4);
-  L->t_tstatus = t;      t = align_up(t + (size_t)L->npt * status_words(L->nblk_t) * 4);
+  L->t_tile_count = t;   t = align_up(t + VT * 4);
+  L->t_cursor = t;       t = align_up(t + VT * 4);
+  L->t_misc = t;         t = align_up(t + 64);
   L->t_zero_bytes = t;
-  for (int b = 0; b < 2; b++) { L->t_dkeys[b] = t; t = align_up(t + VP * 4); }
-  for (int b = 0; b < 2; b++) { L->t_dvals[b] = t; t = align_up(t + VP * 4); }
-  for (int b = 0; b < 2; b++) { L->t_tkeys[b] = t; t = align_up(t + (size_t)d.R_cap * 4); }
-  for (int b = 0; b < 2; b++) { L->t_tvals[b] = t; t = align_up(t + (size_t)d.R_cap * 4); }
+  L->t_inst = t;         t = align_up(t + (size_t)d.R_cap * 8);
+  L->n_chunks = (size_t)d.R_cap / kChunk + VT;
+  L->t_chunks = t;       t = align_up(t + L->n_chunks * 8);
   L->pub.temp_bytes = t;
   L->pub.temp_bwd_bytes = align_up(VP * kAccStride * 4);
   return GHR_OK;
@@ -210,34 +189,22 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   GHR_TRY(launch_preprocess(d, L, cam, g, a->scale_modifier, a->flags, state, temp, a->radii, s),
           "ghr_forward: preprocess");
   tm.stop(0);
-  if (d.P > 0) {
-    tm.start(1);
-    GHR_TRY(launch_depth_sort(d, L, temp, s), "ghr_forward: depth sort");
-    tm.stop(1);
-    tm.start(2);
-    GHR_TRY(launch_scan_duplicate(d, L, state, temp, a->seq, s), "ghr_forward: scan+duplicate");
-    tm.stop(2);
-    if (a->host_status)
-      GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost,
-                              s),
-              "ghr_forward: status copy");
-    if (d.R_cap > 0) {
-      tm.start(3);
-      GHR_TRY(launch_tile_sort(d, L, state, temp, s), "ghr_forward: tile sort");
-      tm.stop(3);
-      tm.start(4);
-      GHR_TRY(launch_gather_ranges(d, L, state, temp, a->dbg_keys_sorted, a->dbg_point_list, s),
-              "ghr_forward: gather+ranges");
-      tm.stop(4);
-    }
-  }
-  GHR_TRY(launch_tile_schedule(d, L, state, s), "ghr_forward: tile schedule");
-  tm.start(5);
-  if (a->host_status && d.P == 0)
+  tm.start(1);
+  GHR_TRY(launch_tile_scan_schedule(d, L, state, temp, s), "ghr_forward: tile scan+schedule");
+  tm.stop(1);
+  if (a->host_status)
     GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
             "ghr_forward: status copy");
+  tm.start(2);
+  GHR_TRY(launch_duplicate(d, L, state, temp, s), "ghr_forward: duplicate");
+  tm.stop(2);
+  tm.start(3);
+  GHR_TRY(launch_sort_gather(d, L, state, temp, a->dbg_keys_sorted, a->dbg_point_list, s),
+          "ghr_forward: sort+gather");
+  tm.stop(3);
+  tm.start(4);
   GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, a->out_mask, s), "ghr_forward: blend");
-  tm.stop(5);
+  tm.stop(4);
   return GHR_OK;
 }
 

@@ -1,30 +1,31 @@
-// Tile binning around the sorts:
-//   scan_duplicate : single-pass prefix sum (decoupled look-back) of tiles_touched taken in
-//                    depth-sorted order, fused with the emission of one ((view,tile), id) pair per
-//                    touched tile and with the digit histograms of the following tile sort.
-//                    Replaces upstream InclusiveSum + blocking D2H of num_rendered +
-//                    duplicateWithKeys (SURVEY.md §2a K2,K3; A.4).  R stays on the device.
-//   gather_ranges  : after the tile sort, copies each instance's 48-byte geometry record into
-//                    sorted order (so the blend kernels stream contiguous slabs with bulk async
-//                    copies) and marks tile range boundaries.  Replaces identifyTileRanges (K5).
+// Tile binning: from per-tile instance counts (preprocess) to the per-tile, depth-sorted slabs of
+// instance records the blend kernels stream.
+//
+// Upstream: InclusiveSum over Gaussians -> blocking D2H of num_rendered ->
+// duplicateWithKeys -> one global stable radix sort of R 64-bit (tile<<32|depth) keys ->
+// identifyTileRanges.  The final order is "by tile, then by depth bits, ties in Gaussian-index order"
+// -- a total order on (tile, depth bits, index).  Here the sort is done most-significant part first:
+//   tile_scan_schedule : exclusive scan of the per-tile counts = the tile ranges (known BEFORE any
+//                        instance exists), R and the overflow flag, plus the heaviest-first launch
+//                        order of the tiles.  One CTA; V*T is a few thousand.
+//   duplicate          : every visible Gaussian drops one (depth bits, id) pair into each tile it
+//                        touches, at a slot taken from the tile's cursor -- unordered inside the tile.
+//                        Slots are reserved per (block, tile) from shared-memory counts, so the global
+//                        atomics are one per touched tile per block, not one per instance.
+//   sort_chunks        : every tile list is cut into chunks of kChunk instances; one CTA sorts one chunk by
+//                        (depth bits, id) in shared memory (two radix passes on the 16 leading significant
+//                        bits + a local fix).  A single-chunk tile is finished here: its 48-byte geometry
+//                        records are gathered in sorted order with their sub-block cull masks.
+//   merge_gather       : for a tile of several chunks, one CTA per chunk ranks its keys in the other
+//                        (sorted) chunks by binary search -- final position = own index + ranks -- and
+//                        gathers its records straight to their final place.
+// No global sort, no cross-block prefix: all work items are uniform chunks, independent after the scan.  Result: bit for
+// bit the upstream order (checked against the oracle's sorted keys / point list / ranges).
 #include "ghr_internal.cuh"
 
 namespace ghr {
 
 namespace {
-
-constexpr uint64_t kScanLocal = 1ull << 62;
-constexpr uint64_t kScanIncl = 2ull << 62;
-constexpr uint64_t kScanMask = (1ull << 62) - 1;
-
-__device__ __forceinline__ uint64_t ld_volatile64(const uint64_t *p) {
-  uint64_t v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_volatile64(uint64_t *p, uint64_t v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 __device__ __forceinline__ void rect_of(float px, float py, int radius, int gx, int gy, int &minx, int &miny,
                                         int &maxx, int &maxy) {
@@ -36,213 +37,424 @@ __device__ __forceinline__ void rect_of(float px, float py, int radius, int gx, 
   maxy = min(gy, max(0, (int)fmul(fsub(fadd(fadd(py, rf), 16.0f), 1.0f), 0.0625f)));
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-scan_duplicate_kernel(int P, FastDiv dP, int V, int gx, int gy, int T, int npt, uint64_t R_cap,
-                      const float4 *__restrict__ geom, const uint32_t *__restrict__ order /*[V,P] depth-sorted ids*/,
-                      uint64_t *__restrict__ scan_status, uint32_t *__restrict__ ticket,
-                      uint32_t *__restrict__ tkeys, uint32_t *__restrict__ tvals, uint32_t *__restrict__ thist,
-                      GhrStatus *__restrict__ status, uint32_t nblk) {
-  constexpr int kItems = kScanItems;
-  constexpr int kBlockItems = kScanThreads * kItems;
-  __shared__ uint32_t s_hist[4][256];
-  __shared__ uint64_t s_warp[kScanThreads / 32];
-  __shared__ uint64_t s_prefix;
-  __shared__ uint32_t s_blk;
-  __shared__ uint32_t s_vis[kScanThreads / 32];
+// Size class of a tile list: 0 for an empty tile, else 1 + ceil(log2 n) (n = 1 -> 1, 2 -> 2, 3..4 -> 3, ...).
+// Lists of one class share the padded power-of-two length 2^(class-1) of the sorting network.
+__device__ __forceinline__ int size_class(uint32_t n) { return n == 0 ? 0 : 33 - __clz(n - 1); }
+
+constexpr int kScanThreads1 = 1024;
+constexpr int kClasses = 34;
+
+// ranges[t] = [start, end) of tile t in the instance arrays (clamped to R_cap; (0,0) for empty tiles,
+// as upstream leaves them), order[] = tile ids by descending size class (the blend launch order),
+// chunks[] = (tile, chunk index) work items of the sort, misc[0] = their number, status = {R, overflow}.
+__global__ void __launch_bounds__(kScanThreads1)
+tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, const uint32_t *__restrict__ tile_count,
+                          uint2 *__restrict__ ranges, uint32_t *__restrict__ order, uint2 *__restrict__ chunks,
+                          uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
+  __shared__ uint64_t s_warp[kScanThreads1 / 32];
+  __shared__ uint32_t s_wchunk[kScanThreads1 / 32];
+  __shared__ uint32_t s_ccarry;
+  __shared__ uint64_t s_carry;
+  __shared__ uint32_t s_cls[kClasses], s_cur[kClasses];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_blk = atomicAdd(ticket, 1u);
-  for (int k = tid; k < 4 * 256; k += kScanThreads) (&s_hist[0][0])[k] = 0;
-  __syncthreads();
-  const uint32_t blk = s_blk;
-  const uint64_t total_elems = (uint64_t)V * P;
-
-  // each thread owns kItems consecutive elements of the (view-major, depth-sorted) sequence
-  uint32_t tt[kItems];
-  uint32_t gid[kItems];
-  float2 xy[kItems];
-  int rad[kItems];
-  uint32_t sum = 0, nvis = 0;
-#pragma unroll
-  for (int k = 0; k < kItems; k++) {
-    uint64_t e = (uint64_t)blk * kBlockItems + (uint64_t)tid * kItems + k;
-    tt[k] = 0;
-    gid[k] = 0;
-    rad[k] = 0;
-    xy[k] = make_float2(0.f, 0.f);
-    if (e < total_elems) {
-      uint32_t v = dP.div((uint32_t)e);
-      uint32_t id = order[e];
-      uint32_t g = v * (uint32_t)P + id;
-      float4 q3 = geom[4 * (size_t)g + 3];
-      tt[k] = __float_as_uint(q3.y);
-      if (tt[k]) {
-        float4 q0 = geom[4 * (size_t)g + 0];
-        xy[k] = make_float2(q0.x, q0.y);
-        rad[k] = __float_as_int(q3.x);
-        gid[k] = g;
-        nvis++;
-      }
-    }
-    sum += tt[k];
-  }
-  // block exclusive scan of per-thread sums
-  uint32_t incl = sum;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  uint32_t wv = nvis;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wv += __shfl_xor_sync(0xFFFFFFFFu, wv, o);
-  if (lane == 31) s_warp[warp] = incl;
-  if (lane == 0) s_vis[warp] = wv;
-  __syncthreads();
-  uint64_t wbase = 0, block_total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; w++) {
-    if (w < warp) wbase += s_warp[w];
-    block_total += s_warp[w];
-  }
-  // decoupled look-back on block totals (warp 0)
-  if (warp == 0) {
-    uint64_t excl = 0;
-    if (blk == 0) {
-      if (lane == 0) st_volatile64(&scan_status[0], kScanIncl | block_total);
-    } else {
-      if (lane == 0) st_volatile64(&scan_status[blk], kScanLocal | block_total);
-      if (nblk <= 2048u) {
-        // every block is resident at once: a look-back would be a serial chain over the blocks, so the
-        // warp sums the local totals of ALL predecessors directly (blk/32 independent loads per lane;
-        // they only wait for the predecessors' block sums, never for their look-back)
-        uint64_t part = 0;
-        for (int64_t j = (int64_t)blk - 1 - lane; j >= 0; j -= 32) {
-          uint64_t sv;
-          do { sv = ld_volatile64(&scan_status[j]); } while ((sv >> 62) == 0);
-          part += sv & kScanMask;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-        excl = part;
-      } else {
-      int64_t b = (int64_t)blk - 1;
-      while (true) {
-        int64_t mine = b - lane;
-        uint64_t sv = 0;
-        if (mine >= 0) {
-          do { sv = ld_volatile64(&scan_status[mine]); } while ((sv >> 62) == 0);
-        } else {
-          sv = kScanIncl;   // virtual predecessor of block 0 with value 0
-        }
-        uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, (sv >> 62) == 2);
-        int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-        uint64_t contrib = (lane <= first) ? (sv & kScanMask) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xFFFFFFFFu, contrib, o);
-        excl += contrib;
-        if (incl_mask) break;
-        b -= 32;
-      }
-      if (lane == 0) st_volatile64(&scan_status[blk], kScanIncl | (excl + block_total));
-      }
-    }
-    if (lane == 0) {
-      s_prefix = excl;
-      uint32_t bv = 0;
-      for (int w = 0; w < kScanThreads / 32; w++) bv += s_vis[w];
-      if (bv) atomicAdd(&status->n_visible, bv);
-      if (blk == nblk - 1) {
-        uint64_t Rtot = excl + block_total;
-        status->R = Rtot;
-        status->overflow = Rtot > R_cap ? 1u : 0u;
-      }
-    }
+  if (tid < kClasses) s_cls[tid] = 0;
+  if (tid == 0) {
+    s_carry = 0;
+    s_ccarry = 0;
   }
   __syncthreads();
-  uint64_t off = s_prefix + wbase + (incl - sum);
-
-  // emission: row-major over the tile rectangle (A.4), in depth-sorted Gaussian order.  Histogram
-  // of the tile key's digits for the tile sort: the low digit per instance; the upper digits change
-  // rarely along a thread's emissions (same view, neighbouring tiles), so they are counted as runs
-  // and flushed once per change instead of one (warp-wide conflicting) shared atomic per instance.
-  uint32_t run_hi = 0xFFFFFFFFu, run_cnt = 0;
-  auto flush = [&]() {
-    if (run_cnt)
-      for (int p = 1; p < npt; p++) atomicAdd(&s_hist[p][(run_hi >> (8 * (p - 1))) & 255u], run_cnt);
-    run_cnt = 0;
-  };
+  for (int base = 0; base < VT; base += kScanThreads1) {
+    const int t = base + tid;
+    const uint32_t c = t < VT ? tile_count[t] : 0u;
+    uint64_t incl = c;
 #pragma unroll
-  for (int k = 0; k < kItems; k++) {
-    if (tt[k]) {
-      int minx, miny, maxx, maxy;
-      rect_of(xy[k].x, xy[k].y, rad[k], gx, gy, minx, miny, maxx, maxy);
-      uint32_t v = dP.div(gid[k]);
-      uint32_t tbase = v * (uint32_t)T;
-      for (int y = miny; y < maxy; y++)
-        for (int x = minx; x < maxx; x++) {
-          uint32_t tk = tbase + (uint32_t)(y * gx + x);
-          if (off < R_cap) {
-            tkeys[off] = tk;
-            tvals[off] = gid[k];
-            atomicAdd(&s_hist[0][tk & 255u], 1u);
-            if ((tk >> 8) != run_hi) {
-              flush();
-              run_hi = tk >> 8;
-            }
-            run_cnt++;
-          }
-          off++;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += up;
     }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint64_t wbase = s_carry;
+    for (int w = 0; w < warp; w++) wbase += s_warp[w];
+    const uint64_t start = wbase + incl - c, end = start + c;
+    const uint32_t cs = (uint32_t)(start < R_cap ? start : R_cap), ce = (uint32_t)(end < R_cap ? end : R_cap);
+    // chunks of this tile (of its clamped list) and their offset in the work list
+    const uint32_t m = (ce - cs + kChunk - 1) / kChunk;
+    uint32_t cincl = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, cincl, o);
+      if (lane >= o) cincl += up;
+    }
+    if (lane == 31) s_wchunk[warp] = cincl;
+    __syncthreads();
+    uint32_t cbase = s_ccarry;
+    for (int w = 0; w < warp; w++) cbase += s_wchunk[w];
+    if (t < VT) {
+      ranges[t] = c ? make_uint2(cs, ce) : make_uint2(0u, 0u);
+      atomicAdd(&s_cls[size_class(c)], 1u);
+      const uint32_t coff = cbase + cincl - m;
+      for (uint32_t j = 0; j < m && coff + j < chunk_cap; j++) chunks[coff + j] = make_uint2((uint32_t)t, j);
+    }
+    __syncthreads();
+    if (tid == kScanThreads1 - 1) {
+      s_carry = wbase + incl;
+      s_ccarry = cbase + cincl;
+    }
+    __syncthreads();
   }
-  flush();
+  if (tid == 0) {
+    const uint64_t R = s_carry;
+    status->R = R;
+    status->overflow = R > R_cap ? 1u : 0u;
+    uint32_t sum = 0;
+    for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
+      s_cur[c] = sum;
+      sum += s_cls[c];
+    }
+    misc[0] = s_ccarry < chunk_cap ? s_ccarry : chunk_cap;
+  }
   __syncthreads();
-  for (int k = tid; k < npt * 256; k += kScanThreads) {
-    uint32_t c = (&s_hist[0][0])[k];
-    if (c) atomicAdd(&thist[k], c);
+  for (int t = tid; t < VT; t += kScanThreads1) {
+    const uint32_t pos = atomicAdd(&s_cur[size_class(tile_count[t])], 1u);
+    order[pos] = (uint32_t)t;
   }
 }
 
-// One thread per sorted instance: loads the instance's 48-byte geometry record (3 independent
-// 128-bit loads), computes the 8-bit mask of 8x4 sub-blocks of its tile the alpha >= 1/255 ellipse
-// reaches (subblock_mask; compact byte array staged by the blend kernels next to the records),
-// marks tile range boundaries, and stages the record in shared memory so that the block writes the
-// sorted slab with fully coalesced 128-bit stores.
-constexpr int kGatherThreads = 256;
-__global__ void __launch_bounds__(kGatherThreads)
-gather_ranges_kernel(FastDiv dP, FastDiv dT, FastDiv dgx, uint64_t R_cap,
-                     const GhrStatus *__restrict__ status, const uint32_t *__restrict__ tkeys,
-                     const uint32_t *__restrict__ tvals, const float4 *__restrict__ geom,
-                     float4 *__restrict__ records, uint8_t *__restrict__ masks, uint2 *__restrict__ ranges,
-                     uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
-  __shared__ float4 s_rec[kGatherThreads * 3];
-  uint64_t R = status->R;
-  if (R > R_cap) R = R_cap;
-  const int tid = threadIdx.x;
-  for (uint64_t base = (uint64_t)blockIdx.x * kGatherThreads; base < R; base += (uint64_t)gridDim.x * kGatherThreads) {
-    const uint64_t r = base + tid;
-    if (r < R) {
-      const uint32_t g = tvals[r], tk = tkeys[r];
-      const uint32_t tk_prev = r ? tkeys[r - 1] : 0xFFFFFFFFu, tk_next = r + 1 < R ? tkeys[r + 1] : 0xFFFFFFFFu;
-      const float4 q0 = geom[4 * (size_t)g], q1 = geom[4 * (size_t)g + 1];
-      float4 q2 = geom[4 * (size_t)g + 2];
-      const uint32_t tile = dT.mod(tk), ty = dgx.div(tile), id = dP.mod(g);
-      masks[r] = (uint8_t)subblock_mask(q0, q1, (int)(tile - ty * dgx.d) * kTile, (int)ty * kTile);
-      if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | __float_as_uint(q2.w);
-      if (dbg_plist) dbg_plist[r] = id;
-      q2.w = __uint_as_float(id);
-      s_rec[3 * tid] = q0;
-      s_rec[3 * tid + 1] = q1;
-      s_rec[3 * tid + 2] = q2;
-      if (tk_prev != tk) ranges[tk].x = (uint32_t)r;
-      if (tk_next != tk) ranges[tk].y = (uint32_t)(r + 1);
+// One thread per (view, Gaussian), a block = 256 consecutive Gaussians of one view.
+__global__ void __launch_bounds__(256)
+duplicate_kernel(int P, int gx, int gy, int T, int smem_tiles, uint64_t R_cap, const float4 *__restrict__ geom,
+                 const uint2 *__restrict__ ranges, uint32_t *__restrict__ cursor, uint2 *__restrict__ inst) {
+  extern __shared__ uint32_t s_mem[];
+  uint32_t *s_cnt = s_mem, *s_base = s_mem + smem_tiles;
+  const int v = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = threadIdx.x; k < smem_tiles; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  int minx = 0, miny = 0, maxx = 0, maxy = 0;
+  uint32_t depth_bits = 0, gid = 0;
+  if (i < P) {
+    gid = (uint32_t)v * (uint32_t)P + (uint32_t)i;
+    const float4 q3 = geom[4 * (size_t)gid + 3];
+    if (__float_as_uint(q3.y)) {
+      const float4 q0 = geom[4 * (size_t)gid];
+      depth_bits = __float_as_uint(geom[4 * (size_t)gid + 2].w);
+      rect_of(q0.x, q0.y, __float_as_int(q3.x), gx, gy, minx, miny, maxx, maxy);
+    }
+  }
+  const uint2 *vr = ranges + (size_t)v * T;
+  uint32_t *vc = cursor + (size_t)v * T;
+  if (smem_tiles) {
+    for (int y = miny; y < maxy; y++)
+      for (int x = minx; x < maxx; x++) atomicAdd(&s_cnt[y * gx + x], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < smem_tiles; k += blockDim.x) {
+      const uint32_t c = s_cnt[k];
+      if (c) {
+        s_base[k] = vr[k].x + atomicAdd(&vc[k], c);
+        s_cnt[k] = 0;
+      }
     }
     __syncthreads();
-    const uint64_t left = R - base;
-    const int nrec = left < (uint64_t)kGatherThreads ? (int)left : kGatherThreads;
-    float4 *dst = records + 3 * base;
-    for (int k = tid; k < 3 * nrec; k += kGatherThreads) dst[k] = s_rec[k];
+    for (int y = miny; y < maxy; y++)
+      for (int x = minx; x < maxx; x++) {
+        const int t = y * gx + x;
+        const uint64_t slot = (uint64_t)s_base[t] + atomicAdd(&s_cnt[t], 1u);
+        if (slot < R_cap) inst[slot] = make_uint2(depth_bits, gid);
+      }
+  } else {
+    // more tiles per view than fit in shared memory: one global atomic per instance
+    for (int y = miny; y < maxy; y++)
+      for (int x = minx; x < maxx; x++) {
+        const int t = y * gx + x;
+        const uint64_t slot = (uint64_t)vr[t].x + atomicAdd(&vc[t], 1u);
+        if (slot < R_cap) inst[slot] = make_uint2(depth_bits, gid);
+      }
+  }
+}
+
+// ---- chunk sort: one CTA per chunk of <= kChunk instances of one tile ----
+// Keys are 64-bit ((depth bits - min depth bits of the chunk) << 32 | Gaussian index within the view).
+// One stable LSD pass on the 8-bit digit at `shift`, `a` -> `b` (shared memory): items in warp-blocked
+// order (warp, iteration, lane), ranks by match.any + per-warp digit counters.
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = kChunk / kSortThreads;
+constexpr int kSortWarps = kSortThreads / 32;
+struct ChunkSort {
+  uint16_t wcnt[kSortWarps][256];   // per-warp digit counts (<= 32*kSortItems each)
+  uint32_t dbase[256];              // output offset of every digit
+  uint32_t scan[kSortWarps];
+  uint32_t dmin, dmax;
+  unsigned long long red_and, red_or;
+};
+
+__device__ __noinline__ void chunk_radix_pass(ChunkSort &S, const uint64_t *a, uint64_t *b, uint32_t n, int shift,
+                                              int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  // items per thread this chunk needs (warp-blocked: warp w owns [w*32*it, (w+1)*32*it))
+  const uint32_t it = (n + kSortThreads - 1) / kSortThreads;
+  for (int k = tid; k < kSortWarps * 128; k += kSortThreads) reinterpret_cast<uint32_t *>(&S.wcnt[0][0])[k] = 0;
+  __syncthreads();
+  uint64_t key[kSortItems];
+  uint32_t rank[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    if (i < (int)it) {
+      const uint32_t idx = warp * 32 * it + i * 32 + lane;
+      const bool ok = idx < n;
+      key[i] = ok ? a[idx] : ~0ull;
+      const uint32_t d = ok ? (uint32_t)(key[i] >> shift) & 255u : 256u;   // 256 = padding, never counted
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+      const int leader = __ffs(peers) - 1;
+      uint32_t old = 0;
+      if (lane == leader && ok) {
+        old = S.wcnt[warp][d];
+        S.wcnt[warp][d] = (uint16_t)(old + __popc(peers));
+      }
+      old = __shfl_sync(0xFFFFFFFFu, old, leader);
+      rank[i] = old + __popc(peers & lt_mask);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // thread d owns digit d: exclusive prefix over warps, then exclusive scan over digits
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) {
+    const uint32_t cw = S.wcnt[w][tid];
+    S.wcnt[w][tid] = (uint16_t)total;
+    total += cw;
+  }
+  uint32_t incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) S.scan[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int w = 0; w < warp; w++) wbase += S.scan[w];
+  S.dbase[tid] = wbase + incl - total;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    if (i < (int)it) {
+      const uint32_t idx = warp * 32 * it + i * 32 + lane;
+      if (idx < n) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        b[S.dbase[d] + S.wcnt[warp][d] + rank[i]] = key[i];
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Writes one sorted instance: gathers its geometry record, computes the sub-block mask.
+__device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uint32_t id, uint32_t gbase, uint32_t tile,
+                                              int tile_x0, int tile_y0, const float4 *__restrict__ geom,
+                                              float4 *__restrict__ records, uint8_t *__restrict__ masks,
+                                              uint64_t *__restrict__ dbg_keys, uint32_t *__restrict__ dbg_plist) {
+  const size_t g = (size_t)gbase + id;
+  const float4 q0 = geom[4 * g], q1 = geom[4 * g + 1];
+  float4 q2 = geom[4 * g + 2];
+  masks[r] = (uint8_t)subblock_mask(q0, q1, tile_x0, tile_y0);
+  if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | depth_bits;
+  if (dbg_plist) dbg_plist[r] = id;
+  q2.w = __uint_as_float(id);
+  records[3 * r] = q0;
+  records[3 * r + 1] = q1;
+  records[3 * r + 2] = q2;
+}
+
+// Sort = two radix passes on the top 16 significant bits of (depth bits - min depth bits of the chunk)
+// followed by a local fix: runs of equal 16-bit prefix (almost always length 1-3; equal depths land
+// here too) are insertion-sorted on the full (depth bits, index) key by the thread at the run start.
+// A chunk with a run longer than kMaxRun (degenerate depth distribution) is re-sorted by LSD passes
+// over every key byte that varies.  Either way the result is the total order on (depth bits, index).
+constexpr uint32_t kMaxRun = 32;
+__global__ void __launch_bounds__(kSortThreads, 4)
+sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
+                   const uint2 *__restrict__ ranges, uint2 *inst, const float4 *__restrict__ geom,
+                   float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
+                   uint32_t *__restrict__ dbg_plist) {
+  __shared__ __align__(16) uint64_t s_buf[2][kChunk];
+  __shared__ ChunkSort S;
+  if (blockIdx.x >= misc[0]) return;
+  const uint2 chunk = chunks[blockIdx.x];
+  const uint32_t vt = chunk.x;
+  const uint2 range = ranges[vt];
+  const uint32_t cstart = range.x + chunk.y * kChunk;
+  const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
+  const bool single = range.y - range.x <= (uint32_t)kChunk;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
+  uint2 *src = inst + cstart;
+  uint64_t *a = s_buf[0], *b = s_buf[1];
+  if (tid == 0) {
+    S.dmin = 0xFFFFFFFFu;
+    S.dmax = 0u;
+    S.red_and = ~0ull;
+    S.red_or = 0ull;
+  }
+  __syncthreads();
+  uint2 e[kSortItems];
+  {
+    uint32_t dmin = 0xFFFFFFFFu, dmax = 0u;
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      const uint32_t k = i * kSortThreads + tid;
+      e[i] = k < n ? src[k] : make_uint2(0u, 0u);
+      if (k < n) {
+        dmin = min(dmin, e[i].x);
+        dmax = max(dmax, e[i].x);
+      }
+    }
+    dmin = __reduce_min_sync(0xFFFFFFFFu, dmin);
+    dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
+    if (lane == 0) {
+      atomicMin(&S.dmin, dmin);
+      atomicMax(&S.dmax, dmax);
+    }
+  }
+  __syncthreads();
+  const uint32_t dmin = S.dmin, span = S.dmax - dmin;
+  const int hi = 32 - __clz(span);                     // significant bits of (depth - dmin); 0 if all equal
+  const int shift0 = hi > 16 ? hi - 16 : 0;
+  {
+    // pack (depth bits - dmin, index in view); AND/OR of the keys for the fallback's byte skipping
+    uint64_t k_and = ~0ull, k_or = 0ull;
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      const uint32_t k = i * kSortThreads + tid;
+      if (k < n) {
+        const uint64_t key = ((uint64_t)(e[i].x - dmin) << 32) | (e[i].y - gbase);
+        a[k] = key;
+        k_and &= key;
+        k_or |= key;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      k_and &= __shfl_xor_sync(0xFFFFFFFFu, k_and, o);
+      k_or |= __shfl_xor_sync(0xFFFFFFFFu, k_or, o);
+    }
+    if (lane == 0) {
+      atomicAnd(&S.red_and, (unsigned long long)k_and);
+      atomicOr(&S.red_or, (unsigned long long)k_or);
+    }
+  }
+  __syncthreads();
+  if (hi > 0) {
+    chunk_radix_pass(S, a, b, n, 32 + shift0, tid);
+    uint64_t *t = a; a = b; b = t;
+  }
+  if (hi > 8) {
+    chunk_radix_pass(S, a, b, n, 32 + shift0 + 8, tid);
+    uint64_t *t = a; a = b; b = t;
+  }
+  // local fix: full-key insertion sort inside runs of equal prefix
+  const int ps = 32 + shift0;
+  bool too_long = false;
+  for (uint32_t k = tid; k < n; k += kSortThreads) {
+    const uint64_t pk = a[k] >> ps;
+    if (k > 0 && (a[k - 1] >> ps) == pk) continue;     // not a run start
+    uint32_t len = 1;
+    while (len <= kMaxRun && k + len < n && (a[k + len] >> ps) == pk) len++;
+    if (len > kMaxRun) {
+      too_long = true;
+      continue;
+    }
+    for (uint32_t i = 1; i < len; i++) {
+      const uint64_t x = a[k + i];
+      uint32_t j = i;
+      while (j > 0 && a[k + j - 1] > x) {
+        a[k + j] = a[k + j - 1];
+        j--;
+      }
+      a[k + j] = x;
+    }
+  }
+  if (__syncthreads_or(too_long)) {
+    const uint64_t vary = S.red_and ^ S.red_or;
+    for (int shift = 0; shift < 64; shift += 8) {
+      if (((vary >> shift) & 255ull) == 0) continue;   // digit constant over the chunk: identity pass
+      chunk_radix_pass(S, a, b, n, shift, tid);
+      uint64_t *t = a; a = b; b = t;
+    }
+  }
+  if (single) {
+    // the whole tile list: gather in sorted order
+    const uint32_t ty = dgx.div(tile);
+    const int tile_x0 = (int)(tile - ty * dgx.d) * kTile, tile_y0 = (int)ty * kTile;
+#pragma unroll 2
+    for (uint32_t k = tid; k < n; k += kSortThreads) {
+      const uint64_t key = a[k];
+      emit_instance((size_t)cstart + k, (uint32_t)(key >> 32) + dmin, (uint32_t)key, gbase, tile, tile_x0, tile_y0,
+                    geom, records, masks, dbg_keys, dbg_plist);
+    }
+  } else {
+    // one of several chunks of its tile: leave the sorted absolute keys in place for merge_gather
+    uint64_t *dst = reinterpret_cast<uint64_t *>(src);
+    for (uint32_t k = tid; k < n; k += kSortThreads) dst[k] = a[k] + ((uint64_t)dmin << 32);
+  }
+}
+
+// Multi-chunk tiles: one CTA per chunk.  Final position of a key = its index in its own (sorted) chunk
+// + the number of smaller keys in every other chunk of the tile (keys are unique: (depth bits, index)).
+__global__ void __launch_bounds__(kSortThreads, 4)
+merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
+                    const uint2 *__restrict__ ranges, const uint2 *__restrict__ inst, const float4 *__restrict__ geom,
+                    float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
+                    uint32_t *__restrict__ dbg_plist) {
+  __shared__ __align__(16) uint64_t s_other[kChunk];
+  if (blockIdx.x >= misc[0]) return;
+  const uint2 chunk = chunks[blockIdx.x];
+  const uint32_t vt = chunk.x;
+  const uint2 range = ranges[vt];
+  const uint32_t nt = range.y - range.x;
+  if (nt <= (uint32_t)kChunk) return;                  // single-chunk tile: finished by sort_chunks
+  const uint32_t m = (nt + kChunk - 1) / kChunk;
+  const uint32_t cstart = range.x + chunk.y * kChunk;
+  const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
+  const int tid = threadIdx.x;
+  const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
+  const uint64_t *keys = reinterpret_cast<const uint64_t *>(inst);
+  uint64_t key[kSortItems];
+  uint32_t pos[kSortItems];
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    const uint32_t k = i * kSortThreads + tid;
+    key[i] = k < n ? keys[cstart + k] : ~0ull;
+    pos[i] = k;
+  }
+  for (uint32_t c = 0; c < m; c++) {
+    if (c == chunk.y) continue;
+    const uint32_t ostart = range.x + c * kChunk, on = min((uint32_t)kChunk, range.y - ostart);
     __syncthreads();
+    for (uint32_t k = tid; k < on; k += kSortThreads) s_other[k] = keys[ostart + k];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      // lower bound of key[i] in s_other[0, on)
+      uint32_t lo = 0, len = on;
+      while (len > 0) {
+        const uint32_t half = len >> 1;
+        const bool less = s_other[lo + half] < key[i];
+        lo = less ? lo + half + 1 : lo;
+        len = less ? len - half - 1 : half;
+      }
+      pos[i] += lo;
+    }
+  }
+  const uint32_t ty = dgx.div(tile);
+  const int tile_x0 = (int)(tile - ty * dgx.d) * kTile, tile_y0 = (int)ty * kTile;
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    const uint32_t k = i * kSortThreads + tid;
+    if (k < n)
+      emit_instance((size_t)range.x + pos[i], (uint32_t)(key[i] >> 32), (uint32_t)key[i], gbase, tile, tile_x0, tile_y0,
+                    geom, records, masks, dbg_keys, dbg_plist);
   }
 }
 
@@ -255,32 +467,48 @@ cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_scan_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t seq,
-                                  cudaStream_t s) {
-  (void)seq;
-  if (L.nblk_scan == 0) return cudaSuccess;
-  scan_duplicate_kernel<<<L.nblk_scan, kScanThreads, 0, s>>>(
-      d.P, make_fastdiv((uint32_t)d.P), d.V, L.gx, L.gy, L.T, L.npt, (uint64_t)d.R_cap, (const float4 *)(state + L.pub.off_geom),
-      (const uint32_t *)(temp + L.t_dvals[depth_sorted_buf()]), (uint64_t *)(temp + L.t_scan_status),
-      (uint32_t *)(temp + L.t_tickets) + 4 * (size_t)d.V + 4, (uint32_t *)(temp + L.t_tkeys[0]),
-      (uint32_t *)(temp + L.t_tvals[0]), (uint32_t *)(temp + L.t_thist), (GhrStatus *)(state + L.pub.off_status),
-      (uint32_t)L.nblk_scan);
+cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s) {
+  const int VT = d.V * L.T;
+  if (VT == 0) return cudaSuccess;
+  tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
+      VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (const uint32_t *)(temp + L.t_tile_count),
+      (uint2 *)(state + L.pub.off_ranges), (uint32_t *)(state + L.pub.off_order), (uint2 *)(temp + L.t_chunks),
+      (uint32_t *)(temp + L.t_misc), (GhrStatus *)(state + L.pub.off_status));
   return cudaGetLastError();
 }
 
-cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state, char *temp,
-                                 uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s) {
-  if (d.R_cap <= 0) return cudaSuccess;
-  int buf = tile_sorted_buf(L);
-  const uint64_t kMax = 148 * 8;
-  uint64_t want = ((uint64_t)d.R_cap + kGatherThreads - 1) / kGatherThreads;
-  int nb = (int)(want < kMax ? want : kMax);
-  gather_ranges_kernel<<<nb, kGatherThreads, 0, s>>>(
-      make_fastdiv((uint32_t)d.P), make_fastdiv((uint32_t)L.T), make_fastdiv((uint32_t)L.gx), (uint64_t)d.R_cap,
-      (const GhrStatus *)(state + L.pub.off_status), (const uint32_t *)(temp + L.t_tkeys[buf]),
-      (const uint32_t *)(temp + L.t_tvals[buf]), (const float4 *)(state + L.pub.off_geom),
-      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks),
-      (uint2 *)(state + L.pub.off_ranges), dbg_keys, dbg_plist);
+cudaError_t launch_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s) {
+  if (d.P == 0 || d.R_cap <= 0) return cudaSuccess;
+  dim3 grid((d.P + 255) / 256, d.V), block(256);
+  const int smem_tiles = L.T <= kMaxSmemTiles ? L.T : 0;
+  const size_t smem = (size_t)smem_tiles * 8;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(duplicate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  duplicate_kernel<<<grid, block, smem, s>>>(d.P, L.gx, L.gy, L.T, smem_tiles, (uint64_t)d.R_cap,
+                                             (const float4 *)(state + L.pub.off_geom),
+                                             (const uint2 *)(state + L.pub.off_ranges),
+                                             (uint32_t *)(temp + L.t_cursor), (uint2 *)(temp + L.t_inst));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t *dbg_keys,
+                               uint32_t *dbg_plist, cudaStream_t s) {
+  const int VT = d.V * L.T;
+  if (VT == 0 || d.R_cap <= 0) return cudaSuccess;
+  const FastDiv dT = make_fastdiv((uint32_t)L.T), dgx = make_fastdiv((uint32_t)L.gx);
+  // grid = upper bound of the chunk count (the scan wrote the exact one to misc[0]); surplus CTAs exit
+  const int grid = (int)L.n_chunks;
+  sort_chunks_kernel<<<grid, kSortThreads, 0, s>>>(
+      d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
+      (const uint2 *)(state + L.pub.off_ranges), (uint2 *)(temp + L.t_inst), (const float4 *)(state + L.pub.off_geom),
+      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
+  merge_gather_kernel<<<grid, kSortThreads, 0, s>>>(
+      d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
+      (const uint2 *)(state + L.pub.off_ranges), (const uint2 *)(temp + L.t_inst),
+      (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
+      (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
   return cudaGetLastError();
 }
 

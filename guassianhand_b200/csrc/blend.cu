@@ -491,45 +491,12 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   }
 }
 
-// Heaviest-first tile schedule: a counting sort of the V*T (view, tile) ids by the class
-// floor(log2(list length)) in descending order (single CTA; V*T is a few thousand).
-__global__ void __launch_bounds__(1024)
-tile_schedule_kernel(int VT, const uint2 *__restrict__ ranges, uint32_t *__restrict__ order) {
-  __shared__ uint32_t cnt[34], cur[34];
-  const int tid = threadIdx.x;
-  if (tid < 34) cnt[tid] = 0;
-  __syncthreads();
-  auto cls = [](uint2 r) -> int {
-    uint32_t n = r.y - r.x;
-    return n == 0 ? 33 : __clz(n);   // fewer leading zeros = longer list = earlier; 33 = empty tile
-  };
-  for (int t = tid; t < VT; t += blockDim.x) atomicAdd(&cnt[cls(ranges[t])], 1u);
-  __syncthreads();
-  if (tid == 0) {
-    uint32_t sum = 0;
-    for (int c = 0; c < 34; c++) { cur[c] = sum; sum += cnt[c]; }
-  }
-  __syncthreads();
-  for (int t = tid; t < VT; t += blockDim.x) {
-    uint32_t pos = atomicAdd(&cur[cls(ranges[t])], 1u);
-    order[pos] = (uint32_t)t;
-  }
-}
-
 int env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e ? atoi(e) : dflt;
 }
 
 }  // namespace
-
-cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s) {
-  int VT = d.V * L.T;
-  if (VT == 0) return cudaSuccess;
-  tile_schedule_kernel<<<1, 1024, 0, s>>>(VT, (const uint2 *)(state + L.pub.off_ranges),
-                                          (uint32_t *)(state + L.pub.off_order));
-  return cudaGetLastError();
-}
 
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
                                  float *out_color, float *out_mask, cudaStream_t s) {

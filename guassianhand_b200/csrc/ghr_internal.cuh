@@ -9,9 +9,8 @@ namespace ghr {
 
 constexpr int kTile = 16;            // 16x16 pixel tiles
 constexpr int kRecBytes = 48;        // sorted instance record: 3 x float4
-constexpr int kSortThreads = 256;
-constexpr int kScanItems = 4;        // Gaussians per thread in scan_duplicate
-constexpr int kScanThreads = 256;
+constexpr int kChunk = 2048;         // instances per work item of the per-tile sort
+constexpr int kMaxSmemTiles = 16384; // tiles per view whose per-block counters fit in shared memory
 constexpr int kSeg = GHR_SEGMENT;     // instances per backward work unit
 constexpr int kAccStride = 12;       // floats per (view,Gaussian) backward accumulator
 
@@ -130,14 +129,13 @@ struct Gaussians {
 struct Layout {
   GhrLayout pub;
   int gx, gy, T;               // tiles per view
-  int tile_bits, npt;          // bits / 8-bit passes of the (view,tile) key
-  int items_d, items_t;        // radix items per thread (depth / tile sorts)
-  int nblk_d, nblk_t, nblk_scan;
   size_t n_slots;              // checkpoint slots = upper bound of backward work units
   // temp (forward)
   size_t t_zero_bytes;         // prefix of temp that must be zeroed before a forward
-  size_t t_dhist, t_thist, t_tickets, t_scan_status, t_dstatus, t_tstatus;
-  size_t t_dkeys[2], t_dvals[2], t_tkeys[2], t_tvals[2];
+  size_t t_tile_count, t_cursor, t_misc;   // uint32 per (view, tile) x 2; misc words
+  size_t t_inst;               // uint2 (depth bits, view*P + id) per instance, unordered inside a tile
+  size_t t_chunks;             // uint2 (view*T + tile, chunk index) per sort work item
+  size_t n_chunks;             // their upper bound: R_cap / kChunk + V*T
 };
 
 int compute_layout(const GhrDims &d, Layout *L);
@@ -147,14 +145,11 @@ void set_error(const char *fmt, ...);
 cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &cam, const Gaussians &g,
                               float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,
                               cudaStream_t s);
-cudaError_t launch_depth_sort(const GhrDims &d, const Layout &L, char *temp, cudaStream_t s);
-cudaError_t launch_scan_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t seq,
-                                  cudaStream_t s);
 cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s);
-cudaError_t launch_tile_sort(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
-cudaError_t launch_gather_ranges(const GhrDims &d, const Layout &L, char *state, char *temp,
-                                 uint64_t *dbg_keys, uint32_t *dbg_plist, cudaStream_t s);
-cudaError_t launch_tile_schedule(const GhrDims &d, const Layout &L, char *state, cudaStream_t s);
+cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
+cudaError_t launch_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
+cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t *dbg_keys,
+                               uint32_t *dbg_plist, cudaStream_t s);
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
                                  float *out_color, float *out_mask, cudaStream_t s);
 cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Cameras &cam, const char *state,
@@ -168,12 +163,5 @@ cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const 
                                        const float *acc, const GradOut &go, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present,
                                 cudaStream_t s);
-
-// status words of one (pass, segment) of a radix sort: 256 per block + 256 per group of 32 blocks
-inline size_t status_words(int nblk) { return ((size_t)nblk + ((size_t)nblk + 31) / 32) * 256; }
-
-// which final sorted buffers hold the results (ping-pong parity)
-inline int depth_sorted_buf() { return 0; }                 // 4 passes: ends in buffer 0
-inline int tile_sorted_buf(const Layout &L) { return L.npt & 1; }  // input in buffer 0
 
 }  // namespace ghr

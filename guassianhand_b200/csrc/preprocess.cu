@@ -1,5 +1,5 @@
 // Per-(view, Gaussian) preprocess: frustum cull, 3D covariance, EWA projection to the 2D conic,
-// radius / tile rectangle, SH colour, depth key + digit histograms for the depth sort.
+// radius / tile rectangle, SH colour, and the per-tile instance counts the binning starts from.
 // Replaces upstream preprocessCUDA<3> -- one thread per
 // (view, Gaussian); output is one 64-byte record (4 x STG.128) instead of seven scattered arrays.
 #include "ghr_internal.cuh"
@@ -83,24 +83,23 @@ __device__ __forceinline__ void sh_to_rgb(int D, const float *sh, float px, floa
 __global__ void __launch_bounds__(256)
 preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, float scale_modifier, uint32_t flags,
                   Cameras cam, Gaussians g, float4 *__restrict__ geom, uint8_t *__restrict__ clamped,
-                  int32_t *__restrict__ radii, uint32_t *__restrict__ depth_keys, uint32_t *__restrict__ dhist,
-                  uint2 *__restrict__ ranges, uint32_t *__restrict__ tilemax, int VT) {
-  __shared__ uint32_t s_hist[4][256];
+                  int32_t *__restrict__ radii, uint32_t *__restrict__ tile_count, uint32_t *__restrict__ tilemax,
+                  GhrStatus *__restrict__ status, int T, int smem_tiles) {
+  // s_cnt[t]: instances this block's Gaussians put on tile t of its view (smem_tiles == T), flushed
+  // as one RED per touched tile; with more tiles than fit (smem_tiles == 0) every instance is a RED
+  extern __shared__ uint32_t s_cnt[];
   const int v = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) (&s_hist[0][0])[k] = 0;
-  // zero the per-tile outputs (grid-stride over all threads of the launch)
+  for (int k = threadIdx.x; k < smem_tiles; k += blockDim.x) s_cnt[k] = 0;
+  // zero the per-tile blend output (grid-stride over all threads of the launch)
   {
     size_t gtid = ((size_t)v * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     size_t gsz = (size_t)gridDim.x * gridDim.y * blockDim.x;
-    for (size_t t = gtid; t < (size_t)VT; t += gsz) {
-      ranges[t] = make_uint2(0u, 0u);
-      tilemax[t] = 0u;
-    }
+    for (size_t t = gtid; t < (size_t)T * V; t += gsz) tilemax[t] = 0u;
   }
   __syncthreads();
 
-  uint32_t key = 0xFFFFFFFFu;
+  bool visible = false;
   if (i < P) {
     const float *Vm = cam.view + 16 * v;
     const float *PV = cam.proj + 16 * v;
@@ -188,7 +187,10 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
           }
           radius = rad;
           tiles = (uint32_t)tt;
-          key = __float_as_uint(pvz);
+          visible = true;
+          uint32_t *cnt = smem_tiles ? s_cnt : tile_count + (size_t)v * T;
+          for (int y = miny; y < maxy; y++)
+            for (int x = minx; x < maxx; x++) atomicAdd(&cnt[y * gx + x], 1u);
           // Cull threshold for the blend kernels (never part of the canonical arithmetic):
           // alpha = o*exp(power) >= 1/255  =>  d^T Q d <= 2 ln(255 o) =: thr.  A warp skips the
           // instance when the minimum of d^T Q d over its pixel block exceeds thr (with margin).
@@ -216,26 +218,15 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     geom[4 * e + 3] = q3;
     if (clamped) clamped[e] = (uint8_t)cbits;
     radii[e] = radius;
-    depth_keys[e] = key;
   }
-  // digit histograms of the depth key: lanes of a warp that share a digit (nearly all of them for
-  // the high bytes: depths of a scene span one or two binades) add once per distinct digit
-  {
-    const uint32_t act = __ballot_sync(0xFFFFFFFFu, i < P);
-    if (i < P) {
-#pragma unroll
-      for (int p = 0; p < 4; p++) {
-        const uint32_t dgt = (key >> (8 * p)) & 255u;
-        const uint32_t peers = __match_any_sync(act, dgt);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[p][dgt], (uint32_t)__popc(peers));
-      }
+  const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
+  if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&status->n_visible, nvis);
+  if (smem_tiles) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < smem_tiles; k += blockDim.x) {
+      const uint32_t c = s_cnt[k];
+      if (c) atomicAdd(&tile_count[(size_t)v * T + k], c);
     }
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < 4 * 256; k += blockDim.x) {
-    uint32_t c = (&s_hist[0][0])[k];
-    int p = k >> 8, dgt = k & 255;
-    if (c) atomicAdd(&dhist[((size_t)p * V + v) * 256 + dgt], c);
   }
 }
 
@@ -255,11 +246,17 @@ cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &
   int nb = (d.P + 255) / 256;
   if (nb == 0) nb = 1;
   dim3 grid(nb, d.V), block(256);
-  preprocess_kernel<<<grid, block, 0, s>>>(
+  const int smem_tiles = L.T <= kMaxSmemTiles ? L.T : 0;
+  const size_t smem = (size_t)smem_tiles * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  preprocess_kernel<<<grid, block, smem, s>>>(
       d.P, d.V, d.H, d.W, d.M, d.sh_degree, L.gx, L.gy, scale_modifier, flags, cam, g,
       (float4 *)(state + L.pub.off_geom), d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr, radii,
-      (uint32_t *)(temp + L.t_dkeys[0]), (uint32_t *)(temp + L.t_dhist), (uint2 *)(state + L.pub.off_ranges),
-      (uint32_t *)(state + L.pub.off_tilemax), d.V * L.T);
+      (uint32_t *)(temp + L.t_tile_count), (uint32_t *)(state + L.pub.off_tilemax),
+      (GhrStatus *)(state + L.pub.off_status), L.T, smem_tiles);
   return cudaGetLastError();
 }
 

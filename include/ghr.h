@@ -41,11 +41,11 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 6
+#define GHR_ABI_VERSION 7
 #define GHR_SEGMENT 256 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
-#define GHR_NSTAGES_FWD 6 /* 0 preprocess, 1 depth sort, 2 scan+duplicate, 3 tile sort, 4 gather+ranges+schedule, 5 blend */
+#define GHR_NSTAGES_FWD 5 /* 0 preprocess (+ per-tile counts), 1 tile scan + schedule, 2 duplicate, 3 per-tile sort + gather, 4 blend */
 #define GHR_NSTAGES_BWD 2 /* 0 blend backward, 1 preprocess backward */
 
 /* Problem dimensions.  T = ceil(W/16)*ceil(H/16) tiles per view, N = H*W pixels per view. */
@@ -125,7 +125,7 @@ typedef struct GhrForwardArgs {
   uint64_t *dbg_keys_sorted;   /* [R_cap] (tile<<32 | depth bits), tile local to its view */
   uint32_t *dbg_point_list;    /* [R_cap] Gaussian index within its view */
   /* optional early status report: if non-NULL (PINNED HOST memory), GhrStatus is copied there
-   * as soon as R is known (after the scan, before the tile sort and the blend are enqueued), with
+   * as soon as R is known (after the tile scan, before duplication, the per-tile sort and the blend are enqueued), with
    * reserved[0] == seq.  The host can poll it while the GPU keeps working -- this replaces the
    * blocking D2H read of num_rendered in upstream's forward without stalling the pipeline. */
   GhrStatus *host_status;

@@ -47,75 +47,76 @@ constexpr int kClasses = 34;
 // ranges[t] = [start, end) of tile t in the instance arrays (clamped to R_cap; (0,0) for empty tiles,
 // as upstream leaves them), order[] = tile ids by descending size class (the blend launch order),
 // chunks[] = (tile, chunk index) work items of the sort, misc[0] = their number, status = {R, overflow}.
+// One CTA: every thread owns a run of consecutive tiles, sums it, one block scan of the 1024 run
+// totals, then walks its run again.
 __global__ void __launch_bounds__(kScanThreads1)
 tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, const uint32_t *__restrict__ tile_count,
                           uint2 *__restrict__ ranges, uint32_t *__restrict__ order, uint2 *__restrict__ chunks,
                           uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
   __shared__ uint64_t s_warp[kScanThreads1 / 32];
   __shared__ uint32_t s_wchunk[kScanThreads1 / 32];
-  __shared__ uint32_t s_ccarry;
-  __shared__ uint64_t s_carry;
   __shared__ uint32_t s_cls[kClasses], s_cur[kClasses];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kClasses) s_cls[tid] = 0;
-  if (tid == 0) {
-    s_carry = 0;
-    s_ccarry = 0;
+  const int per = (VT + kScanThreads1 - 1) / kScanThreads1;
+  const int t0 = min(VT, tid * per), t1 = min(VT, t0 + per);
+  uint64_t sum = 0;
+  uint32_t csum = 0;
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    sum += c;
+    csum += (c + kChunk - 1) / kChunk;
+  }
+  uint64_t incl = sum;
+  uint32_t cincl = csum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    const uint32_t cup = __shfl_up_sync(0xFFFFFFFFu, cincl, o);
+    if (lane >= o) {
+      incl += up;
+      cincl += cup;
+    }
+  }
+  if (lane == 31) {
+    s_warp[warp] = incl;
+    s_wchunk[warp] = cincl;
   }
   __syncthreads();
-  for (int base = 0; base < VT; base += kScanThreads1) {
-    const int t = base + tid;
-    const uint32_t c = t < VT ? tile_count[t] : 0u;
-    uint64_t incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-      if (lane >= o) incl += up;
+  uint64_t start = incl - sum, total = 0;
+  uint32_t coff = cincl - csum, ctotal = 0;
+  for (int w = 0; w < kScanThreads1 / 32; w++) {
+    if (w < warp) {
+      start += s_warp[w];
+      coff += s_wchunk[w];
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint64_t wbase = s_carry;
-    for (int w = 0; w < warp; w++) wbase += s_warp[w];
-    const uint64_t start = wbase + incl - c, end = start + c;
-    const uint32_t cs = (uint32_t)(start < R_cap ? start : R_cap), ce = (uint32_t)(end < R_cap ? end : R_cap);
-    // chunks of this tile (of its clamped list) and their offset in the work list
-    const uint32_t m = (ce - cs + kChunk - 1) / kChunk;
-    uint32_t cincl = m;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, cincl, o);
-      if (lane >= o) cincl += up;
-    }
-    if (lane == 31) s_wchunk[warp] = cincl;
-    __syncthreads();
-    uint32_t cbase = s_ccarry;
-    for (int w = 0; w < warp; w++) cbase += s_wchunk[w];
-    if (t < VT) {
-      ranges[t] = c ? make_uint2(cs, ce) : make_uint2(0u, 0u);
-      atomicAdd(&s_cls[size_class(c)], 1u);
-      const uint32_t coff = cbase + cincl - m;
-      for (uint32_t j = 0; j < m && coff + j < chunk_cap; j++) chunks[coff + j] = make_uint2((uint32_t)t, j);
-    }
-    __syncthreads();
-    if (tid == kScanThreads1 - 1) {
-      s_carry = wbase + incl;
-      s_ccarry = cbase + cincl;
-    }
-    __syncthreads();
+    total += s_warp[w];
+    ctotal += s_wchunk[w];
   }
+  for (int t = t0; t < t1; t++) {
+    const uint32_t c = tile_count[t];
+    const uint64_t end = start + c;
+    ranges[t] = c ? make_uint2((uint32_t)(start < R_cap ? start : R_cap), (uint32_t)(end < R_cap ? end : R_cap))
+                  : make_uint2(0u, 0u);
+    atomicAdd(&s_cls[size_class(c)], 1u);
+    const uint32_t m = (c + kChunk - 1) / kChunk;
+    for (uint32_t j = 0; j < m && coff + j < chunk_cap; j++) chunks[coff + j] = make_uint2((uint32_t)t, j);
+    coff += m;
+    start = end;
+  }
+  __syncthreads();
   if (tid == 0) {
-    const uint64_t R = s_carry;
-    status->R = R;
-    status->overflow = R > R_cap ? 1u : 0u;
-    uint32_t sum = 0;
+    status->R = total;
+    status->overflow = total > R_cap ? 1u : 0u;
+    misc[0] = ctotal < chunk_cap ? ctotal : chunk_cap;
+    uint32_t acc = 0;
     for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
-      s_cur[c] = sum;
-      sum += s_cls[c];
+      s_cur[c] = acc;
+      acc += s_cls[c];
     }
-    misc[0] = s_ccarry < chunk_cap ? s_ccarry : chunk_cap;
   }
   __syncthreads();
-  for (int t = tid; t < VT; t += kScanThreads1) {
+  for (int t = t0; t < t1; t++) {
     const uint32_t pos = atomicAdd(&s_cur[size_class(tile_count[t])], 1u);
     order[pos] = (uint32_t)t;
   }
@@ -182,9 +183,7 @@ constexpr int kSortWarps = kSortThreads / 32;
 struct ChunkSort {
   uint16_t wcnt[kSortWarps][256];   // per-warp digit counts (<= 32*kSortItems each)
   uint32_t dbase[256];              // output offset of every digit
-  uint32_t scan[kSortWarps];
-  uint32_t dmin, dmax;
-  unsigned long long red_and, red_or;
+  uint32_t scan[8];
 };
 
 __device__ __noinline__ void chunk_radix_pass(ChunkSort &S, const uint64_t *a, uint64_t *b, uint32_t n, int shift,
@@ -217,25 +216,29 @@ __device__ __noinline__ void chunk_radix_pass(ChunkSort &S, const uint64_t *a, u
     }
   }
   __syncthreads();
-  // thread d owns digit d: exclusive prefix over warps, then exclusive scan over digits
-  uint32_t total = 0;
+  // thread d (< 256) owns digit d: exclusive prefix over warps, then exclusive scan over digits
+  uint32_t total = 0, incl = 0;
+  if (tid < 256) {
 #pragma unroll
-  for (int w = 0; w < kSortWarps; w++) {
-    const uint32_t cw = S.wcnt[w][tid];
-    S.wcnt[w][tid] = (uint16_t)total;
-    total += cw;
-  }
-  uint32_t incl = total;
+    for (int w = 0; w < kSortWarps; w++) {
+      const uint32_t cw = S.wcnt[w][tid];
+      S.wcnt[w][tid] = (uint16_t)total;
+      total += cw;
+    }
+    incl = total;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= o) incl += up;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) S.scan[warp] = incl;
   }
-  if (lane == 31) S.scan[warp] = incl;
   __syncthreads();
-  uint32_t wbase = 0;
-  for (int w = 0; w < warp; w++) wbase += S.scan[w];
-  S.dbase[tid] = wbase + incl - total;
+  if (tid < 256) {
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += S.scan[w];
+    S.dbase[tid] = wbase + incl - total;
+  }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < kSortItems; i++) {
@@ -267,36 +270,49 @@ __device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uin
   records[3 * r + 2] = q2;
 }
 
-// Sort = two radix passes on the top 16 significant bits of (depth bits - min depth bits of the chunk)
-// followed by a local fix: runs of equal 16-bit prefix (almost always length 1-3; equal depths land
-// here too) are insertion-sorted on the full (depth bits, index) key by the thread at the run start.
-// A chunk with a run longer than kMaxRun (degenerate depth distribution) is re-sorted by LSD passes
-// over every key byte that varies.  Either way the result is the total order on (depth bits, index).
+// Sort of one chunk = ONE counting pass on the kBinBits leading significant bits of (depth bits - min
+// depth bits of the chunk) -- as many bins as the chunk has slots, slot inside a bin taken with a
+// shared-memory atomic (unordered) -- followed by a local fix: every bin with more than one key
+// (equal depths land here too) is insertion-sorted on the full (depth bits, index) key by the thread
+// that owns the bin's first slot.  A chunk with a bin longer than kMaxRun (degenerate depth
+// distribution) is re-sorted by stable LSD radix passes over every key byte that varies.  Either way
+// the result is the total order on (depth bits, index).
 constexpr uint32_t kMaxRun = 32;
+constexpr int kBinBits = 11;
+constexpr int kBins = 1 << kBinBits;
+static_assert(kBins == kSortThreads * 8, "bin scan assumes 8 bins per thread");
 __global__ void __launch_bounds__(kSortThreads, 4)
 sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
                    const uint2 *__restrict__ ranges, uint2 *inst, const float4 *__restrict__ geom,
                    float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
                    uint32_t *__restrict__ dbg_plist) {
-  __shared__ __align__(16) uint64_t s_buf[2][kChunk];
-  __shared__ ChunkSort S;
+  extern __shared__ __align__(16) uint64_t s_buf[];   // [kChunk] keys
+  __shared__ union {
+    ChunkSort cs;              // fallback passes only
+    uint32_t hist[kBins];      // bin counts, then bin offsets
+  } U;
+  __shared__ uint32_t s_scan[kSortWarps];
+  __shared__ uint32_t s_dmin, s_dmax;
+  __shared__ unsigned long long s_and, s_or;
   if (blockIdx.x >= misc[0]) return;
   const uint2 chunk = chunks[blockIdx.x];
   const uint32_t vt = chunk.x;
   const uint2 range = ranges[vt];
   const uint32_t cstart = range.x + chunk.y * kChunk;
+  if (cstart >= range.y) return;                       // chunk of a list clamped by an instance-capacity overflow
   const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
   const bool single = range.y - range.x <= (uint32_t)kChunk;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
   uint2 *src = inst + cstart;
-  uint64_t *a = s_buf[0], *b = s_buf[1];
   if (tid == 0) {
-    S.dmin = 0xFFFFFFFFu;
-    S.dmax = 0u;
-    S.red_and = ~0ull;
-    S.red_or = 0ull;
+    s_dmin = 0xFFFFFFFFu;
+    s_dmax = 0u;
+    s_and = ~0ull;
+    s_or = 0ull;
   }
+#pragma unroll
+  for (int i = 0; i < 8; i++) U.hist[tid * 8 + i] = 0;
   __syncthreads();
   uint2 e[kSortItems];
   {
@@ -313,23 +329,26 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
     dmin = __reduce_min_sync(0xFFFFFFFFu, dmin);
     dmax = __reduce_max_sync(0xFFFFFFFFu, dmax);
     if (lane == 0) {
-      atomicMin(&S.dmin, dmin);
-      atomicMax(&S.dmax, dmax);
+      atomicMin(&s_dmin, dmin);
+      atomicMax(&s_dmax, dmax);
     }
   }
   __syncthreads();
-  const uint32_t dmin = S.dmin, span = S.dmax - dmin;
+  const uint32_t dmin = s_dmin, span = s_dmax - dmin;
   const int hi = 32 - __clz(span);                     // significant bits of (depth - dmin); 0 if all equal
-  const int shift0 = hi > 16 ? hi - 16 : 0;
+  const int shift0 = hi > kBinBits ? hi - kBinBits : 0;
+  // bin + slot of every key; AND/OR of the packed keys for the fallback's byte skipping
+  uint32_t slot[kSortItems];
   {
-    // pack (depth bits - dmin, index in view); AND/OR of the keys for the fallback's byte skipping
     uint64_t k_and = ~0ull, k_or = 0ull;
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
       const uint32_t k = i * kSortThreads + tid;
+      slot[i] = 0;
       if (k < n) {
-        const uint64_t key = ((uint64_t)(e[i].x - dmin) << 32) | (e[i].y - gbase);
-        a[k] = key;
+        const uint32_t rel = e[i].x - dmin;
+        slot[i] = atomicAdd(&U.hist[rel >> shift0], 1u);
+        const uint64_t key = ((uint64_t)rel << 32) | (e[i].y - gbase);
         k_and &= key;
         k_or |= key;
       }
@@ -340,49 +359,76 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
       k_or |= __shfl_xor_sync(0xFFFFFFFFu, k_or, o);
     }
     if (lane == 0) {
-      atomicAnd(&S.red_and, (unsigned long long)k_and);
-      atomicOr(&S.red_or, (unsigned long long)k_or);
+      atomicAnd(&s_and, (unsigned long long)k_and);
+      atomicOr(&s_or, (unsigned long long)k_or);
     }
   }
   __syncthreads();
-  if (hi > 0) {
-    chunk_radix_pass(S, a, b, n, 32 + shift0, tid);
-    uint64_t *t = a; a = b; b = t;
-  }
-  if (hi > 8) {
-    chunk_radix_pass(S, a, b, n, 32 + shift0 + 8, tid);
-    uint64_t *t = a; a = b; b = t;
-  }
-  // local fix: full-key insertion sort inside runs of equal prefix
-  const int ps = 32 + shift0;
+  // exclusive scan of the bin counts: 8 bins per thread, warp scan, warp totals
   bool too_long = false;
-  for (uint32_t k = tid; k < n; k += kSortThreads) {
-    const uint64_t pk = a[k] >> ps;
-    if (k > 0 && (a[k - 1] >> ps) == pk) continue;     // not a run start
-    uint32_t len = 1;
-    while (len <= kMaxRun && k + len < n && (a[k + len] >> ps) == pk) len++;
-    if (len > kMaxRun) {
-      too_long = true;
-      continue;
+  {
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      c[i] = U.hist[tid * 8 + i];
+      too_long |= c[i] > kMaxRun;
+      sum += c[i];
     }
-    for (uint32_t i = 1; i < len; i++) {
-      const uint64_t x = a[k + i];
-      uint32_t j = i;
-      while (j > 0 && a[k + j - 1] > x) {
-        a[k + j] = a[k + j - 1];
-        j--;
-      }
-      a[k + j] = x;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t base = incl - sum;
+    for (int w = 0; w < warp; w++) base += s_scan[w];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      U.hist[tid * 8 + i] = base;
+      base += c[i];
     }
   }
-  if (__syncthreads_or(too_long)) {
-    const uint64_t vary = S.red_and ^ S.red_or;
+  __syncthreads();
+  // the fallback's second buffer is the chunk's own (already consumed) slice of inst in global memory
+  uint64_t *a = s_buf, *b = reinterpret_cast<uint64_t *>(src);
+#pragma unroll
+  for (int i = 0; i < kSortItems; i++) {
+    const uint32_t k = i * kSortThreads + tid;
+    if (k < n) {
+      const uint32_t rel = e[i].x - dmin;
+      a[U.hist[rel >> shift0] + slot[i]] = ((uint64_t)rel << 32) | (e[i].y - gbase);
+    }
+  }
+  too_long = __syncthreads_or(too_long);
+  if (!too_long) {
+    // local fix: the thread that owns the first slot of a bin insertion-sorts the bin on the full key
+    const int ps = 32 + shift0;
+    for (uint32_t k = tid; k < n; k += kSortThreads) {
+      const uint64_t pk = a[k] >> ps;
+      if (k > 0 && (a[k - 1] >> ps) == pk) continue;     // not the first slot of its bin
+      uint32_t len = 1;
+      while (k + len < n && (a[k + len] >> ps) == pk) len++;
+      for (uint32_t i = 1; i < len; i++) {
+        const uint64_t x = a[k + i];
+        uint32_t j = i;
+        while (j > 0 && a[k + j - 1] > x) {
+          a[k + j] = a[k + j - 1];
+          j--;
+        }
+        a[k + j] = x;
+      }
+    }
+  } else {
+    const uint64_t vary = s_and ^ s_or;
     for (int shift = 0; shift < 64; shift += 8) {
       if (((vary >> shift) & 255ull) == 0) continue;   // digit constant over the chunk: identity pass
-      chunk_radix_pass(S, a, b, n, shift, tid);
+      chunk_radix_pass(U.cs, a, b, n, shift, tid);
       uint64_t *t = a; a = b; b = t;
     }
   }
+  __syncthreads();
   if (single) {
     // the whole tile list: gather in sorted order
     const uint32_t ty = dgx.div(tile);
@@ -395,6 +441,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
     }
   } else {
     // one of several chunks of its tile: leave the sorted absolute keys in place for merge_gather
+    // (a may already be that slice after an odd number of fallback passes: same index, in place)
     uint64_t *dst = reinterpret_cast<uint64_t *>(src);
     for (uint32_t k = tid; k < n; k += kSortThreads) dst[k] = a[k] + ((uint64_t)dmin << 32);
   }
@@ -416,10 +463,14 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ ch
   if (nt <= (uint32_t)kChunk) return;                  // single-chunk tile: finished by sort_chunks
   const uint32_t m = (nt + kChunk - 1) / kChunk;
   const uint32_t cstart = range.x + chunk.y * kChunk;
+  if (cstart >= range.y) return;
   const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
   const int tid = threadIdx.x;
   const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
   const uint64_t *keys = reinterpret_cast<const uint64_t *>(inst);
+  // a thread owns keys k = i*256 + tid (consecutive lanes = consecutive keys, so the final positions
+  // of a warp are nearly consecutive and the record stores coalesce); its keys ascend with i, and so
+  // do their lower bounds in another sorted chunk
   uint64_t key[kSortItems];
   uint32_t pos[kSortItems];
 #pragma unroll
@@ -434,10 +485,11 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ ch
     __syncthreads();
     for (uint32_t k = tid; k < on; k += kSortThreads) s_other[k] = keys[ostart + k];
     __syncthreads();
+    uint32_t lo = 0;
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
-      // lower bound of key[i] in s_other[0, on)
-      uint32_t lo = 0, len = on;
+      // lower bound of key[i] in s_other[lo, on)
+      uint32_t len = on - lo;
       while (len > 0) {
         const uint32_t half = len >> 1;
         const bool less = s_other[lo + half] < key[i];
@@ -500,7 +552,10 @@ cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, c
   const FastDiv dT = make_fastdiv((uint32_t)L.T), dgx = make_fastdiv((uint32_t)L.gx);
   // grid = upper bound of the chunk count (the scan wrote the exact one to misc[0]); surplus CTAs exit
   const int grid = (int)L.n_chunks;
-  sort_chunks_kernel<<<grid, kSortThreads, 0, s>>>(
+  const size_t sort_smem = (size_t)kChunk * 8;
+  cudaError_t e = cudaFuncSetAttribute(sort_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+  if (e != cudaSuccess) return e;
+  sort_chunks_kernel<<<grid, kSortThreads, sort_smem, s>>>(
       d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
       (const uint2 *)(state + L.pub.off_ranges), (uint2 *)(temp + L.t_inst), (const float4 *)(state + L.pub.off_geom),
       (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);

@@ -26,7 +26,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr int kMaxIlpB = 2;
-constexpr int kDirectMax = 8;    // <= this many contributing lanes: no warp reduction, direct REDs
+constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

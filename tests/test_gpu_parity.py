@@ -109,6 +109,32 @@ def test_edge_cases_empty_culled_single(cuda_device):
     _full_compare(tie, [cam], BG)
 
 
+def test_long_tile_lists_with_depth_ties_and_merge(cuda_device):
+    """Tile lists longer than one sort chunk (2048) whose depths collide massively: exercises the
+    chunk sort's degenerate-bin fallback (stable LSD passes through global scratch) and the
+    rank-merge of several chunks; the order must still be (depth bits, Gaussian index)."""
+    cam = scenes.simple_camera(48, 48)
+    sc = scenes.random_scene(12000, seed=7, behind_frac=0, huge_frac=0)
+    sc.means3D[:, 2] = np.where(np.arange(sc.P) % 3 == 0, 0.25, 0.2500001).astype(np.float32)   # two depth values
+    info = _full_compare(sc, [cam], BG)
+    gout, _, _ = util.run_gpu(sc, [cam], BG)
+    r = gout[0]["ranges"].astype(np.int64)
+    assert (r[:, 1] - r[:, 0]).max() > 2048
+    # and a continuous depth distribution on long lists (the common path: counting pass + local fix)
+    sc2 = scenes.random_scene(12000, seed=8, behind_frac=0, huge_frac=0)
+    _full_compare(sc2, [cam], BG)
+
+
+def test_more_tiles_than_shared_memory_counters(cuda_device):
+    """> 16384 tiles per view: preprocess / duplicate fall back from per-block shared-memory tile
+    counters to one global atomic per instance."""
+    cam = scenes.simple_camera(2064, 2064, fx=3000.0)
+    sc = scenes.random_scene(400, seed=9, behind_frac=0, huge_frac=0.02)
+    gout, _, info = util.run_gpu(sc, [cam], BG)
+    f, _ = util.run_oracle(sc, cam, BG)
+    _check_forward(f, gout[0])
+
+
 def _aniso_scene(seed, stretch, squash):
     sc = scenes.random_scene(1200, seed=seed, huge_frac=0.0)
     rng = np.random.default_rng(seed)

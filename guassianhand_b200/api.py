@@ -57,6 +57,8 @@ class _Workspace:
         self.temp = torch.empty(0, dtype=torch.uint8, device=device)
         self.cap = {}          # (P, V, H, W) -> entries
         self.pinned = torch.zeros(64, 4, dtype=torch.int64).pin_memory()   # 64 slots of GhrStatus
+        self.pinned_np = self.pinned.numpy()      # same memory: reading a status word costs no tensor op
+        self.pinned_ptr = self.pinned.data_ptr()
         self.slot = 0
         self.pending = []      # deferred checks: (row, seq, key, cap, fixed_cap)
 
@@ -73,21 +75,22 @@ class _Workspace:
         return c
 
     def next_slot(self):
-        self.slot = (self.slot + 1) % self.pinned.shape[0]
-        row = self.pinned[self.slot]
-        if any(p[0] is row or p[0].data_ptr() == row.data_ptr() for p in self.pending):
+        """Returns (numpy row view [4] int64, host address) of the next pinned GhrStatus slot."""
+        self.slot = (self.slot + 1) % self.pinned_np.shape[0]
+        if any(p[5] == self.slot for p in self.pending):
             self.verify_pending(wait=True)          # the ring wrapped around an unverified report
-        row.zero_()
-        return row
+        row = self.pinned_np[self.slot]
+        row[:] = 0
+        return row, self.pinned_ptr + 32 * self.slot
 
     def verify_pending(self, wait: bool = False):
         """check="deferred": look at the status reports of earlier forwards that have arrived (all of
         them when `wait`); raises if one overflowed its capacity (its outputs were invalid)."""
         keep = []
-        for row, seq, key, cap, fixed in self.pending:
+        for row, seq, key, cap, fixed, slot in self.pending:
             if int(row[2]) != seq:
                 if not wait:
-                    keep.append((row, seq, key, cap, fixed))
+                    keep.append((row, seq, key, cap, fixed, slot))
                     continue
                 torch.cuda.synchronize(self.device)
                 if int(row[2]) != seq:
@@ -108,8 +111,27 @@ _workspaces = {}
 _seq = itertools.count(1)
 
 
+def _raw_stream(dev) -> int:
+    """cudaStream_t of torch's current stream on `dev` (no Stream object is built)."""
+    return torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+_layouts = {}
+
+
+def _layout(P, V, H, W, M, sh_degree, cap):
+    key = (P, V, H, W, M, sh_degree, cap)
+    lay = _layouts.get(key)
+    if lay is None:
+        if len(_layouts) > 256:
+            _layouts.clear()
+        lay = _layouts[key] = N.layout(*key)
+    return lay
+
+
 def _workspace(device, stream) -> _Workspace:
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream.cuda_stream)
+    raw = stream if isinstance(stream, int) else stream.cuda_stream
+    key = (device.index if device.index is not None else torch.cuda.current_device(), raw)
     with _ws_lock:
         ws = _workspaces.get(key)
         if ws is None:
@@ -182,7 +204,7 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
     under CUDA-graph capture)."""
     L = N.lib()
     dev = means3D.device
-    stream = torch.cuda.current_stream(dev)
+    stream = _raw_stream(dev)
     ws = _workspace(dev, stream)
     P = means3D.shape[0]
     M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
@@ -191,7 +213,7 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
         ws.verify_pending()
     cap = int(R_cap) if R_cap is not None else ws.capacity(key, P, cams.V)
     while True:
-        lay = N.layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
+        lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
         state = torch.empty(lay.state_bytes, dtype=torch.uint8, device=dev)
         temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
         color = torch.empty(cams.V, 3, cams.H, cams.W, dtype=torch.float32, device=dev)
@@ -215,17 +237,16 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
         seq = next(_seq)
         a.seq = seq
         if check in ("poll", "deferred"):
-            row = ws.next_slot()
-            a.host_status = row.data_ptr()
-        N.check(L.ghr_forward(C.byref(a), stream.cuda_stream), "ghr_forward")
+            row, a.host_status = ws.next_slot()
+        N.check(L.ghr_forward(C.byref(a), stream), "ghr_forward")
         R = None
         if check == "deferred":
-            ws.pending.append((row, seq, key, cap, R_cap is not None))
+            ws.pending.append((row, seq, key, cap, R_cap is not None, ws.slot))
         if check == "poll":
             t0 = time.perf_counter()
             while int(row[2]) != seq:           # reserved[0]
                 if time.perf_counter() - t0 > 10.0:
-                    stream.synchronize()
+                    torch.cuda.current_stream(dev).synchronize()
                     if int(row[2]) != seq:
                         raise RuntimeError("ghr_forward: status report never arrived")
             R = int(row[0])
@@ -256,11 +277,11 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     dL_dmeans2D which is per view)."""
     L = N.lib()
     dev = means3D.device
-    stream = torch.cuda.current_stream(dev)
+    stream = _raw_stream(dev)
     ws = _workspace(dev, stream)
     P = means3D.shape[0]
     M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
-    lay = N.layout(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
+    lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
     temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
     a = N.GhrBackwardArgs()
     _fill_common(a, cams, P, M, sh_degree, R_cap, scale_modifier, flags, means3D, opacities, scales, rotations, cov3D,
@@ -275,15 +296,17 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     g = None if accumulate_into is None else dict(accumulate_into)
     a.accumulate = 1 if (g is not None and accumulate) else 0
     if g is None:
-        new = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
-        g = dict(dL_dmeans3D=new(P, 3), dL_dopacity=new(P, 1), dL_dcov3D=new(P, 6))
-        if M > 0:
-            g["dL_dsh"] = new(P, M, 3)
-        else:
-            g["dL_dcolors"] = new(P, 3)
+        # one allocation, carved into the per-attribute gradients (each block 16-byte aligned)
+        shapes = [("dL_dmeans3D", (P, 3)), ("dL_dopacity", (P, 1)), ("dL_dcov3D", (P, 6))]
+        shapes.append(("dL_dsh", (P, M, 3)) if M > 0 else ("dL_dcolors", (P, 3)))
         if scales is not None and scales.numel():
-            g["dL_dscales"] = new(P, 3)
-            g["dL_drotations"] = new(P, 4)
+            shapes += [("dL_dscales", (P, 3)), ("dL_drotations", (P, 4))]
+        sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for _, sh in shapes]
+        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+        g, o = {}, 0
+        for (name, sh), n in zip(shapes, sizes):
+            g[name] = flat[o:o + int(torch.Size(sh).numel())].view(sh)
+            o += n
     if want_means2D:
         g["dL_dmeans2D"] = torch.empty(cams.V, P, 3, dtype=torch.float32, device=dev)
     if want_conic:
@@ -293,7 +316,7 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
         setattr(a, k, _ptr(g.get(k)))
     if stage_events is not None:
         a.stage_events = stage_events.ptr()
-    N.check(L.ghr_backward(C.byref(a), stream.cuda_stream), "ghr_backward")
+    N.check(L.ghr_backward(C.byref(a), stream), "ghr_backward")
     return g
 
 

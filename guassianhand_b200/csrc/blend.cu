@@ -68,7 +68,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32
 
 constexpr int kMaskBytes = kStageN + 16;   // a stage's mask bytes start at a 16-byte boundary at or before it
 struct __align__(128) StageBuf {
-  float4 rec[kStages][kStageN * 3];
+  float4 rec[kStages][kStageN * 3 + 3];   // + one all-zero record (index kStageN): queue padding, alpha = 0
   uint8_t msk[kStages][kMaskBytes];
   uint64_t full[kStages];
   uint64_t empty[kStages];
@@ -99,6 +99,7 @@ __device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
     sb.tmax = 0;
     mbar_fence_init();
   }
+  if (tid < 3 * kStages) sb.rec[tid / 3][kStageN * 3 + tid % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 }
 
@@ -123,9 +124,10 @@ __device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
 // instances whose sub-block mask (one byte per instance, written by gather_ranges) has this warp's
 // bit set.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the blend loop then
 // takes kIlp indices per iteration from one broadcast LDS instead of peeling bits off a mask.
-// Survivor i is q[kQPad + i]; kQPad entries of index 0 pad both ends.  Returns the survivor count.
+// Survivor i is q[kQPad + i]; kQPad entries pad both ends (front: index 0, back: `pad` -- the forward
+// passes kStageN, its all-zero record whose alpha is 0).  Returns the survivor count.
 __device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt, uint32_t limit, int warp, int lane,
-                                                uint8_t *q) {
+                                                uint8_t *q, uint32_t pad) {
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t total = 0;
 #pragma unroll
@@ -137,7 +139,7 @@ __device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt
     if (hit) q[kQPad + total + __popc(m & lt)] = (uint8_t)e;
     total += __popc(m);
   }
-  if (lane < kQPad) q[kQPad + total + lane] = 0;     // q[0, kQPad) stays 0 from the kernel prologue
+  if (lane < kQPad) q[kQPad + total + lane] = (uint8_t)pad;
   __syncwarp();
   return total;
 }
@@ -227,7 +229,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         ckpt[((size_t)(range.x / kSeg) + vt + (r * kStageN) / kSeg) * 256 + tid] = make_float4(Tr, C0, C1, C2);
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const float4 *rec = &sb.rec[s][0];
-      const uint32_t total = build_queue(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, kStageN, warp, lane, q);
+      const uint32_t total = build_queue(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, kStageN, warp, lane, q, kStageN);
       for (uint32_t b = 0; b < total; b += kIlpF) {
         // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
         // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
@@ -247,18 +249,20 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
           const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
           const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
           const float alpha = fminf(0.99f, fmul(bq.y, exp_fast(power)));
-          al[k] = (b + k < total && power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;
+          al[k] = (power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;   // padding: opacity 0 -> alpha 0
         }
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
           float a = done ? 0.f : al[k];
           const float test_T = fmul(Tr, fsub(1.f, a));          // a == 0: test_T == Tr exactly
-          const bool term = a != 0.f && test_T < 0.0001f;        // the stopping Gaussian is not blended
+          // Tr >= 1e-4 always holds (the stopping Gaussian is never applied), so test_T < 1e-4 implies a != 0
+          const bool term = test_T < 0.0001f;
           done = done || term;
           a = term ? 0.f : a;
-          C0 = ffma(fmul(col[k].x, a), Tr, C0);
-          C1 = ffma(fmul(col[k].y, a), Tr, C1);
-          C2 = ffma(fmul(col[k].z, a), Tr, C2);
+          const float w = fmul(a, Tr);
+          C0 = ffma(col[k].x, w, C0);
+          C1 = ffma(col[k].y, w, C1);
+          C2 = ffma(col[k].z, w, C2);
           Tr = term ? Tr : test_T;
           last = a != 0.f ? r * kStageN + jj[k] + 1 : last;
         }
@@ -419,7 +423,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
     const uint32_t scnt = min((uint32_t)kStageN, cnt - sub * kStageN);
     const float4 *rec = s_rec + 3 * sub * kStageN;
     // survivors of this warp's sub-block among the instances that precede the warp's last contributor
-    const uint32_t total = build_queue(&s_msk[(g0 & 15u) + sub * kStageN], scnt, wlast - pos0, warp, lane, q);
+    const uint32_t total = build_queue(&s_msk[(g0 & 15u) + sub * kStageN], scnt, wlast - pos0, warp, lane, q, 0u);
     for (uint32_t b = 0; b < total; b += kIlpB) {
       // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
       float al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB], cdk[kIlpB];

@@ -259,10 +259,9 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
           const bool term = test_T < 0.0001f;
           done = done || term;
           a = term ? 0.f : a;
-          const float w = fmul(a, Tr);
-          C0 = ffma(col[k].x, w, C0);
-          C1 = ffma(col[k].y, w, C1);
-          C2 = ffma(col[k].z, w, C2);
+          C0 = ffma(fmul(col[k].x, a), Tr, C0);                 // upstream's order: (c * alpha) * T
+          C1 = ffma(fmul(col[k].y, a), Tr, C1);
+          C2 = ffma(fmul(col[k].z, a), Tr, C2);
           Tr = term ? Tr : test_T;
           last = a != 0.f ? r * kStageN + jj[k] + 1 : last;
         }

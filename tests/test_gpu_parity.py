@@ -19,7 +19,7 @@ GRAD_KEYS = {"dL_dmeans3D": "dL_dmeans3D", "dL_dcolors": "dL_dcolors", "dL_dopac
              "dL_dcov3D": "dL_dcov3D", "dL_dsh": "dL_dsh", "dL_dscales": "dL_dscales", "dL_drots": "dL_drotations"}
 
 
-def _check_forward(f, g):
+def _check_forward(f, g, img_tol=IMG_TOL):
     """f: oracle dict, g: CUDA dict of one view."""
     for k in ("radii", "tiles_touched"):
         assert np.array_equal(f[k], g[k]), k
@@ -33,8 +33,14 @@ def _check_forward(f, g):
     # 4e-6 relative of the threshold are flagged by the oracle and excluded (and must stay rare)
     assert np.array_equal(f["n_contrib"][~amb], g["n_contrib"][~amb])
     assert amb.mean() < 1e-3
-    assert np.abs(f["out_color"] - g["out_color"]).max() <= IMG_TOL
-    assert np.abs(f["final_T"] - g["final_T"]).max() <= IMG_TOL
+    # the same holds for the image: where a pair sits on the alpha = 1/255 threshold, including or
+    # skipping it moves the pixel by up to c * alpha * T ~ 4e-3; such pixels must be rare and bounded,
+    # every other pixel meets the 1e-5 bar (measured <= 5e-7 even with 2700 contributors per pixel)
+    d_img = np.abs(f["out_color"] - g["out_color"])
+    d_T = np.abs(f["final_T"] - g["final_T"])
+    assert np.where(amb[None], 0, d_img).max() <= img_tol
+    assert np.where(amb, 0, d_T).max() <= img_tol
+    assert d_img.max() <= 1e-2 and d_T.max() <= 1e-2
 
 
 def _check_grads(oracle_sum, ggrad):
@@ -235,3 +241,42 @@ def test_full_size_c2_properties(cuda_device):
         assert np.array_equal(a["n_contrib"], b["n_contrib"])             # geometry-only quantities
         assert np.abs(a["out_color"] + b["out_color"] - c["out_color"]).max() < 5e-6
         assert np.abs(c["out_color"][0] - (1.0 - c["final_T"])).max() < 5e-6     # mask render = 1 - T
+
+
+def test_full_size_c4_dense_sh3(cuda_device):
+    """BASELINE.json config 4 (1M Gaussians, SH degree 3, 1024x1024): one view forward + backward
+    against the oracle, plus sortedness / range partition of the exported keys.  Tile lists reach
+    tens of thousands of instances here (dozens of sort chunks per tile, hundreds of backward
+    segments)."""
+    sc = scenes.two_hand_scene(1000000, seed=0, sh_degree=3, tile=4)
+    cam = scenes.fibonacci_cameras(2, 1024, 1024, seed=0)[1]
+    bg0 = np.zeros(3, np.float32)
+    info = _full_compare(sc, [cam], bg0)
+    assert info["R"] > 1000000
+    # the same million Gaussians packed into ONE pair of hands: ~15M instances, tile lists of up to
+    # ~77k (38 sort chunks merged per tile, 300 backward segments); forward against the oracle
+    dense = scenes.two_hand_scene(1000000, seed=0, sh_degree=3)
+    cam0 = scenes.fibonacci_cameras(2, 1024, 1024, seed=0)[0]
+    gout, _, dinfo = util.run_gpu(dense, [cam0], bg0)
+    f, _ = util.run_oracle(dense, cam0, bg0)
+    _check_forward(f, gout[0])
+    assert dinfo["R"] > 10000000 and (f["ranges"][:, 1].astype(np.int64) - f["ranges"][:, 0]).max() > 50000
+    k = gout[0]["keys"].astype(np.uint64)
+    assert (k[1:] >= k[:-1]).all()
+    same = k[1:] == k[:-1]
+    assert (gout[0]["point_list"][1:][same] > gout[0]["point_list"][:-1][same]).all()
+    r = gout[0]["ranges"].astype(np.int64)
+    assert (r[:, 1] - r[:, 0]).sum() == gout[0]["R"] == gout[0]["tiles_touched"].sum()
+
+
+def test_full_size_c5_1080p_forward(cuda_device):
+    """BASELINE.json config 5 shape (forward only, 1920x1080 = 8160 tiles per view): two poses in
+    one call against the oracle."""
+    sc = scenes.two_hand_scene(60000, seed=0)
+    cams = scenes.fibonacci_cameras(4, 1080, 1920, seed=2)[:2]
+    bg0 = np.zeros(3, np.float32)
+    gout, _, info = util.run_gpu(sc, cams, bg0)
+    assert info["overflow"] == 0
+    for v, cam in enumerate(cams):
+        f, _ = util.run_oracle(sc, cam, bg0)
+        _check_forward(f, gout[v])

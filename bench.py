@@ -502,10 +502,16 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
                                     "sample": f"{done} single views of the same C2 scene, fwd+bwd, "
                                               f"oracle/gs_oracle.c OpenMP on {nthr} threads"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: destroy_process_group() with NCCL calls captured in live
+        # CUDA graphs can block forever (seen at N=2), and the line above is already out.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -11,14 +11,15 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 7
+GHR_ABI_VERSION = 8
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
 FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
 
 EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",
            "ghr_mark_visible", "ghr_read_status_async", "ghr_event_create", "ghr_event_destroy", "ghr_event_record",
-           "ghr_event_elapsed_ms", "ghr_fp32_probe"]
+           "ghr_event_elapsed_ms", "ghr_fp32_probe", "ghr_attributes_forward", "ghr_attributes_backward"]
+GHR_ATTR_XYZ_OFFSET, GHR_ATTR_RESTRICT_OFFSET, GHR_ATTR_CLIP_SCALING = 1, 2, 4
 
 _vp = C.c_void_p
 
@@ -72,6 +73,19 @@ class GhrBackwardArgs(C.Structure):
     ]
 
 
+class GhrAttributeArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("flags", C.c_uint32), ("clip_scaling", C.c_float)] + [(n, _vp) for n in (
+        "xyz_raw", "pts", "scaling_raw", "rotation_raw", "opacity_raw", "rgb_raw", "xyz_b", "opacity_b", "color_w0",
+        "color_w1", "color_b0", "means3D", "scales", "rotations", "opacities", "colors")]
+
+
+class GhrAttributeGrads(C.Structure):
+    _fields_ = [(n, _vp) for n in (
+        "dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dcolors", "d_xyz_raw", "d_pts",
+        "d_scaling_raw", "d_rotation_raw", "d_opacity_raw", "d_rgb_raw", "d_xyz_b", "d_opacity_b", "d_color_w0",
+        "d_color_w1", "d_color_b0")]
+
+
 _lib = None
 
 
@@ -107,7 +121,11 @@ def lib():
     L.ghr_fp32_probe.argtypes = [C.c_int32, _vp, C.POINTER(C.c_double), _vp]
     L.ghr_struct_size.restype = C.c_size_t
     L.ghr_struct_size.argtypes = [C.c_char_p]
-    for cls in (GhrDims, GhrLayout, GhrStatus, GhrForwardArgs, GhrBackwardArgs):
+    L.ghr_attributes_forward.restype = C.c_int
+    L.ghr_attributes_forward.argtypes = [C.POINTER(GhrAttributeArgs), _vp]
+    L.ghr_attributes_backward.restype = C.c_int
+    L.ghr_attributes_backward.argtypes = [C.POINTER(GhrAttributeArgs), C.POINTER(GhrAttributeGrads), _vp]
+    for cls in (GhrDims, GhrLayout, GhrStatus, GhrForwardArgs, GhrBackwardArgs, GhrAttributeArgs, GhrAttributeGrads):
         want = L.ghr_struct_size(cls.__name__.encode())
         if want != C.sizeof(cls):
             raise RuntimeError(f"ctypes mirror of {cls.__name__} is {C.sizeof(cls)} bytes, libghr.so says {want}")

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libghr.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "preprocess_bwd.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "preprocess_bwd.cu", "attributes.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",

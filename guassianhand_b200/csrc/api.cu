@@ -120,6 +120,8 @@ size_t ghr_struct_size(const char *name) {
   if (!strcmp(name, "GhrStatus")) return sizeof(GhrStatus);
   if (!strcmp(name, "GhrForwardArgs")) return sizeof(GhrForwardArgs);
   if (!strcmp(name, "GhrBackwardArgs")) return sizeof(GhrBackwardArgs);
+  if (!strcmp(name, "GhrAttributeArgs")) return sizeof(GhrAttributeArgs);
+  if (!strcmp(name, "GhrAttributeGrads")) return sizeof(GhrAttributeGrads);
   return 0;
 }
 

@@ -41,7 +41,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 7
+#define GHR_ABI_VERSION 8
 #define GHR_SEGMENT 256 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
@@ -190,6 +190,51 @@ int ghr_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both must h
 /* FP32 roofline denominator: launches a dependent-FMA kernel (8 chains/thread) on `cuda_stream`;
  * *flops_out = floating-point operations it executes.  Time it with events. `sink` = 4 device bytes. */
 int ghr_fp32_probe(int32_t iters, float *sink, double *flops_out, void *cuda_stream);
+
+/* ---- fused attribute head ----
+ * Activations of GSLayer.forward (/root/reference/tgs/models/renderer_one_shot.py:191-214: normalize,
+ * trunc_exp (+clamp), sigmoid, xyz offset) and the interaction-aware attribute blending of
+ * forward_single_view (:298-334: + xyz_b, + opacity_b, colour*w0 + w1 - 1 + b0), use_rgb path, in one
+ * launch; outputs are the tensors ghr_forward takes.  All pointers device fp32, contiguous. */
+#define GHR_ATTR_XYZ_OFFSET 1u      /* GSLayer.Config.xyz_offset (:161) */
+#define GHR_ATTR_RESTRICT_OFFSET 2u /* GSLayer.Config.restrict_offset (:162) */
+#define GHR_ATTR_CLIP_SCALING 4u    /* clip_scaling is set (:164) */
+
+typedef struct GhrAttributeArgs {
+  int32_t P;
+  uint32_t flags;
+  float clip_scaling;
+  /* head outputs (after the Linear layers) and the points they offset */
+  const float *xyz_raw;      /* [P,3] */
+  const float *pts;          /* [P,3] */
+  const float *scaling_raw;  /* [P,3] */
+  const float *rotation_raw; /* [P,4] */
+  const float *opacity_raw;  /* [P]   */
+  const float *rgb_raw;      /* [P,3] */
+  /* blending terms, each may be NULL */
+  const float *xyz_b;        /* [P,3] */
+  const float *opacity_b;    /* [P]   */
+  const float *color_w0;     /* [P,3] = color_w.view(-1,16,3)[:,0,:] */
+  const float *color_w1;     /* [P,3] = color_w.view(-1,16,3)[:,1,:] */
+  const float *color_b0;     /* [P,3] = color_b.view(-1,16,3)[:,0,:] */
+  /* outputs */
+  float *means3D;            /* [P,3] */
+  float *scales;             /* [P,3] */
+  float *rotations;          /* [P,4] */
+  float *opacities;          /* [P]   */
+  float *colors;             /* [P,3] */
+} GhrAttributeArgs;
+
+typedef struct GhrAttributeGrads {
+  /* incoming: gradients w.r.t. the five outputs (NULL = zero) */
+  const float *dL_dmeans3D, *dL_dscales, *dL_drotations, *dL_dopacity, *dL_dcolors;
+  /* outgoing (NULL = not wanted) */
+  float *d_xyz_raw, *d_pts, *d_scaling_raw, *d_rotation_raw, *d_opacity_raw, *d_rgb_raw;
+  float *d_xyz_b, *d_opacity_b, *d_color_w0, *d_color_w1, *d_color_b0;
+} GhrAttributeGrads;
+
+int ghr_attributes_forward(const GhrAttributeArgs *args, void *cuda_stream);
+int ghr_attributes_backward(const GhrAttributeArgs *args, const GhrAttributeGrads *grads, void *cuda_stream);
 
 /* Enqueue an async copy of GhrStatus from `state` into pinned host memory `host_status`. */
 int ghr_read_status_async(const void *state, GhrStatus *host_status, void *cuda_stream);

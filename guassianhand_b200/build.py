@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         f.write(log)
     if verbose:
         print(log)
-    cmd = [nvcc, "-shared", "-o", OUT, *[r[0] for r in res], "-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *[r[0] for r in res], "-lcudart"]
     subprocess.check_call(cmd)
     return OUT
 

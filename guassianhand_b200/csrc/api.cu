@@ -51,7 +51,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->n_slots = (size_t)d.R_cap / GHR_SEGMENT + VT + 1;
   L->pub.off_tilefinal = o; o = align_up(o + VT * 256 * 16);
   L->pub.off_ckpt = o;     o = align_up(o + L->n_slots * 256 * 16);
-  L->pub.off_units = o;    o = align_up(o + L->n_slots * 8);
+  L->pub.off_units = o;    o = align_up(o + L->n_slots * 16);
   L->pub.state_bytes = o;
 
   // ---- temp (forward): zeroed prefix first ----

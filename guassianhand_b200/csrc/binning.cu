@@ -21,6 +21,8 @@
 //                        gathers its records straight to their final place.
 // No global sort, no cross-block prefix: all work items are uniform chunks, independent after the scan.  Result: bit for
 // bit the upstream order (checked against the oracle's sorted keys / point list / ranges).
+#include <cstdlib>
+
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -50,22 +52,24 @@ constexpr int kClasses = 34;
 // One CTA: every thread owns a run of consecutive tiles, sums it, one block scan of the 1024 run
 // totals, then walks its run again.
 __global__ void __launch_bounds__(kScanThreads1)
-tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, const uint32_t *__restrict__ tile_count,
+tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, int chunk_log2,
+                          const uint32_t *__restrict__ tile_count,
                           uint2 *__restrict__ ranges, uint32_t *__restrict__ order, uint2 *__restrict__ chunks,
                           uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
   __shared__ uint64_t s_warp[kScanThreads1 / 32];
   __shared__ uint32_t s_wchunk[kScanThreads1 / 32];
-  __shared__ uint32_t s_cls[kClasses], s_cur[kClasses];
+  __shared__ uint32_t s_cls[kClasses + 1], s_cur[kClasses + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kClasses) s_cls[tid] = 0;
   const int per = (VT + kScanThreads1 - 1) / kScanThreads1;
   const int t0 = min(VT, tid * per), t1 = min(VT, t0 + per);
+  const uint32_t chunk_mask = (1u << chunk_log2) - 1u;
   uint64_t sum = 0;
   uint32_t csum = 0;
   for (int t = t0; t < t1; t++) {
     const uint32_t c = tile_count[t];
     sum += c;
-    csum += (c + kChunk - 1) / kChunk;
+    csum += (c + chunk_mask) >> chunk_log2;
   }
   uint64_t incl = sum;
   uint32_t cincl = csum;
@@ -93,16 +97,24 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, const uint
     total += s_warp[w];
     ctotal += s_wchunk[w];
   }
-  for (int t = t0; t < t1; t++) {
-    const uint32_t c = tile_count[t];
-    const uint64_t end = start + c;
-    ranges[t] = c ? make_uint2((uint32_t)(start < R_cap ? start : R_cap), (uint32_t)(end < R_cap ? end : R_cap))
-                  : make_uint2(0u, 0u);
-    atomicAdd(&s_cls[size_class(c)], 1u);
-    const uint32_t m = (c + kChunk - 1) / kChunk;
-    for (uint32_t j = 0; j < m && coff + j < chunk_cap; j++) chunks[coff + j] = make_uint2((uint32_t)t, j);
-    coff += m;
-    start = end;
+  // class counters are warp-aggregated (match.any): most tiles are empty, and 5000 shared-memory atomics
+  // on one address would serialise
+  for (int j = 0; j < per; j++) {
+    const int t = t0 + j;
+    const bool valid = t < t1;
+    const uint32_t c = valid ? tile_count[t] : 0u;
+    const int cls = valid ? size_class(c) : kClasses;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    if (valid) {
+      const uint64_t end = start + c;
+      ranges[t] = c ? make_uint2((uint32_t)(start < R_cap ? start : R_cap), (uint32_t)(end < R_cap ? end : R_cap))
+                    : make_uint2(0u, 0u);
+      if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
+      const uint32_t m = (c + chunk_mask) >> chunk_log2;
+      for (uint32_t q = 0; q < m && coff + q < chunk_cap; q++) chunks[coff + q] = make_uint2((uint32_t)t, q);
+      coff += m;
+      start = end;
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -116,9 +128,17 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, const uint
     }
   }
   __syncthreads();
-  for (int t = t0; t < t1; t++) {
-    const uint32_t pos = atomicAdd(&s_cur[size_class(tile_count[t])], 1u);
-    order[pos] = (uint32_t)t;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int j = 0; j < per; j++) {
+    const int t = t0 + j;
+    const bool valid = t < t1;
+    const int cls = valid ? size_class(tile_count[t]) : kClasses;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(&s_cur[cls], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (valid) order[base + __popc(peers & lt_mask)] = (uint32_t)t;
   }
 }
 
@@ -177,17 +197,20 @@ duplicate_kernel(int P, int gx, int gy, int T, int smem_tiles, uint64_t R_cap, c
 // Keys are 64-bit ((depth bits - min depth bits of the chunk) << 32 | Gaussian index within the view).
 // One stable LSD pass on the 8-bit digit at `shift`, `a` -> `b` (shared memory): items in warp-blocked
 // order (warp, iteration, lane), ranks by match.any + per-warp digit counters.
-constexpr int kSortThreads = 256;
-constexpr int kSortItems = kChunk / kSortThreads;
-constexpr int kSortWarps = kSortThreads / 32;
+// A chunk is kSortItems instances per thread of its CTA: 2048 with 256 threads, 4096 with 512 (larger
+// chunks = fewer multi-chunk tiles and fewer rank passes in merge_gather).
+constexpr int kSortItems = 8;
+template <int kSortThreads>
 struct ChunkSort {
-  uint16_t wcnt[kSortWarps][256];   // per-warp digit counts (<= 32*kSortItems each)
-  uint32_t dbase[256];              // output offset of every digit
+  uint16_t wcnt[kSortThreads / 32][256];   // per-warp digit counts (<= 32*kSortItems each)
+  uint32_t dbase[256];                     // output offset of every digit
   uint32_t scan[8];
 };
 
-__device__ __noinline__ void chunk_radix_pass(ChunkSort &S, const uint64_t *a, uint64_t *b, uint32_t n, int shift,
-                                              int tid) {
+template <int kSortThreads>
+__device__ __noinline__ void chunk_radix_pass(ChunkSort<kSortThreads> &S, const uint64_t *a, uint64_t *b, uint32_t n,
+                                              int shift, int tid) {
+  constexpr int kSortWarps = kSortThreads / 32;
   const int lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   // items per thread this chunk needs (warp-blocked: warp w owns [w*32*it, (w+1)*32*it))
@@ -278,18 +301,21 @@ __device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uin
 // distribution) is re-sorted by stable LSD radix passes over every key byte that varies.  Either way
 // the result is the total order on (depth bits, index).
 constexpr uint32_t kMaxRun = 32;
-constexpr int kBinBits = 11;
-constexpr int kBins = 1 << kBinBits;
-static_assert(kBins == kSortThreads * 8, "bin scan assumes 8 bins per thread");
-__global__ void __launch_bounds__(kSortThreads, 4)
+template <int kSortThreads>
+__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
 sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
                    const uint2 *__restrict__ ranges, uint2 *inst, const float4 *__restrict__ geom,
                    float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
                    uint32_t *__restrict__ dbg_plist) {
+  constexpr int kSortWarps = kSortThreads / 32;
+  constexpr int kChunk = kSortThreads * kSortItems;
+  constexpr int kBins = kChunk;                       // 8 bins per thread in the bin scan
+  constexpr int kBinBits = kSortThreads == 256 ? 11 : 12;
+  static_assert(kBins == 1 << kBinBits, "chunk size");
   extern __shared__ __align__(16) uint64_t s_buf[];   // [kChunk] keys
   __shared__ union {
-    ChunkSort cs;              // fallback passes only
-    uint32_t hist[kBins];      // bin counts, then bin offsets
+    ChunkSort<kSortThreads> cs;   // fallback passes only
+    uint32_t hist[kBins];         // bin counts, then bin offsets
   } U;
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_dmin, s_dmax;
@@ -403,23 +429,30 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
   }
   too_long = __syncthreads_or(too_long);
   if (!too_long) {
-    // local fix: the thread that owns the first slot of a bin insertion-sorts the bin on the full key
+    // local fix: every key ranks itself inside its bin on the full (depth bits, index) key -- keys are
+    // unique, so bin start + #smaller keys of the bin is its final slot.  One key per thread and
+    // iteration, bins hold one or two keys on average: short uniform loops instead of per-bin owners.
     const int ps = 32 + shift0;
-    for (uint32_t k = tid; k < n; k += kSortThreads) {
-      const uint64_t pk = a[k] >> ps;
-      if (k > 0 && (a[k - 1] >> ps) == pk) continue;     // not the first slot of its bin
-      uint32_t len = 1;
-      while (k + len < n && (a[k + len] >> ps) == pk) len++;
-      for (uint32_t i = 1; i < len; i++) {
-        const uint64_t x = a[k + i];
-        uint32_t j = i;
-        while (j > 0 && a[k + j - 1] > x) {
-          a[k + j] = a[k + j - 1];
-          j--;
-        }
-        a[k + j] = x;
+    uint64_t x[kSortItems];
+    uint32_t pos[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) {
+      const uint32_t k = i * kSortThreads + tid;
+      x[i] = 0;
+      pos[i] = 0;
+      if (k < n) {
+        x[i] = a[k];
+        const uint32_t bin = (uint32_t)(x[i] >> ps);
+        const uint32_t start = U.hist[bin], end = bin + 1 < (uint32_t)kBins ? U.hist[bin + 1] : n;
+        uint32_t rank = 0;
+        for (uint32_t j = start; j < end; j++) rank += a[j] < x[i];
+        pos[i] = start + rank;
       }
     }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++)
+      if (i * kSortThreads + tid < n) a[pos[i]] = x[i];
   } else {
     const uint64_t vary = s_and ^ s_or;
     for (int shift = 0; shift < 64; shift += 8) {
@@ -449,11 +482,13 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
 
 // Multi-chunk tiles: one CTA per chunk.  Final position of a key = its index in its own (sorted) chunk
 // + the number of smaller keys in every other chunk of the tile (keys are unique: (depth bits, index)).
-__global__ void __launch_bounds__(kSortThreads, 4)
+template <int kSortThreads>
+__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
 merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
                     const uint2 *__restrict__ ranges, const uint2 *__restrict__ inst, const float4 *__restrict__ geom,
                     float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
                     uint32_t *__restrict__ dbg_plist) {
+  constexpr int kChunk = kSortThreads * kSortItems;
   __shared__ __align__(16) uint64_t s_other[kChunk];
   if (blockIdx.x >= misc[0]) return;
   const uint2 chunk = chunks[blockIdx.x];
@@ -485,18 +520,24 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ ch
     __syncthreads();
     for (uint32_t k = tid; k < on; k += kSortThreads) s_other[k] = keys[ostart + k];
     __syncthreads();
-    uint32_t lo = 0;
+    // lower bound of every key in s_other[0, on): branch-free halving with the thread's kSortItems
+    // searches advancing in lockstep, so their dependent shared-memory probes overlap
+    uint32_t lb[kSortItems];
+#pragma unroll
+    for (int i = 0; i < kSortItems; i++) lb[i] = 0;
+#pragma unroll 1
+    for (uint32_t step = kChunk / 2; step > 0; step >>= 1) {
+#pragma unroll
+      for (int i = 0; i < kSortItems; i++) {
+        const uint32_t probe = lb[i] + step;
+        if (probe <= on && s_other[probe - 1] < key[i]) lb[i] = probe;
+      }
+    }
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
-      // lower bound of key[i] in s_other[lo, on)
-      uint32_t len = on - lo;
-      while (len > 0) {
-        const uint32_t half = len >> 1;
-        const bool less = s_other[lo + half] < key[i];
-        lo = less ? lo + half + 1 : lo;
-        len = less ? len - half - 1 : half;
-      }
-      pos[i] += lo;
+      // (the halving covers [0, kChunk): one last probe settles a full other chunk's final element)
+      if (lb[i] < on && s_other[lb[i]] < key[i]) lb[i]++;
+      pos[i] += lb[i];
     }
   }
   const uint32_t ty = dgx.div(tile);
@@ -514,6 +555,17 @@ __global__ void init_status_kernel(GhrStatus *st, GhrStatus v) { *st = v; }
 
 }  // namespace
 
+// log2 of the sort chunk size: 11 (2048, 256-thread CTAs) or 12 (4096, 512-thread CTAs); the layout's
+// chunk-list capacity is sized for the smaller one.  GHR_CHUNK_LOG2 overrides (A/B only).
+static int chunk_log2() {
+  static const int v = [] {
+    const char *e = getenv("GHR_CHUNK_LOG2");
+    const int x = e ? atoi(e) : 11;
+    return x == 11 ? 11 : 12;
+  }();
+  return v;
+}
+
 cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s) {
   init_status_kernel<<<1, 1, 0, s>>>((GhrStatus *)status, st0);
   return cudaGetLastError();
@@ -523,7 +575,7 @@ cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *s
   const int VT = d.V * L.T;
   if (VT == 0) return cudaSuccess;
   tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
-      VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (const uint32_t *)(temp + L.t_tile_count),
+      VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, chunk_log2(), (const uint32_t *)(temp + L.t_tile_count),
       (uint2 *)(state + L.pub.off_ranges), (uint32_t *)(state + L.pub.off_order), (uint2 *)(temp + L.t_chunks),
       (uint32_t *)(temp + L.t_misc), (GhrStatus *)(state + L.pub.off_status));
   return cudaGetLastError();
@@ -552,18 +604,25 @@ cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, c
   const FastDiv dT = make_fastdiv((uint32_t)L.T), dgx = make_fastdiv((uint32_t)L.gx);
   // grid = upper bound of the chunk count (the scan wrote the exact one to misc[0]); surplus CTAs exit
   const int grid = (int)L.n_chunks;
-  const size_t sort_smem = (size_t)kChunk * 8;
-  cudaError_t e = cudaFuncSetAttribute(sort_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+  auto launch = [&](auto sort_k, auto merge_k, int threads) -> cudaError_t {
+    const size_t sort_smem = (size_t)threads * kSortItems * 8;
+    cudaError_t e = cudaFuncSetAttribute(sort_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    if (e != cudaSuccess) return e;
+    sort_k<<<grid, threads, sort_smem, s>>>(
+        d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
+        (const uint2 *)(state + L.pub.off_ranges), (uint2 *)(temp + L.t_inst),
+        (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
+        (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
+    merge_k<<<grid, threads, 0, s>>>(
+        d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
+        (const uint2 *)(state + L.pub.off_ranges), (const uint2 *)(temp + L.t_inst),
+        (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
+        (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
+    return cudaSuccess;
+  };
+  cudaError_t e = chunk_log2() == 12 ? launch(sort_chunks_kernel<512>, merge_gather_kernel<512>, 512)
+                                     : launch(sort_chunks_kernel<256>, merge_gather_kernel<256>, 256);
   if (e != cudaSuccess) return e;
-  sort_chunks_kernel<<<grid, kSortThreads, sort_smem, s>>>(
-      d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
-      (const uint2 *)(state + L.pub.off_ranges), (uint2 *)(temp + L.t_inst), (const float4 *)(state + L.pub.off_geom),
-      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
-  merge_gather_kernel<<<grid, kSortThreads, 0, s>>>(
-      d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
-      (const uint2 *)(state + L.pub.off_ranges), (const uint2 *)(temp + L.t_inst),
-      (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
-      (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
   return cudaGetLastError();
 }
 

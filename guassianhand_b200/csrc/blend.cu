@@ -144,6 +144,32 @@ __device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt
   return total;
 }
 
+// Forward variant of the survivor queue: entries are the 16-bit shared-memory ADDRESSES of the
+// survivors' records (the kernel's shared window is far below 64 KB), eight of them per LDS.128, so an
+// instance costs one extract and no address arithmetic before its three record loads.
+__device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_t cnt, int warp, int lane, uint16_t *q,
+                                                     uint32_t rec_base, uint32_t pad_addr) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kStageN / 32; w++) {
+    const uint32_t e = w * 32 + lane;
+    bool hit = false;
+    if (e < cnt) hit = (msk[e] >> warp) & 1u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) q[kQPad + total + __popc(m & lt)] = (uint16_t)(rec_base + e * kRecBytes);
+    total += __popc(m);
+  }
+  if (lane < kQPad) q[kQPad + total + lane] = (uint16_t)pad_addr;
+  __syncwarp();
+  return total;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // kIlpF = instances blended per inner iteration (ILP): 4 or 8
 template <int kIlpF>
 __global__ void __launch_bounds__(kBlendThreads, kIlpF <= 4 ? 4 : 3)
@@ -151,10 +177,10 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float4 *__restrict__ tilefinal, float4 *__restrict__ ckpt,
-                     uint2 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
-                     float *__restrict__ out_mask) {
+                     uint4 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
+                     float *__restrict__ out_mask, uint32_t bo_active, uint32_t bo_done) {
   __shared__ StageBuf sb;
-  __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
+  __shared__ __align__(16) uint16_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
   const uint32_t vt = order[blockIdx.x];
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -210,17 +236,19 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
   const bool inside = px < W && py < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px, pyf = (float)py;
-  uint8_t *q = &s_q[warp][0];
-  if (lane < kQPad) q[lane] = 0;
+  uint16_t *q = &s_q[warp][0];
 
-  bool done = !inside;
-  bool wdone = __all_sync(0xFFFFFFFFu, done);
+  // Tw: transmittance while the pixel is live, 0 once it has terminated (or lies outside the image) --
+  // then test_T = 0 keeps `term` set and every later weight is 0; Tr: the last live value (the output)
+  float Tw = inside ? 1.0f : 0.f, Tr = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+  bool wdone = __all_sync(0xFFFFFFFFu, !inside);
   if (wdone && lane == 0) atomicAdd(&sb.done_warps, 1u);
-  float Tr = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
   uint32_t last = 0;
   for (uint32_t r = 0; r < rounds; r++) {
     const int s = r % kStages;
-    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 512u : 32u);
+    // a consumer that waits here is ahead of the tile's slowest warp by the whole ring: it can sleep long
+    // between polls (its wake-up is not on the critical path), the producer polls `empty` tightly
+    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? bo_done : bo_active);
     if (r >= *(volatile uint32_t *)&sb.stop_round) break;
     if (!wdone) {
       // running state at every kSeg-instance boundary: the backward restarts from it (one work unit per
@@ -228,23 +256,29 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       if (r > 0 && (r * kStageN) % kSeg == 0)
         ckpt[((size_t)(range.x / kSeg) + vt + (r * kStageN) / kSeg) * 256 + tid] = make_float4(Tr, C0, C1, C2);
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
-      const float4 *rec = &sb.rec[s][0];
-      const uint32_t total = build_queue(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, kStageN, warp, lane, q, kStageN);
+      const uint32_t rec_base = smem_u32(&sb.rec[s][0]);
+      const uint32_t total = build_queue_addr(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, warp, lane, q, rec_base,
+                                              rec_base + kStageN * kRecBytes);
+      uint32_t lastq = 0;                                     // 1 + queue index of the last blended survivor
       for (uint32_t b = 0; b < total; b += kIlpF) {
         // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
         // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
         // short T / colour update is serial (and branch-free: a rejected pair blends alpha = 0).
-        uint32_t jj[kIlpF];
         float al[kIlpF];
         float4 col[kIlpF];
-        uint32_t packed[kIlpF / 4];
-#pragma unroll
-        for (int w = 0; w < kIlpF / 4; w++) packed[w] = *reinterpret_cast<const uint32_t *>(q + kQPad + b + 4 * w);
+        uint32_t packed[kIlpF / 2];
+        if constexpr (kIlpF == 8) {
+          const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
+          packed[0] = p4.x; packed[1] = p4.y; packed[2] = p4.z; packed[3] = p4.w;
+        } else {
+          const uint2 p2 = *reinterpret_cast<const uint2 *>(q + kQPad + b);
+          packed[0] = p2.x; packed[1] = p2.y;
+        }
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
-          jj[k] = (packed[k >> 2] >> (8 * (k & 3))) & 255u;
-          const float4 a = rec[3 * jj[k]], bq = rec[3 * jj[k] + 1];
-          col[k] = rec[3 * jj[k] + 2];
+          const uint32_t addr = (k & 1) ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu;
+          const float4 a = lds128(addr), bq = lds128(addr + 16);
+          col[k] = lds128(addr + 32);
           const float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
           const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
           const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
@@ -253,24 +287,25 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         }
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
-          float a = done ? 0.f : al[k];
-          const float test_T = fmul(Tr, fsub(1.f, a));          // a == 0: test_T == Tr exactly
-          // Tr >= 1e-4 always holds (the stopping Gaussian is never applied), so test_T < 1e-4 implies a != 0
+          const float test_T = fmul(Tw, fsub(1.f, al[k]));      // alpha == 0: test_T == Tw exactly
+          // a live Tw is >= 1e-4 (the stopping Gaussian is never applied), so a live pixel terminates only
+          // on alpha != 0; a terminated one (Tw == 0) stays terminated
           const bool term = test_T < 0.0001f;
-          done = done || term;
-          a = term ? 0.f : a;
-          C0 = ffma(fmul(col[k].x, a), Tr, C0);                 // upstream's order: (c * alpha) * T
-          C1 = ffma(fmul(col[k].y, a), Tr, C1);
-          C2 = ffma(fmul(col[k].z, a), Tr, C2);
+          const float Tm = term ? 0.f : Tw;                     // the stopping Gaussian is not blended
+          C0 = ffma(fmul(col[k].x, al[k]), Tm, C0);             // upstream's order: (c * alpha) * T
+          C1 = ffma(fmul(col[k].y, al[k]), Tm, C1);
+          C2 = ffma(fmul(col[k].z, al[k]), Tm, C2);
+          Tw = term ? 0.f : test_T;
           Tr = term ? Tr : test_T;
-          last = a != 0.f ? r * kStageN + jj[k] + 1 : last;
+          lastq = (!term && al[k] != 0.f) ? b + k + 1 : lastq;
         }
-        if (__all_sync(0xFFFFFFFFu, done)) {
+        if (__all_sync(0xFFFFFFFFu, Tw == 0.f)) {
           wdone = true;
           if (lane == 0) atomicAdd(&sb.done_warps, 1u);
           break;
         }
       }
+      if (lastq) last = r * kStageN + ((uint32_t)q[kQPad + lastq - 1] - rec_base) / kRecBytes + 1;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sb.empty[s]);
@@ -301,7 +336,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         base = (uint32_t)atomicAdd((unsigned long long *)&status->reserved[1], (unsigned long long)nseg);
       }
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
-      for (uint32_t i = lane; i < nseg; i += 32) units[base + i] = make_uint2(vt, i);
+      for (uint32_t i = lane; i < nseg; i += 32) units[base + i] = make_uint4(vt, i, range.x, tmax);
     }
   }
 }
@@ -332,6 +367,38 @@ __device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
   return sum + s1 + s2;
 }
 
+// Ring reduction (kRing): instead of reducing every instance on its own, a warp parks the 9 partials
+// of up to kRingSlots instances as rows of 32 floats (row stride 36 floats: lane l writes column l,
+// conflict-free) and reduces the slots together: the 27 rows are cut into 54 half-rows, lane l sums
+// half-row l (then 32 + l) with four LDS.128 + 15 FADD, one xor-shuffle joins the halves, and the even
+// lanes send the totals as REDs -- two rounds for three instances (~16 issue slots per instance
+// instead of ~40 for the per-instance column sum).  Eight consecutive half-rows start in eight
+// different 4-bank groups, so the 128-bit loads are conflict-free as well.
+constexpr int kRingSlots = 3;
+constexpr int kRowStride = 36;
+constexpr int kSlotFloats = 9 * kRowStride;
+__device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *ids, uint32_t nslots, float *accb,
+                                           int lane) {
+  const uint32_t ntask = nslots * 18u;
+#pragma unroll
+  for (int round = 0; round < 2; round++) {
+    if ((uint32_t)round * 32u >= ntask) break;          // warp-uniform
+    const uint32_t t = round * 32 + lane, r = t >> 1;
+    float sum = 0.f;
+    if (t < ntask) {
+      const float4 *p = reinterpret_cast<const float4 *>(ring + r * kRowStride + (t & 1u) * 16u);
+      const float4 a = p[0], b = p[1], c = p[2], d = p[3];
+      sum = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
+            (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    }
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
+    if (t < ntask && !(t & 1u)) {
+      const uint32_t slot = (r * 57u) >> 9, val = r - 9u * slot;      // r / 9 for r < 27
+      atomicAdd(accb + (size_t)ids[slot] * kAccStride + val, sum);
+    }
+  }
+}
+
 // Backward blend: one CTA per work unit = (view, tile, segment of kSeg instances), emitted by the
 // forward.  Each unit restarts the per-pixel recursion from the forward's checkpoint at the segment
 // start and walks the segment FRONT TO BACK, so units of one tile are independent: the launch has
@@ -342,30 +409,40 @@ __device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
 // normalised by T_{j+1}) becomes  T_j (c_j.dL/dpix) - (D_j + T_final bg.dL/dpix) / (1-alpha_j):  two scalar
 // recurrences (T, D) instead of the back-to-front vector one, and T replays the forward's products exactly.
 constexpr int kUnitThreads = kConsumerWarps * 32;
-template <int kIlpB>
-__global__ void __launch_bounds__(kUnitThreads, 4)
+template <int kIlpB, bool kRing, int kMinCtas>
+__global__ void __launch_bounds__(kUnitThreads, kMinCtas)
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const GhrStatus *__restrict__ status,
-                      const uint2 *__restrict__ units, const uint2 *__restrict__ ranges,
-                      const float4 *__restrict__ records, const uint8_t *__restrict__ masks,
-                      const float4 *__restrict__ tilefinal, const float4 *__restrict__ ckpt,
-                      const uint32_t *__restrict__ n_contrib, const uint32_t *__restrict__ tilemax,
+                      const uint4 *__restrict__ units, const float4 *__restrict__ records,
+                      const uint8_t *__restrict__ masks, const float4 *__restrict__ tilefinal,
+                      const float4 *__restrict__ ckpt, const uint32_t *__restrict__ n_contrib,
                       const float *__restrict__ dL_dout, const float *__restrict__ dL_dmask,
-                      float *__restrict__ acc, int direct_max) {
+                      float *__restrict__ acc, int direct_max, int reverse) {
   constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
   __shared__ __align__(128) float4 s_rec[kSeg * 3];
   __shared__ __align__(16) uint8_t s_msk[kSeg + 16];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ float s_red[kConsumerWarps][kRedBufs][32 * 9];
+  __shared__ __align__(16) float s_red[kConsumerWarps][kRing ? kRingSlots * kSlotFloats : kRedBufs * 32 * 9];
+  __shared__ uint32_t s_ids[kConsumerWarps][4];
   __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
-  if (blockIdx.x >= (uint32_t)status->reserved[1]) return;
-  const uint2 unit = units[blockIdx.x];
+  // The unit record {view*T + tile, segment, start of the tile's slab, instances up to the tile's last
+  // contributor} carries everything the copy needs, and it is read together with the unit count (the
+  // list is allocated to its upper bound): one memory round trip between CTA start and the bulk copy.
+  // `reverse`: the forward appends a tile's units when the tile completes, so the heaviest tiles sit at
+  // the end of the list; walking it backwards starts their (long, dense) units first and leaves the
+  // short ones to fill the tail of the launch.
+  const uint32_t n_units = (uint32_t)status->reserved[1];
+  uint32_t uidx = blockIdx.x;
+  if (reverse) {
+    if (blockIdx.x >= n_units) return;
+    uidx = n_units - 1u - blockIdx.x;
+  }
+  const uint4 unit = units[uidx];
+  if (blockIdx.x >= n_units) return;
   const uint32_t vt = unit.x, first = unit.y * kSeg;      // first = position of the segment in the tile list
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint2 range = ranges[vt];
-  const uint32_t n = min(range.y - range.x, tilemax[vt]);  // instances past the last contributor never matter
-  const uint32_t cnt = min((uint32_t)kSeg, n - first);
-  const size_t g0 = (size_t)range.x + first;
+  const uint32_t cnt = min((uint32_t)kSeg, unit.w - first);   // instances past the last contributor never matter
+  const size_t g0 = (size_t)unit.z + first;
 
   if (tid == 0) {
     mbar_init(&s_bar, 1);
@@ -379,7 +456,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   uint8_t *q = &s_q[warp][0];
   if (lane < kQPad) q[lane] = 0;
 
-  // per-pixel state while the segment is in flight
+  // per-pixel state while the segment is in flight (all loads independent of each other)
   int lx, ly;
   pixel_of_thread(tid, lx, ly);
   const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
@@ -388,6 +465,10 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   const float pxf = (float)px, pyf = (float)py;
   float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLm = 0.f;
   uint32_t last = 0;
+  const float4 fin = tilefinal[(size_t)vt * 256 + tid];
+  float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+  // (a checkpoint no later unit needs was never written: whatever is read there is not used)
+  if (first) c = ckpt[((size_t)(unit.z / kSeg) + vt + unit.y) * 256 + tid];
   if (inside) {
     const size_t pix = (size_t)py * W + px;
     last = n_contrib[(size_t)v * N + pix];
@@ -399,9 +480,6 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   }
   float Tr = 0.f, Drem = 0.f, Tb = 0.f;
   if (last > first) {
-    const float4 fin = tilefinal[(size_t)vt * 256 + tid];
-    float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
-    if (first) c = ckpt[((size_t)(range.x / kSeg) + vt + unit.y) * 256 + tid];
     Tr = c.x;
     Drem = (fin.x - c.y) * dLp0 + (fin.y - c.z) * dLp1 + (fin.z - c.w) * dLp2;
     const float *bg = cam.bg + (size_t)cam.bg_stride * v;
@@ -415,14 +493,20 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   __syncthreads();                  // barrier initialised before anyone polls it
   if (wlast <= first) return;
   mbar_wait(&s_bar, 0);
+  float *ring = &s_red[warp][0];
+  uint32_t *ids = &s_ids[warp][0];
+  uint32_t pend = 0;                // instances parked in the ring (warp-uniform)
+  const float4 *s_rec_cur = s_rec;
+  const uint8_t *s_msk_cur = s_msk;
+  const uint32_t g0lo = (uint32_t)g0 & 15u;
 
   for (uint32_t sub = 0; sub * kStageN < cnt; sub++) {
     const uint32_t pos0 = first + sub * kStageN;
     if (pos0 >= wlast) break;
     const uint32_t scnt = min((uint32_t)kStageN, cnt - sub * kStageN);
-    const float4 *rec = s_rec + 3 * sub * kStageN;
+    const float4 *rec = s_rec_cur + 3 * sub * kStageN;
     // survivors of this warp's sub-block among the instances that precede the warp's last contributor
-    const uint32_t total = build_queue(&s_msk[(g0 & 15u) + sub * kStageN], scnt, wlast - pos0, warp, lane, q, 0u);
+    const uint32_t total = build_queue(&s_msk_cur[g0lo + sub * kStageN], scnt, wlast - pos0, warp, lane, q, 0u);
     for (uint32_t b = 0; b < total; b += kIlpB) {
       // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
       float al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB], cdk[kIlpB];
@@ -462,34 +546,65 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
         vals[k][3] = wG; vals[k][4] = m10; vals[k][5] = m01;
         vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
       }
-      // phase 3 (independent): slots with few contributing lanes send their partials straight
-      // to L2 (9 REDs for the warp); the others are reduced through shared memory first and
-      // leave as one RED per value
+      // phase 3: slots with few contributing lanes send their partials straight to L2 (9 REDs for the
+      // warp); the others are reduced through shared memory first and leave as one RED per value
+      if constexpr (kRing) {
 #pragma unroll
-      for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
-        int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
+        for (int k = 0; k < kIlpB; k++) {
+          const uint32_t cm = __ballot_sync(0xFFFFFFFFu, contrib[k]);
+          if (cm == 0u) continue;
+          if (__popc(cm) <= direct_max) {
+            if (contrib[k]) {
+              float *dst = accb + (size_t)idk[k] * kAccStride;
 #pragma unroll
-        for (int qi = 0; qi < kRedBufs; qi++) {
-          const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-          const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
-          mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
-          if (mode[qi] == 2) warp_store9(&s_red[warp][qi][0], vals[k], lane);
-          if (mode[qi] == 1 && contrib[k]) {
-            float *dst = accb + (size_t)idk[k] * kAccStride;
+              for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
+            }
+          } else {
+            float *row = ring + pend * kSlotFloats + lane;
 #pragma unroll
-            for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
+            for (int t = 0; t < 9; t++) row[t * kRowStride] = vals[k][t];
+            if (lane == 0) ids[pend] = idk[k];
+            if (++pend == kRingSlots) {
+              __syncwarp();
+              ring_flush(ring, ids, kRingSlots, accb, lane);
+              __syncwarp();
+              pend = 0;
+            }
           }
         }
-        __syncwarp();
+      } else {
 #pragma unroll
-        for (int qi = 0; qi < kRedBufs; qi++) {
-          const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-          if (mode[qi] != 2) continue;
-          float tot = warp_colsum9(&s_red[warp][qi][0], lane);
-          if (owner) atomicAdd(accb + (size_t)idk[k] * kAccStride + lane, tot);
+        for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
+          int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
+#pragma unroll
+          for (int qi = 0; qi < kRedBufs; qi++) {
+            const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+            const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
+            mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
+            if (mode[qi] == 2) warp_store9(&s_red[warp][qi * 32 * 9], vals[k], lane);
+            if (mode[qi] == 1 && contrib[k]) {
+              float *dst = accb + (size_t)idk[k] * kAccStride;
+#pragma unroll
+              for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int qi = 0; qi < kRedBufs; qi++) {
+            const int k = k0 + qi < kIlpB ? k0 + qi : 0;
+            if (mode[qi] != 2) continue;
+            float tot = warp_colsum9(&s_red[warp][qi * 32 * 9], lane);
+            if (owner) atomicAdd(accb + (size_t)idk[k] * kAccStride + lane, tot);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
+    }
+  }
+  if constexpr (kRing) {
+    if (pend) {
+      __syncwarp();
+      ring_flush(ring, ids, pend, accb, lane);
     }
   }
 }
@@ -506,6 +621,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   dim3 grid(L.T * d.V), block(kBlendThreads);
   static const int ilp = env_int("GHR_ILPF", 8);
+  static const int bo_active = env_int("GHR_BO_ACTIVE", 256), bo_done = env_int("GHR_BO_DONE", 1024);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
@@ -514,8 +630,8 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                 (const uint8_t *)(state + L.pub.off_masks), (float *)(state + L.pub.off_final_T),
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
                                 (float4 *)(state + L.pub.off_tilefinal), (float4 *)(state + L.pub.off_ckpt),
-                                (uint2 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
-                                out_color, out_mask);
+                                (uint4 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
+                                out_color, out_mask, (uint32_t)bo_active, (uint32_t)bo_done);
   };
   if (ilp <= 4) launch(blend_forward_kernel<4>);
   else launch(blend_forward_kernel<8>);
@@ -526,25 +642,35 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                   const float *dL_dout, const float *dL_dmask, float *acc, cudaStream_t s) {
   if (L.T == 0 || d.V == 0 || d.R_cap <= 0) return cudaSuccess;
   // upper bound of the unit count (the forward wrote the exact one to GhrStatus.reserved[1]); surplus
-  // CTAs exit on their first instruction
+  // CTAs exit on their first instructions
   dim3 grid((unsigned)(L.n_slots - 1)), block(kUnitThreads);
   static const int ilp = env_int("GHR_ILPB", 2);
   static const int direct = env_int("GHR_DIRECT", kDirectMax);
+  static const int ring = env_int("GHR_RING", 1);
+  static const int reverse = env_int("GHR_BWD_REV", 1);
+  static const int occ = env_int("GHR_BWD_OCC", 4);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const GhrStatus *)(state + L.pub.off_status),
-                                (const uint2 *)(state + L.pub.off_units),
-                                (const uint2 *)(state + L.pub.off_ranges),
+                                (const uint4 *)(state + L.pub.off_units),
                                 (const float4 *)(state + L.pub.off_records),
                                 (const uint8_t *)(state + L.pub.off_masks),
                                 (const float4 *)(state + L.pub.off_tilefinal),
                                 (const float4 *)(state + L.pub.off_ckpt),
-                                (const uint32_t *)(state + L.pub.off_ncontrib),
-                                (const uint32_t *)(state + L.pub.off_tilemax), dL_dout, dL_dmask, acc, direct);
+                                (const uint32_t *)(state + L.pub.off_ncontrib), dL_dout, dL_dmask, acc, direct,
+                                reverse);
   };
-  if (ilp <= 1) launch(blend_backward_kernel<1>);
-  else if (ilp <= 2) launch(blend_backward_kernel<2>);
-  else launch(blend_backward_kernel<3>);
+  if (occ >= 5) {
+    if (ring) launch(blend_backward_kernel<2, true, 5>);
+    else launch(blend_backward_kernel<2, false, 5>);
+  } else if (ring) {
+    if (ilp <= 2) launch(blend_backward_kernel<2, true, 4>);
+    else launch(blend_backward_kernel<3, true, 4>);
+  } else {
+    if (ilp <= 1) launch(blend_backward_kernel<1, false, 4>);
+    else if (ilp <= 2) launch(blend_backward_kernel<2, false, 4>);
+    else launch(blend_backward_kernel<3, false, 4>);
+  }
   return cudaGetLastError();
 }
 

@@ -81,7 +81,8 @@ typedef struct GhrLayout {
   size_t off_ckpt;     /* float4 {T, C.r, C.g, C.b} per (slot, pixel-in-tile): the forward's running state at
                           every GHR_SEGMENT-instance boundary of a tile list; slot(tile, s) =
                           ranges[tile].start / GHR_SEGMENT + tile + s, s >= 1 */
-  size_t off_units;    /* uint32[2] (view*T + tile, segment) per backward work unit, GhrStatus.reserved[1] of them */
+  size_t off_units;    /* uint32[4] (view*T + tile, segment, slab start, instances up to the tile's last contributor)
+                          per backward work unit, GhrStatus.reserved[1] of them */
 } GhrLayout;
 
 typedef struct GhrStatus {

@@ -8,7 +8,7 @@ gradient buffer -- 56 B x P for the colors_precomp path.  The rasterizer backwar
 into that packed buffer (one flat allocation, one segment per attribute), so there is no
 pack/concat kernel before the collective.
 """
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -70,28 +70,105 @@ class PackedGrads:
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class StepResult(NamedTuple):
+    """Result of an overlapped step: one api.ForwardResult per view group (contiguous view blocks)."""
+    results: list
+    bounds: list              # range of views per group
+
+    @property
+    def R(self):
+        return None if any(r.R is None for r in self.results) else sum(r.R for r in self.results)
+
+    @property
+    def R_cap(self):
+        return [r.R_cap for r in self.results]
+
+    @property
+    def color(self):
+        return torch.cat([r.color for r in self.results], 0)
+
+
+_side_streams: Dict[int, list] = {}
+
+
+def _streams(dev: torch.device, n: int):
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _side_streams.setdefault(idx, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=idx))
+    return pool[:n]
+
+
+def _slice_views(views, lo: int, hi: int):
+    bg = views.bg if views.bg.dim() == 1 else views.bg[lo:hi]
+    return views._replace(viewmatrix=views.viewmatrix[lo:hi], projmatrix=views.projmatrix[lo:hi],
+                          campos=views.campos[lo:hi], tanfov=views.tanfov[lo:hi], bg=bg)
+
+
 def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
                    group=None, sh_degree: int = 0, scale_modifier: float = 1.0,
-                   R_cap: Optional[int] = None, check: str = "poll", fwd_events=None, bwd_events=None):
+                   R_cap=None, check: str = "poll", fwd_events=None, bwd_events=None,
+                   overlap: int = 1, partials: Optional[Sequence[PackedGrads]] = None):
     """One camera-sharded step on this rank: forward + backward of the LOCAL views, gradients written
     into `grads` (overwritten), then the all-reduce.  Returns the api.ForwardResult (color, radii, state).
 
     gauss: dict with means3D, opacities, scales, rotations and colors_precomp or shs (CUDA fp32).
-    views: guassianhand_b200.api.ViewBatch of the local shard.  dL_dout: [V,3,H,W]."""
+    views: guassianhand_b200.api.ViewBatch of the local shard.  dL_dout: [V,3,H,W].
+
+    overlap = G > 1 cuts the local views into G contiguous groups and runs each group's forward ->
+    backward chain on its own stream (group 0 on the current one).  The chains are independent until the
+    gradient sum, so the single-CTA tile scan, the half-empty sort launches and the tails of the blend
+    kernels of one group are filled with the other groups' work.  Group g > 0 writes into
+    `partials[g-1]` (allocated when absent; pass static buffers under CUDA-graph capture), which are
+    added into `grads` after the join.  `R_cap` may then be a list (one capacity per group).  Returns a
+    StepResult."""
     from . import api
-    cams = views.cams()
     f32 = api._f32c
     means3D, opac = f32(gauss["means3D"]), f32(gauss["opacities"])
     sc, rot = f32(gauss["scales"]), f32(gauss["rotations"])
     shs = f32(gauss["shs"]) if gauss.get("shs") is not None else None
     col = f32(gauss["colors_precomp"]) if gauss.get("colors_precomp") is not None else None
-    res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier, check=check,
-                          R_cap=R_cap, stage_events=fwd_events)
-    api.backward_raw(cams, res.state, res.R_cap, dL_dout, means3D, opac, sc, rot, None, shs, col, sh_degree,
-                     scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False,
-                     stage_events=bwd_events)
+    V = int(views.viewmatrix.shape[0])
+    G = max(1, min(int(overlap), V))
+    if G == 1:
+        cams = views.cams()
+        cap = R_cap[0] if isinstance(R_cap, (list, tuple)) else R_cap
+        res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier, check=check,
+                              R_cap=cap, stage_events=fwd_events)
+        api.backward_raw(cams, res.state, res.R_cap, dL_dout, means3D, opac, sc, rot, None, shs, col, sh_degree,
+                         scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False,
+                         stage_events=bwd_events)
+        grads.all_reduce_(group)
+        return res
+    if fwd_events is not None or bwd_events is not None:
+        raise ValueError("per-stage events need overlap=1 (stages of different groups run concurrently)")
+    dev = means3D.device
+    bounds = [shard_views(V, g, G) for g in range(G)]
+    if partials is None:
+        partials = [PackedGrads(grads.P, grads.M, device=dev) for _ in range(G - 1)]
+    main = torch.cuda.current_stream(dev)
+    streams = [main] + _streams(dev, G - 1)
+    for st in streams[1:]:
+        st.wait_stream(main)          # fork before group 0 is enqueued: the chains must not wait for it
+    results = []
+    for g, rng in enumerate(bounds):
+        st = streams[g]
+        with torch.cuda.stream(st):
+            cams = _slice_views(views, rng.start, rng.stop).cams()
+            cap = R_cap[g] if isinstance(R_cap, (list, tuple)) else R_cap
+            res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier,
+                                  check=check, R_cap=cap)
+            target = grads if g == 0 else partials[g - 1]
+            api.backward_raw(cams, res.state, res.R_cap, dL_dout[rng.start:rng.stop], means3D, opac, sc, rot, None,
+                             shs, col, sh_degree, scale_modifier, want_means2D=False,
+                             accumulate_into=target.views(), accumulate=False)
+        results.append(res)
+    for g in range(1, G):
+        main.wait_stream(streams[g])
+    for p in partials[:G - 1]:
+        grads.flat.add_(p.flat)
     grads.all_reduce_(group)
-    return res
+    return StepResult(results, bounds)
 
 
 class GraphedFitStep:
@@ -104,9 +181,14 @@ class GraphedFitStep:
     (`R_cap`); check `status()` for overflow when the scene changes a lot."""
 
     def __init__(self, gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
-                 R_cap: int, group=None, sh_degree: int = 0, scale_modifier: float = 1.0, warmup: int = 2):
-        self.gauss, self.views, self.dL_dout, self.grads, self.R_cap = gauss, views, dL_dout, grads, int(R_cap)
-        kw = dict(group=group, sh_degree=sh_degree, scale_modifier=scale_modifier, R_cap=self.R_cap, check="none")
+                 R_cap, group=None, sh_degree: int = 0, scale_modifier: float = 1.0, warmup: int = 2,
+                 overlap: int = 1):
+        self.gauss, self.views, self.dL_dout, self.grads, self.R_cap = gauss, views, dL_dout, grads, R_cap
+        V = int(views.viewmatrix.shape[0])
+        self.overlap = max(1, min(int(overlap), V))
+        self.partials = [PackedGrads(grads.P, grads.M, device=grads.flat.device) for _ in range(self.overlap - 1)]
+        kw = dict(group=group, sh_degree=sh_degree, scale_modifier=scale_modifier, R_cap=self.R_cap, check="none",
+                  overlap=self.overlap, partials=self.partials)
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -124,11 +206,20 @@ class GraphedFitStep:
         self.graph.replay()
         return self.result
 
+    def states(self):
+        """State blobs of the captured step (one per view group)."""
+        r = self.result
+        return [x.state for x in r.results] if isinstance(r, StepResult) else [r.state]
+
     def status(self):
-        """(R, overflow) of the last replay; synchronises the current stream."""
+        """(R, overflow) of the last replay, summed / or-ed over view groups; synchronises the current stream."""
         from . import _native as N
         s = torch.cuda.current_stream()
-        N.check(N.lib().ghr_read_status_async(self.result.state.data_ptr(), self._pin.data_ptr(), s.cuda_stream),
-                "ghr_read_status_async")
-        s.synchronize()
-        return int(self._pin[0]), int(self._pin[1]) & 0xFFFFFFFF
+        R, ov = 0, 0
+        for st in self.states():
+            N.check(N.lib().ghr_read_status_async(st.data_ptr(), self._pin.data_ptr(), s.cuda_stream),
+                    "ghr_read_status_async")
+            s.synchronize()
+            R += int(self._pin[0])
+            ov |= int(self._pin[1]) & 0xFFFFFFFF
+        return R, ov

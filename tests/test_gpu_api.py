@@ -176,3 +176,47 @@ def test_fused_mask_equals_second_render(cuda_device):
         assert np.abs(masks[v].detach().cpu().numpy() - fb["out_color"][0]).max() <= 1e-5
         tot = tot + ga["dL_dmeans3D"].astype(np.float64) + gb["dL_dmeans3D"]
     assert util.rel_err(xyz2.grad.cpu().numpy(), tot) <= 1e-4
+
+
+def test_overlapped_view_groups_equal_single_chain(cuda_device):
+    """rasterize_views(overlap=G) and dist.fit_step_grads(overlap=G) only change the schedule (view groups
+    on concurrent streams): images, masks and radii are bit-identical, gradients equal up to the order
+    of the sum over views."""
+    from guassianhand_b200 import rasterize_views
+    from guassianhand_b200.dist import GraphedFitStep, PackedGrads, fit_step_grads
+    dev = cuda_device
+    sc = scenes.two_hand_scene(5000, seed=11)
+    cams = scenes.fibonacci_cameras(5, 96, 112, seed=11)
+    bg = np.stack([np.array([0.1 * v, 0.2, 0.3], np.float32) for v in range(5)])     # per-view background
+    views = util.gpu_views(cams, bg, dev)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    w = t((np.random.default_rng(3).normal(size=(5, 3, 96, 112)) / 10752).astype(np.float32))
+    wm = t((np.random.default_rng(4).normal(size=(5, 96, 112)) / 10752).astype(np.float32))
+    out = {}
+    for G in (1, 3, 5):
+        leaf = lambda a: t(a).requires_grad_(True)
+        xyz, opacity, scaling, rotation, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+        imgs, mask, radii = rasterize_views(xyz, opacity, views, colors_precomp=colors, scales=scaling,
+                                            rotations=rotation, return_mask=True, overlap=G)
+        ((imgs * w).sum() + (mask * wm).sum()).backward()
+        torch.cuda.synchronize()
+        out[G] = (imgs.detach().clone(), mask.detach().clone(), radii.clone(),
+                  [x.grad.clone() for x in (xyz, opacity, scaling, rotation, colors)])
+    for G in (3, 5):
+        assert torch.equal(out[G][0], out[1][0]) and torch.equal(out[G][1], out[1][1]) and torch.equal(out[G][2], out[1][2])
+        for a, b in zip(out[G][3], out[1][3]):
+            assert util.rel_err(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) <= 1e-5
+
+    gauss = dict(means3D=t(sc.means3D), opacities=t(sc.opacities), scales=t(sc.scales), rotations=t(sc.rotations),
+                 colors_precomp=t(sc.colors))
+    g1, g2, g3 = (PackedGrads(sc.P, 0, device=dev) for _ in range(3))
+    r1 = fit_step_grads(gauss, views, w, g1)
+    r2 = fit_step_grads(gauss, views, w, g2, overlap=2)
+    assert r2.R == r1.R and torch.equal(r2.color, r1.color)
+    assert util.rel_err(g2.flat.cpu().numpy(), g1.flat.cpu().numpy().astype(np.float64)) <= 1e-5
+    caps = [int(x.R * 1.25) + 1024 for x in r2.results]
+    step = GraphedFitStep(gauss, views, w, g3, R_cap=caps, overlap=2)
+    step.replay()
+    R, overflow = step.status()
+    assert R == r1.R and not overflow
+    assert util.rel_err(g3.flat.cpu().numpy(), g1.flat.cpu().numpy().astype(np.float64)) <= 1e-5

@@ -23,6 +23,7 @@ ap.add_argument("--H", type=int, default=512)
 ap.add_argument("--W", type=int, default=334)
 ap.add_argument("--sh", type=int, default=-1, help="SH degree (-1 = colors_precomp)")
 ap.add_argument("--no-flush", action="store_true")
+ap.add_argument("--overlap", type=int, nargs="+", default=[1], help="view groups on concurrent streams (graph timing)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 sc = scenes.two_hand_scene(a.P, seed=0, sh_degree=a.sh if a.sh >= 0 else None)
@@ -61,17 +62,27 @@ for V in a.views:
         out[name] = round(float(np.mean([e.elapsed_ms(si) for e in fe])) * 1000, 1)
     for si, name in enumerate(NV.BWD_STAGES):
         out[name] = round(float(np.mean([e.elapsed_ms(si) for e in be])) * 1000, 1)
-    g = GraphedFitStep(gauss, views, dL, grads, R_cap=cap, **kw)
-    for _ in range(3):
-        g.replay()
-    torch.cuda.synchronize()
-    for i in range(a.steps):
-        if not a.no_flush:
-            flush.zero_()
-        s0[i].record()
-        g.replay()
-        s1[i].record()
-    torch.cuda.synchronize()
-    out["graph_ms"] = float(np.mean([x.elapsed_time(y) for x, y in zip(s0, s1)]))
-    out["views_per_s_graph"] = V / out["graph_ms"] * 1000
+    for G in a.overlap:
+        G = max(1, min(G, V))
+        caps = cap
+        if G > 1:
+            r = fit_step_grads(gauss, views, dL, grads, overlap=G, **kw)
+            caps = [int(x.R * 1.25) + (1 << 14) for x in r.results]
+        g = GraphedFitStep(gauss, views, dL, grads, R_cap=caps, overlap=G, **kw)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        for i in range(a.steps):
+            if not a.no_flush:
+                flush.zero_()
+            s0[i].record()
+            g.replay()
+            s1[i].record()
+        torch.cuda.synchronize()
+        if g.status()[1]:
+            raise RuntimeError("overflow in the graphed step")
+        ms = float(np.mean([x.elapsed_time(y) for x, y in zip(s0, s1)]))
+        tag = "" if G == 1 else f"_overlap{G}"
+        out["graph_ms" + tag] = ms
+        out["views_per_s_graph" + tag] = V / ms * 1000
     print(json.dumps(out))

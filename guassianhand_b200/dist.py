@@ -74,6 +74,8 @@ class StepResult(NamedTuple):
     """Result of an overlapped step: one api.ForwardResult per view group (contiguous view blocks)."""
     results: list
     bounds: list              # range of views per group
+    color: torch.Tensor       # [V,3,H,W]: the groups' images are blocks of one tensor
+    radii: torch.Tensor       # [V,P]
 
     @property
     def R(self):
@@ -83,9 +85,6 @@ class StepResult(NamedTuple):
     def R_cap(self):
         return [r.R_cap for r in self.results]
 
-    @property
-    def color(self):
-        return torch.cat([r.color for r in self.results], 0)
 
 
 _side_streams: Dict[int, list] = {}
@@ -148,6 +147,9 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
         partials = [PackedGrads(grads.P, grads.M, device=dev) for _ in range(G - 1)]
     main = torch.cuda.current_stream(dev)
     streams = [main] + _streams(dev, G - 1)
+    P, H, W = means3D.shape[0], int(views.image_height), int(views.image_width)
+    color = torch.empty(V, 3, H, W, dtype=torch.float32, device=dev)
+    radii = torch.empty(V, max(P, 1), dtype=torch.int32, device=dev)
     for st in streams[1:]:
         st.wait_stream(main)          # fork before group 0 is enqueued: the chains must not wait for it
     results = []
@@ -157,7 +159,7 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
             cams = _slice_views(views, rng.start, rng.stop).cams()
             cap = R_cap[g] if isinstance(R_cap, (list, tuple)) else R_cap
             res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier,
-                                  check=check, R_cap=cap)
+                                  check=check, R_cap=cap, out=(color[rng.start:rng.stop], radii[rng.start:rng.stop], None))
             target = grads if g == 0 else partials[g - 1]
             api.backward_raw(cams, res.state, res.R_cap, dL_dout[rng.start:rng.stop], means3D, opac, sc, rot, None,
                              shs, col, sh_degree, scale_modifier, want_means2D=False,
@@ -168,7 +170,7 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
     for p in partials[:G - 1]:
         grads.flat.add_(p.flat)
     grads.all_reduce_(group)
-    return StepResult(results, bounds)
+    return StepResult(results, bounds, color, radii[:, :P])
 
 
 class GraphedFitStep:

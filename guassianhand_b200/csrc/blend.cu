@@ -408,9 +408,12 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
 // upstream's  dL/dalpha_j = T_j (c_j - A_j).dL/dpix - T_final/(1-alpha_j) bg.dL/dpix  (A_j = suffix colour
 // normalised by T_{j+1}) becomes  T_j (c_j.dL/dpix) - (D_j + T_final bg.dL/dpix) / (1-alpha_j):  two scalar
 // recurrences (T, D) instead of the back-to-front vector one, and T replays the forward's products exactly.
-constexpr int kUnitThreads = kConsumerWarps * 32;
-template <int kIlpB, bool kRing, int kMinCtas>
-__global__ void __launch_bounds__(kUnitThreads, kMinCtas)
+// kW warps per CTA: 8 (the whole tile) or 4 (half a tile: two CTAs per unit, each staging the slab).
+// Warps of a CTA finish at very different times (a sub-block outside the hands has few survivors) and the
+// CTA keeps its registers and shared memory until the slowest one is done; smaller CTAs give those
+// resources back sooner.
+template <int kIlpB, bool kRing, int kMinCtas, int kW>
+__global__ void __launch_bounds__(kW * 32, kMinCtas)
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const GhrStatus *__restrict__ status,
                       const uint4 *__restrict__ units, const float4 *__restrict__ records,
                       const uint8_t *__restrict__ masks, const float4 *__restrict__ tilefinal,
@@ -421,9 +424,11 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   __shared__ __align__(128) float4 s_rec[kSeg * 3];
   __shared__ __align__(16) uint8_t s_msk[kSeg + 16];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(16) float s_red[kConsumerWarps][kRing ? kRingSlots * kSlotFloats : kRedBufs * 32 * 9];
-  __shared__ uint32_t s_ids[kConsumerWarps][4];
-  __shared__ __align__(16) uint8_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
+  __shared__ __align__(16) float s_red[kW][kRing ? kRingSlots * kSlotFloats : kRedBufs * 32 * 9];
+  __shared__ uint32_t s_ids[kW][4];
+  __shared__ __align__(16) uint8_t s_q[kW][kStageN + 2 * kQPad];
+  constexpr uint32_t kParts = kConsumerWarps / kW;       // CTAs per unit
+  const uint32_t bid = blockIdx.x / kParts, part = blockIdx.x % kParts;
   // The unit record {view*T + tile, segment, start of the tile's slab, instances up to the tile's last
   // contributor} carries everything the copy needs, and it is read together with the unit count (the
   // list is allocated to its upper bound): one memory round trip between CTA start and the bulk copy.
@@ -431,20 +436,22 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   // the end of the list; walking it backwards starts their (long, dense) units first and leaves the
   // short ones to fill the tail of the launch.
   const uint32_t n_units = (uint32_t)status->reserved[1];
-  uint32_t uidx = blockIdx.x;
+  uint32_t uidx = bid;
   if (reverse) {
-    if (blockIdx.x >= n_units) return;
-    uidx = n_units - 1u - blockIdx.x;
+    if (bid >= n_units) return;
+    uidx = n_units - 1u - bid;
   }
   const uint4 unit = units[uidx];
-  if (blockIdx.x >= n_units) return;
+  if (bid >= n_units) return;
   const uint32_t vt = unit.x, first = unit.y * kSeg;      // first = position of the segment in the tile list
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lane = threadIdx.x & 31, wloc = threadIdx.x >> 5;      // warp inside the CTA
+  const int warp = (int)part * kW + wloc, tid = warp * 32 + lane;   // warp / thread inside the tile
+  uint8_t *q = &s_q[wloc][0];
   const uint32_t cnt = min((uint32_t)kSeg, unit.w - first);   // instances past the last contributor never matter
   const size_t g0 = (size_t)unit.z + first;
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     mbar_init(&s_bar, 1);
     mbar_fence_init();
     const size_t m0 = g0 & ~(size_t)15;
@@ -453,7 +460,6 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
     bulk_g2s(s_rec, records + 3 * g0, cnt * kRecBytes, &s_bar);
     bulk_g2s(s_msk, masks + m0, mbytes, &s_bar);
   }
-  uint8_t *q = &s_q[warp][0];
   if (lane < kQPad) q[lane] = 0;
 
   // per-pixel state while the segment is in flight (all loads independent of each other)
@@ -493,8 +499,8 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   __syncthreads();                  // barrier initialised before anyone polls it
   if (wlast <= first) return;
   mbar_wait(&s_bar, 0);
-  float *ring = &s_red[warp][0];
-  uint32_t *ids = &s_ids[warp][0];
+  float *ring = &s_red[wloc][0];
+  uint32_t *ids = &s_ids[wloc][0];
   uint32_t pend = 0;                // instances parked in the ring (warp-uniform)
   const float4 *s_rec_cur = s_rec;
   const uint8_t *s_msk_cur = s_msk;
@@ -581,7 +587,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
             const int k = k0 + qi < kIlpB ? k0 + qi : 0;
             const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
             mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
-            if (mode[qi] == 2) warp_store9(&s_red[warp][qi * 32 * 9], vals[k], lane);
+            if (mode[qi] == 2) warp_store9(&s_red[wloc][qi * 32 * 9], vals[k], lane);
             if (mode[qi] == 1 && contrib[k]) {
               float *dst = accb + (size_t)idk[k] * kAccStride;
 #pragma unroll
@@ -593,7 +599,7 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
           for (int qi = 0; qi < kRedBufs; qi++) {
             const int k = k0 + qi < kIlpB ? k0 + qi : 0;
             if (mode[qi] != 2) continue;
-            float tot = warp_colsum9(&s_red[warp][qi * 32 * 9], lane);
+            float tot = warp_colsum9(&s_red[wloc][qi * 32 * 9], lane);
             if (owner) atomicAdd(accb + (size_t)idk[k] * kAccStride + lane, tot);
           }
           __syncwarp();
@@ -643,13 +649,13 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
   if (L.T == 0 || d.V == 0 || d.R_cap <= 0) return cudaSuccess;
   // upper bound of the unit count (the forward wrote the exact one to GhrStatus.reserved[1]); surplus
   // CTAs exit on their first instructions
-  dim3 grid((unsigned)(L.n_slots - 1)), block(kUnitThreads);
   static const int ilp = env_int("GHR_ILPB", 2);
   static const int direct = env_int("GHR_DIRECT", kDirectMax);
   static const int ring = env_int("GHR_RING", 1);
   static const int reverse = env_int("GHR_BWD_REV", 1);
-  static const int occ = env_int("GHR_BWD_OCC", 4);
-  auto launch = [&](auto kern) {
+  static const int warps = env_int("GHR_BWD_WARPS", 4);
+  auto launch = [&](auto kern, int kw) {
+    dim3 grid((unsigned)((L.n_slots - 1) * (kConsumerWarps / kw))), block(kw * 32);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const GhrStatus *)(state + L.pub.off_status),
                                 (const uint4 *)(state + L.pub.off_units),
@@ -660,16 +666,16 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                 (const uint32_t *)(state + L.pub.off_ncontrib), dL_dout, dL_dmask, acc, direct,
                                 reverse);
   };
-  if (occ >= 5) {
-    if (ring) launch(blend_backward_kernel<2, true, 5>);
-    else launch(blend_backward_kernel<2, false, 5>);
+  if (warps <= 4) {
+    if (ring) launch(blend_backward_kernel<2, true, 7, 4>, 4);
+    else launch(blend_backward_kernel<2, false, 8, 4>, 4);
   } else if (ring) {
-    if (ilp <= 2) launch(blend_backward_kernel<2, true, 4>);
-    else launch(blend_backward_kernel<3, true, 4>);
+    if (ilp <= 2) launch(blend_backward_kernel<2, true, 4, 8>, 8);
+    else launch(blend_backward_kernel<3, true, 4, 8>, 8);
   } else {
-    if (ilp <= 1) launch(blend_backward_kernel<1, false, 4>);
-    else if (ilp <= 2) launch(blend_backward_kernel<2, false, 4>);
-    else launch(blend_backward_kernel<3, false, 4>);
+    if (ilp <= 1) launch(blend_backward_kernel<1, false, 4, 8>, 8);
+    else if (ilp <= 2) launch(blend_backward_kernel<2, false, 4, 8>, 8);
+    else launch(blend_backward_kernel<3, false, 4, 8>, 8);
   }
   return cudaGetLastError();
 }

@@ -667,8 +667,8 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
                                 reverse);
   };
   if (warps <= 4) {
-    if (ring) launch(blend_backward_kernel<2, true, 7, 4>, 4);
-    else launch(blend_backward_kernel<2, false, 8, 4>, 4);
+    if (!ring) launch(blend_backward_kernel<2, false, 8, 4>, 4);
+    else launch(blend_backward_kernel<2, true, 7, 4>, 4);
   } else if (ring) {
     if (ilp <= 2) launch(blend_backward_kernel<2, true, 4, 8>, 8);
     else launch(blend_backward_kernel<3, true, 4, 8>, 8);

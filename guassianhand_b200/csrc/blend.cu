@@ -178,7 +178,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float4 *__restrict__ tilefinal, float4 *__restrict__ ckpt,
                      uint4 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
-                     float *__restrict__ out_mask, uint32_t bo_active, uint32_t bo_done) {
+                     float *__restrict__ out_mask, uint32_t bo_active, uint32_t bo_done, uint32_t bo_prod) {
   __shared__ StageBuf sb;
   __shared__ __align__(16) uint16_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
   const uint32_t vt = order[blockIdx.x];
@@ -215,7 +215,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     if (lane == 0) {
       for (uint32_t r = 0; r < rounds; r++) {
         const int s = r % kStages;
-        if (r >= kStages) mbar_wait(&sb.empty[s], ((r / kStages) - 1) & 1);
+        if (r >= kStages) mbar_wait(&sb.empty[s], ((r / kStages) - 1) & 1, bo_prod);
         if (*(volatile uint32_t *)&sb.done_warps == kConsumerWarps) {
           // every pixel of the tile has terminated: complete the phase without data ("poison")
           *(volatile uint32_t *)&sb.stop_round = r;
@@ -628,6 +628,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
   dim3 grid(L.T * d.V), block(kBlendThreads);
   static const int ilp = env_int("GHR_ILPF", 8);
   static const int bo_active = env_int("GHR_BO_ACTIVE", 256), bo_done = env_int("GHR_BO_DONE", 1024);
+  static const int bo_prod = env_int("GHR_BO_PROD", 256);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
@@ -637,7 +638,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                 (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
                                 (float4 *)(state + L.pub.off_tilefinal), (float4 *)(state + L.pub.off_ckpt),
                                 (uint4 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
-                                out_color, out_mask, (uint32_t)bo_active, (uint32_t)bo_done);
+                                out_color, out_mask, (uint32_t)bo_active, (uint32_t)bo_done, (uint32_t)bo_prod);
   };
   if (ilp <= 4) launch(blend_forward_kernel<4>);
   else launch(blend_forward_kernel<8>);

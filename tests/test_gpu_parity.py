@@ -82,6 +82,30 @@ def test_ragged_image_sizes(cuda_device, hw):
     _full_compare(sc, [scenes.simple_camera(hw[0], hw[1], fx=60.0)], BG)
 
 
+def test_property_random_shapes(cuda_device):
+    """SURVEY.md §8(c) property test: random P, ragged H x W (not multiples of 16), SH degree 0-3 or
+    precomputed colours, scale_modifier != 1, non-black backgrounds, 1-3 views, with Gaussians behind the
+    camera, huge ones and exact depth ties (scenes.random_scene) -- every case to the full parity bar."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=12, deadline=None, derandomize=True, database=None,
+              suppress_health_check=list(HealthCheck))
+    @given(P=st.integers(1, 3000), H=st.integers(1, 150), W=st.integers(1, 150),
+           deg=st.sampled_from([None, 0, 1, 2, 3]), mod=st.sampled_from([1.0, 0.6, 1.9]),
+           V=st.integers(1, 3), seed=st.integers(0, 10_000), huge=st.sampled_from([0.0, 0.01, 0.05]))
+    def run(P, H, W, deg, mod, V, seed, huge):
+        sc = scenes.random_scene(P, seed=seed, sh_degree=deg, behind_frac=0.1, huge_frac=huge)
+        rng = np.random.default_rng(seed)
+        bg = rng.uniform(0, 1, size=3).astype(np.float32)
+        if V == 1:
+            cams = [scenes.simple_camera(H, W, fx=float(rng.uniform(40, 300)))]
+        else:
+            cams = scenes.fibonacci_cameras(V, H, W, seed=seed)
+        _full_compare(sc, cams, bg, seed=seed, scale_modifier=mod)
+
+    run()
+
+
 def test_multi_view_batch_matches_per_view_oracle(cuda_device):
     sc = scenes.two_hand_scene(5000, seed=3)
     _full_compare(sc, scenes.fibonacci_cameras(5, 96, 112, seed=3), BG)

@@ -55,14 +55,24 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->pub.state_bytes = o;
 
   // ---- temp (forward): zeroed prefix first ----
+  L->n_heavy = (size_t)d.R_cap / kChunk + 1;          // tiles with more than kChunk instances
+  L->n_hchunks = 2 * ((size_t)d.R_cap / kChunk) + 1;  // their kChunk-sized pieces
+  L->n_chunks = 3 * ((size_t)d.R_cap / kChunk) + VT + 8;   // sort items: light tiles + depth buckets
   size_t t = 0;
   L->t_tile_count = t;   t = align_up(t + VT * 4);
   L->t_cursor = t;       t = align_up(t + VT * 4);
   L->t_misc = t;         t = align_up(t + 64);
+  L->t_dmm = t;          t = align_up(t + L->n_heavy * 8);
+  L->t_slab_count = t;   t = align_up(t + L->n_heavy * 256 * 4);
   L->t_zero_bytes = t;
+  L->t_slab_off = t;     t = align_up(t + L->n_heavy * 256 * 4);
+  L->t_heavy_flag = t;   t = align_up(t + L->n_heavy * 4);
+  L->t_heavy = t;        t = align_up(t + L->n_heavy * 4);
+  L->t_heavy_id = t;     t = align_up(t + VT * 4);
+  L->t_hchunks = t;      t = align_up(t + L->n_hchunks * 8);
   L->t_inst = t;         t = align_up(t + (size_t)d.R_cap * 8);
-  L->n_chunks = (size_t)d.R_cap / kChunk + VT;
-  L->t_chunks = t;       t = align_up(t + L->n_chunks * 8);
+  L->t_inst_b = t;       t = align_up(t + (size_t)d.R_cap * 8);
+  L->t_chunks = t;       t = align_up(t + L->n_chunks * 16);
   L->pub.temp_bytes = t;
   L->pub.temp_bwd_bytes = align_up(VP * kAccStride * 4);
   return GHR_OK;

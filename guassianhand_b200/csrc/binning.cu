@@ -46,56 +46,84 @@ __device__ __forceinline__ int size_class(uint32_t n) { return n == 0 ? 0 : 33 -
 constexpr int kScanThreads1 = 1024;
 constexpr int kClasses = 34;
 
+// Sort work items.  A tile list of at most kChunk instances is one item and is final after its chunk
+// sort.  A list of a few chunks is sorted chunk by chunk and finished by the rank merge (each chunk ranks
+// its keys in the others: quadratic in the chunk count, cheapest up to ~6 chunks).  A longer list
+// ("heavy", more than part_min instances) is first partitioned by depth into buckets of at most kChunk
+// instances (minmax -> slab histogram -> plan -> scatter below), each bucket one final item; a heavy
+// tile whose depths are too degenerate to partition falls back to chunks + merge as well.
+// Item = {view*T + tile, offset inside the tile list, count, flags}.
+constexpr uint32_t kItemSrcB = 1u;     // instances are read from the partitioned copy (inst_b)
+constexpr uint32_t kItemFinal = 2u;    // the sorted item is in its final place: gather its records
+constexpr int kSlabs = 256;            // depth slabs of a heavy tile (fine histogram bins)
+
 // ranges[t] = [start, end) of tile t in the instance arrays (clamped to R_cap; (0,0) for empty tiles,
 // as upstream leaves them), order[] = tile ids by descending size class (the blend launch order),
-// chunks[] = (tile, chunk index) work items of the sort, misc[0] = their number, status = {R, overflow}.
+// items[] = one sort item per light tile (misc[0] = their number; the plan kernel appends the heavy
+// tiles' buckets), hchunks[] = (tile, chunk index) pieces of the heavy tiles for the partition passes
+// (misc[1]), heavy[] = the heavy tiles (misc[2]) with heavy_id[tile] their index, status = {R, overflow}.
 // One CTA: every thread owns a run of consecutive tiles, sums it, one block scan of the 1024 run
 // totals, then walks its run again.
 __global__ void __launch_bounds__(kScanThreads1)
-tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, int chunk_log2,
-                          const uint32_t *__restrict__ tile_count,
-                          uint2 *__restrict__ ranges, uint32_t *__restrict__ order, uint2 *__restrict__ chunks,
+tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hchunk_cap, uint32_t heavy_cap,
+                          uint32_t part_min, const uint32_t *__restrict__ tile_count, uint2 *__restrict__ ranges,
+                          uint32_t *__restrict__ order, uint4 *__restrict__ items, uint2 *__restrict__ hchunks,
+                          uint32_t *__restrict__ heavy, uint32_t *__restrict__ heavy_id,
                           uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
   __shared__ uint64_t s_warp[kScanThreads1 / 32];
-  __shared__ uint32_t s_wchunk[kScanThreads1 / 32];
+  __shared__ uint32_t s_wl[kScanThreads1 / 32], s_wh[kScanThreads1 / 32], s_whc[kScanThreads1 / 32];
   __shared__ uint32_t s_cls[kClasses + 1], s_cur[kClasses + 1];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kClasses) s_cls[tid] = 0;
   const int per = (VT + kScanThreads1 - 1) / kScanThreads1;
   const int t0 = min(VT, tid * per), t1 = min(VT, t0 + per);
-  const uint32_t chunk_mask = (1u << chunk_log2) - 1u;
   uint64_t sum = 0;
-  uint32_t csum = 0;
+  uint32_t lsum = 0, hsum = 0, hcsum = 0;      // light tiles, heavy tiles, heavy chunks of this run
   for (int t = t0; t < t1; t++) {
     const uint32_t c = tile_count[t];
     sum += c;
-    csum += (c + chunk_mask) >> chunk_log2;
+    if (c > part_min) {
+      hsum++;
+      hcsum += (c + kChunk - 1) / kChunk;
+    } else {
+      lsum += (c + kChunk - 1) / kChunk;       // one final item, or plain chunks finished by the rank merge
+    }
   }
   uint64_t incl = sum;
-  uint32_t cincl = csum;
+  uint32_t lincl = lsum, hincl = hsum, hcincl = hcsum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint64_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    const uint32_t cup = __shfl_up_sync(0xFFFFFFFFu, cincl, o);
+    const uint32_t lup = __shfl_up_sync(0xFFFFFFFFu, lincl, o);
+    const uint32_t hup = __shfl_up_sync(0xFFFFFFFFu, hincl, o);
+    const uint32_t hcup = __shfl_up_sync(0xFFFFFFFFu, hcincl, o);
     if (lane >= o) {
       incl += up;
-      cincl += cup;
+      lincl += lup;
+      hincl += hup;
+      hcincl += hcup;
     }
   }
   if (lane == 31) {
     s_warp[warp] = incl;
-    s_wchunk[warp] = cincl;
+    s_wl[warp] = lincl;
+    s_wh[warp] = hincl;
+    s_whc[warp] = hcincl;
   }
   __syncthreads();
   uint64_t start = incl - sum, total = 0;
-  uint32_t coff = cincl - csum, ctotal = 0;
+  uint32_t loff = lincl - lsum, hoff = hincl - hsum, hcoff = hcincl - hcsum, ltotal = 0, htotal = 0, hctotal = 0;
   for (int w = 0; w < kScanThreads1 / 32; w++) {
     if (w < warp) {
       start += s_warp[w];
-      coff += s_wchunk[w];
+      loff += s_wl[w];
+      hoff += s_wh[w];
+      hcoff += s_whc[w];
     }
     total += s_warp[w];
-    ctotal += s_wchunk[w];
+    ltotal += s_wl[w];
+    htotal += s_wh[w];
+    hctotal += s_whc[w];
   }
   // class counters are warp-aggregated (match.any): most tiles are empty, and 5000 shared-memory atomics
   // on one address would serialise
@@ -110,9 +138,21 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, int chunk_
       ranges[t] = c ? make_uint2((uint32_t)(start < R_cap ? start : R_cap), (uint32_t)(end < R_cap ? end : R_cap))
                     : make_uint2(0u, 0u);
       if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
-      const uint32_t m = (c + chunk_mask) >> chunk_log2;
-      for (uint32_t q = 0; q < m && coff + q < chunk_cap; q++) chunks[coff + q] = make_uint2((uint32_t)t, q);
-      coff += m;
+      const uint32_t m = (c + kChunk - 1) / kChunk;
+      if (c > part_min) {
+        if (hoff < heavy_cap) {
+          heavy[hoff] = (uint32_t)t;
+          heavy_id[t] = hoff;
+          for (uint32_t q = 0; q < m && hcoff + q < hchunk_cap; q++) hchunks[hcoff + q] = make_uint2((uint32_t)t, q);
+        }
+        hoff++;
+        hcoff += m;
+      } else {
+        for (uint32_t q = 0; q < m && loff + q < item_cap; q++)
+          items[loff + q] = make_uint4((uint32_t)t, q * kChunk, min((uint32_t)kChunk, c - q * kChunk),
+                                       m == 1 ? kItemFinal : 0u);
+        loff += m;
+      }
       start = end;
     }
   }
@@ -120,7 +160,9 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t chunk_cap, int chunk_
   if (tid == 0) {
     status->R = total;
     status->overflow = total > R_cap ? 1u : 0u;
-    misc[0] = ctotal < chunk_cap ? ctotal : chunk_cap;
+    misc[0] = ltotal < item_cap ? ltotal : item_cap;
+    misc[1] = hctotal < hchunk_cap ? hctotal : hchunk_cap;
+    misc[2] = htotal < heavy_cap ? htotal : heavy_cap;
     uint32_t acc = 0;
     for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
       s_cur[c] = acc;
@@ -190,6 +232,185 @@ duplicate_kernel(int P, int gx, int gy, int T, int smem_tiles, uint64_t R_cap, c
         const uint64_t slot = (uint64_t)vr[t].x + atomicAdd(&vc[t], 1u);
         if (slot < R_cap) inst[slot] = make_uint2(depth_bits, gid);
       }
+  }
+}
+
+// ---- depth partition of the heavy tiles ----
+// A heavy tile's instances sit unordered in its range.  They are cut into at most kSlabs slabs of equal
+// width in depth bits between the tile's own minimum and maximum, consecutive slabs are grouped into
+// buckets of at most kChunk instances, and the instances are copied bucket by bucket (unordered inside a
+// bucket) into inst_b at the same range: buckets are depth-disjoint and in depth order, so sorting each
+// one in shared memory finishes the tile -- linear in the list length, where ranking every chunk in
+// every other chunk of its tile is quadratic (77k-instance lists at 1M Gaussians: 38 chunks).
+constexpr int kPartThreads = 256;
+constexpr int kPartItems = kChunk / kPartThreads;
+
+// slab of a depth inside its tile: (depth bits - dmin) >> shift with shift such that the span fits kSlabs
+__device__ __forceinline__ uint32_t slab_shift(uint32_t span) {
+  const int hi = 32 - __clz(span);
+  return hi > 8 ? (uint32_t)(hi - 8) : 0u;
+}
+
+// pass 1: per heavy tile, minimum (stored inverted: zero-initialised maximum of ~depth) and maximum depth
+__global__ void __launch_bounds__(kPartThreads)
+heavy_minmax_kernel(const uint2 *__restrict__ hchunks, const uint32_t *__restrict__ misc,
+                    const uint2 *__restrict__ ranges, const uint32_t *__restrict__ heavy_id,
+                    const uint2 *__restrict__ inst, uint2 *__restrict__ dmm) {
+  if (blockIdx.x >= misc[1]) return;
+  const uint2 hc = hchunks[blockIdx.x];
+  const uint2 range = ranges[hc.x];
+  const uint32_t cstart = range.x + hc.y * kChunk;
+  if (cstart >= range.y) return;
+  const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
+  uint32_t inv = 0u, mx = 0u;
+#pragma unroll
+  for (int i = 0; i < kPartItems; i++) {
+    const uint32_t k = i * kPartThreads + threadIdx.x;
+    if (k < n) {
+      const uint32_t d = inst[cstart + k].x;
+      inv = max(inv, ~d);
+      mx = max(mx, d);
+    }
+  }
+  inv = __reduce_max_sync(0xFFFFFFFFu, inv);
+  mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+  __shared__ uint32_t s_inv, s_mx;
+  if (threadIdx.x == 0) {
+    s_inv = 0u;
+    s_mx = 0u;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&s_inv, inv);
+    atomicMax(&s_mx, mx);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint2 *d = dmm + heavy_id[hc.x];
+    atomicMax(&d->x, s_inv);
+    atomicMax(&d->y, s_mx);
+  }
+}
+
+// pass 2 (kScatter = false): slab histogram of every heavy tile; pass 4 (kScatter = true): copy the
+// instances to their bucket in inst_b -- slots inside a slab are reserved per block from a shared-memory
+// histogram, one global atomic per (block, slab), like duplicate_kernel
+template <bool kScatter>
+__global__ void __launch_bounds__(kPartThreads)
+heavy_slab_kernel(const uint2 *__restrict__ hchunks, const uint32_t *__restrict__ misc,
+                  const uint2 *__restrict__ ranges, const uint32_t *__restrict__ heavy_id,
+                  const uint2 *__restrict__ inst, const uint2 *__restrict__ dmm, uint32_t *__restrict__ slab_count,
+                  const uint32_t *__restrict__ slab_off, const uint32_t *__restrict__ heavy_flag,
+                  uint2 *__restrict__ inst_b) {
+  __shared__ uint32_t s_cnt[kSlabs], s_base[kSlabs];
+  if (blockIdx.x >= misc[1]) return;
+  const uint2 hc = hchunks[blockIdx.x];
+  const uint2 range = ranges[hc.x];
+  const uint32_t cstart = range.x + hc.y * kChunk;
+  if (cstart >= range.y) return;
+  const uint32_t hid = heavy_id[hc.x];
+  if (kScatter && heavy_flag[hid]) return;             // fallback tile: stays in place, plain chunks + merge
+  const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
+  const uint2 mm = dmm[hid];
+  const uint32_t dmin = ~mm.x, shift = slab_shift(mm.y - dmin);
+  for (int k = threadIdx.x; k < kSlabs; k += kPartThreads) s_cnt[k] = 0;
+  __syncthreads();
+  uint2 e[kPartItems];
+  uint32_t slot[kPartItems];
+#pragma unroll
+  for (int i = 0; i < kPartItems; i++) {
+    const uint32_t k = i * kPartThreads + threadIdx.x;
+    slot[i] = 0;
+    if (k < n) {
+      e[i] = inst[cstart + k];
+      slot[i] = atomicAdd(&s_cnt[(e[i].x - dmin) >> shift], 1u);
+    }
+  }
+  __syncthreads();
+  uint32_t *cnt = slab_count + (size_t)hid * kSlabs;
+  for (int k = threadIdx.x; k < kSlabs; k += kPartThreads) {
+    const uint32_t c = s_cnt[k];
+    if (c) {
+      const uint32_t at = atomicAdd(&cnt[k], c);       // histogram; in the scatter pass: the slab's cursor
+      if (kScatter) s_base[k] = range.x + slab_off[(size_t)hid * kSlabs + k] + at;
+    }
+  }
+  if (!kScatter) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kPartItems; i++) {
+    const uint32_t k = i * kPartThreads + threadIdx.x;
+    if (k < n) {
+      const uint32_t dst = s_base[(e[i].x - dmin) >> shift] + slot[i];
+      if (dst < range.y) inst_b[dst] = e[i];
+    }
+  }
+}
+
+// pass 3: one CTA per heavy tile.  Exclusive scan of its slab counts (= slab offsets inside the tile
+// range; the counters are zeroed to serve as the scatter's cursors), consecutive slabs grouped greedily
+// into buckets of at most kChunk instances, one sort item per bucket appended to the item list.  A slab
+// that alone exceeds kChunk (thousands of equal depths) cannot be cut: the tile then keeps the plain
+// chunking and is finished by merge_gather.
+__global__ void __launch_bounds__(kSlabs)
+heavy_plan_kernel(const uint32_t *__restrict__ heavy, const uint2 *__restrict__ ranges, uint32_t *__restrict__ slab_count,
+                  uint32_t *__restrict__ slab_off, uint32_t *__restrict__ heavy_flag, uint4 *__restrict__ items,
+                  uint32_t *__restrict__ misc, uint32_t item_cap, int force_fallback) {
+  __shared__ uint32_t s_c[kSlabs], s_o[kSlabs], s_warp[kSlabs / 32];
+  __shared__ uint2 s_bucket[kSlabs];
+  __shared__ uint32_t s_nb, s_at, s_over;
+  if (blockIdx.x >= misc[2]) return;
+  const uint32_t hid = blockIdx.x, vt = heavy[hid];
+  const uint2 range = ranges[vt];
+  const uint32_t nt = range.y - range.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *cnt = slab_count + (size_t)hid * kSlabs;
+  const uint32_t c = cnt[tid];
+  cnt[tid] = 0u;
+  uint32_t incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  if (tid == 0) s_over = force_fallback ? 1u : 0u;
+  __syncthreads();
+  uint32_t off = incl - c;
+  for (int w = 0; w < warp; w++) off += s_warp[w];
+  s_c[tid] = c;
+  s_o[tid] = off;
+  slab_off[(size_t)hid * kSlabs + tid] = off;
+  if (c > (uint32_t)kChunk) s_over = 1u;
+  __syncthreads();
+  const bool fallback = s_over != 0u;
+  if (tid == 0) {
+    uint32_t nb = 0;
+    if (fallback) {
+      nb = (nt + kChunk - 1) / kChunk;
+    } else {
+      uint32_t start = 0, cur = 0;
+      for (int k = 0; k < kSlabs; k++) {
+        const uint32_t ck = s_c[k];
+        if (cur && cur + ck > (uint32_t)kChunk) {
+          s_bucket[nb++] = make_uint2(start, cur);
+          start = s_o[k];
+          cur = 0;
+        }
+        cur += ck;
+      }
+      if (cur) s_bucket[nb++] = make_uint2(start, cur);
+    }
+    heavy_flag[hid] = fallback ? 1u : 0u;
+    s_nb = nb;
+    s_at = atomicAdd(&misc[0], nb);
+  }
+  __syncthreads();
+  const uint32_t nb = s_nb, at = s_at;
+  for (uint32_t b = tid; b < nb; b += kSlabs) {
+    if (at + b >= item_cap) break;
+    if (fallback) items[at + b] = make_uint4(vt, b * kChunk, min((uint32_t)kChunk, nt - b * kChunk), 0u);
+    else items[at + b] = make_uint4(vt, s_bucket[b].x, s_bucket[b].y, kItemFinal | kItemSrcB);
   }
 }
 
@@ -303,8 +524,8 @@ __device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uin
 constexpr uint32_t kMaxRun = 32;
 template <int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
-sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
-                   const uint2 *__restrict__ ranges, uint2 *inst, const float4 *__restrict__ geom,
+sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ items, const uint32_t *__restrict__ misc,
+                   const uint2 *__restrict__ ranges, uint2 *inst, uint2 *inst_b, const float4 *__restrict__ geom,
                    float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
                    uint32_t *__restrict__ dbg_plist) {
   constexpr int kSortWarps = kSortThreads / 32;
@@ -321,15 +542,16 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
   __shared__ uint32_t s_dmin, s_dmax;
   __shared__ unsigned long long s_and, s_or;
   if (blockIdx.x >= misc[0]) return;
-  const uint2 chunk = chunks[blockIdx.x];
-  const uint32_t vt = chunk.x;
+  const uint4 item = items[blockIdx.x];
+  const uint32_t vt = item.x;
   const uint2 range = ranges[vt];
-  const uint32_t cstart = range.x + chunk.y * kChunk;
-  if (cstart >= range.y) return;                       // chunk of a list clamped by an instance-capacity overflow
-  const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
-  const bool single = range.y - range.x <= (uint32_t)kChunk;
+  const uint32_t cstart = range.x + item.y;
+  if (cstart >= range.y) return;                       // item of a list clamped by an instance-capacity overflow
+  const uint32_t n = min(min((uint32_t)kChunk, item.z), range.y - cstart);
+  const bool single = item.w & kItemFinal;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
+  if (item.w & kItemSrcB) inst = inst_b;
   uint2 *src = inst + cstart;
   if (tid == 0) {
     s_dmin = 0xFFFFFFFFu;
@@ -484,20 +706,21 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chu
 // + the number of smaller keys in every other chunk of the tile (keys are unique: (depth bits, index)).
 template <int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
-merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ chunks, const uint32_t *__restrict__ misc,
+merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ items, const uint32_t *__restrict__ misc,
                     const uint2 *__restrict__ ranges, const uint2 *__restrict__ inst, const float4 *__restrict__ geom,
                     float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
                     uint32_t *__restrict__ dbg_plist) {
   constexpr int kChunk = kSortThreads * kSortItems;
   __shared__ __align__(16) uint64_t s_other[kChunk];
   if (blockIdx.x >= misc[0]) return;
-  const uint2 chunk = chunks[blockIdx.x];
-  const uint32_t vt = chunk.x;
+  const uint4 item = items[blockIdx.x];
+  if (item.w & kItemFinal) return;                     // light tile or depth bucket: finished by sort_chunks
+  const uint32_t vt = item.x;
   const uint2 range = ranges[vt];
   const uint32_t nt = range.y - range.x;
-  if (nt <= (uint32_t)kChunk) return;                  // single-chunk tile: finished by sort_chunks
-  const uint32_t m = (nt + kChunk - 1) / kChunk;
-  const uint32_t cstart = range.x + chunk.y * kChunk;
+  const uint32_t m = (nt + kChunk - 1) / kChunk;       // the tile's plain chunks (plan_kernel's fallback)
+  const uint32_t own = item.y / kChunk;
+  const uint32_t cstart = range.x + item.y;
   if (cstart >= range.y) return;
   const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
   const int tid = threadIdx.x;
@@ -515,7 +738,7 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint2 *__restrict__ ch
     pos[i] = k;
   }
   for (uint32_t c = 0; c < m; c++) {
-    if (c == chunk.y) continue;
+    if (c == own) continue;
     const uint32_t ostart = range.x + c * kChunk, on = min((uint32_t)kChunk, range.y - ostart);
     __syncthreads();
     for (uint32_t k = tid; k < on; k += kSortThreads) s_other[k] = keys[ostart + k];
@@ -555,15 +778,16 @@ __global__ void init_status_kernel(GhrStatus *st, GhrStatus v) { *st = v; }
 
 }  // namespace
 
-// log2 of the sort chunk size: 11 (2048, 256-thread CTAs) or 12 (4096, 512-thread CTAs); the layout's
-// chunk-list capacity is sized for the smaller one.  GHR_CHUNK_LOG2 overrides (A/B only).
-static int chunk_log2() {
-  static const int v = [] {
-    const char *e = getenv("GHR_CHUNK_LOG2");
-    const int x = e ? atoi(e) : 11;
-    return x == 11 ? 11 : 12;
-  }();
-  return v;
+// Lists longer than kPartMin are depth-partitioned instead of rank-merged.  The partition passes are
+// launched only when the instance capacity says long lists are likely (average list >= kChunk; the
+// Python layer sizes R_cap from the instance counts it has seen): at the two-hand sizes no list reaches
+// kPartMin and four empty launches per forward would be pure overhead.  Either way every list is
+// handled exactly -- the merge has no length limit.  GHR_PARTITION=0/1 forces the choice (A/B).
+constexpr int kPartMin = 6 * kChunk;
+static bool use_partition(const GhrDims &d, const Layout &L) {
+  static const int forced = [] { const char *e = getenv("GHR_PARTITION"); return e ? atoi(e) : -1; }();
+  if (forced >= 0) return forced != 0;
+  return (uint64_t)d.R_cap >= (uint64_t)d.V * L.T * kChunk;
 }
 
 cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s) {
@@ -575,9 +799,11 @@ cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *s
   const int VT = d.V * L.T;
   if (VT == 0) return cudaSuccess;
   tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
-      VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, chunk_log2(), (const uint32_t *)(temp + L.t_tile_count),
-      (uint2 *)(state + L.pub.off_ranges), (uint32_t *)(state + L.pub.off_order), (uint2 *)(temp + L.t_chunks),
-      (uint32_t *)(temp + L.t_misc), (GhrStatus *)(state + L.pub.off_status));
+      VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (uint32_t)L.n_hchunks, (uint32_t)L.n_heavy,
+      use_partition(d, L) ? (uint32_t)kPartMin : 0xFFFFFFFFu, (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
+      (uint32_t *)(state + L.pub.off_order), (uint4 *)(temp + L.t_chunks), (uint2 *)(temp + L.t_hchunks),
+      (uint32_t *)(temp + L.t_heavy), (uint32_t *)(temp + L.t_heavy_id), (uint32_t *)(temp + L.t_misc),
+      (GhrStatus *)(state + L.pub.off_status));
   return cudaGetLastError();
 }
 
@@ -602,27 +828,42 @@ cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, c
   const int VT = d.V * L.T;
   if (VT == 0 || d.R_cap <= 0) return cudaSuccess;
   const FastDiv dT = make_fastdiv((uint32_t)L.T), dgx = make_fastdiv((uint32_t)L.gx);
-  // grid = upper bound of the chunk count (the scan wrote the exact one to misc[0]); surplus CTAs exit
-  const int grid = (int)L.n_chunks;
-  auto launch = [&](auto sort_k, auto merge_k, int threads) -> cudaError_t {
-    const size_t sort_smem = (size_t)threads * kSortItems * 8;
-    cudaError_t e = cudaFuncSetAttribute(sort_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
-    if (e != cudaSuccess) return e;
-    sort_k<<<grid, threads, sort_smem, s>>>(
-        d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
-        (const uint2 *)(state + L.pub.off_ranges), (uint2 *)(temp + L.t_inst),
-        (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
-        (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
-    merge_k<<<grid, threads, 0, s>>>(
-        d.P, dT, dgx, (const uint2 *)(temp + L.t_chunks), (const uint32_t *)(temp + L.t_misc),
-        (const uint2 *)(state + L.pub.off_ranges), (const uint2 *)(temp + L.t_inst),
-        (const float4 *)(state + L.pub.off_geom), (float4 *)(state + L.pub.off_records),
-        (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
-    return cudaSuccess;
-  };
-  cudaError_t e = chunk_log2() == 12 ? launch(sort_chunks_kernel<512>, merge_gather_kernel<512>, 512)
-                                     : launch(sort_chunks_kernel<256>, merge_gather_kernel<256>, 256);
+  const bool partition = use_partition(d, L);
+  const uint32_t *misc = (const uint32_t *)(temp + L.t_misc);
+  const uint2 *ranges = (const uint2 *)(state + L.pub.off_ranges);
+  uint2 *inst = (uint2 *)(temp + L.t_inst), *inst_b = (uint2 *)(temp + L.t_inst_b);
+  uint4 *items = (uint4 *)(temp + L.t_chunks);
+  if (partition) {
+    const uint2 *hchunks = (const uint2 *)(temp + L.t_hchunks);
+    const uint32_t *heavy_id = (const uint32_t *)(temp + L.t_heavy_id);
+    uint2 *dmm = (uint2 *)(temp + L.t_dmm);
+    uint32_t *slab_count = (uint32_t *)(temp + L.t_slab_count), *slab_off = (uint32_t *)(temp + L.t_slab_off);
+    uint32_t *heavy_flag = (uint32_t *)(temp + L.t_heavy_flag);
+    // grids are upper bounds (the scan wrote the exact counts to misc[]), surplus CTAs exit on their first
+    // instruction
+    const int hgrid = (int)L.n_hchunks;
+    heavy_minmax_kernel<<<hgrid, kPartThreads, 0, s>>>(hchunks, misc, ranges, heavy_id, inst, dmm);
+    heavy_slab_kernel<false><<<hgrid, kPartThreads, 0, s>>>(hchunks, misc, ranges, heavy_id, inst, dmm, slab_count,
+                                                            slab_off, heavy_flag, inst_b);
+    heavy_plan_kernel<<<(int)L.n_heavy, kSlabs, 0, s>>>((const uint32_t *)(temp + L.t_heavy), ranges, slab_count,
+                                                        slab_off, heavy_flag, items, (uint32_t *)(temp + L.t_misc),
+                                                        (uint32_t)L.n_chunks, 0);
+    heavy_slab_kernel<true><<<hgrid, kPartThreads, 0, s>>>(hchunks, misc, ranges, heavy_id, inst, dmm, slab_count,
+                                                           slab_off, heavy_flag, inst_b);
+  }
+  // chunk sort of every item (light tiles and depth buckets are final), rank merge for the fallback tiles
+  const int grid = partition ? (int)L.n_chunks : (int)((size_t)d.R_cap / kChunk + VT + 1);
+  constexpr int kThreads = 256;
+  const size_t sort_smem = (size_t)kThreads * kSortItems * 8;
+  cudaError_t e = cudaFuncSetAttribute(sort_chunks_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sort_smem);
   if (e != cudaSuccess) return e;
+  sort_chunks_kernel<kThreads><<<grid, kThreads, sort_smem, s>>>(
+      d.P, dT, dgx, items, misc, ranges, inst, inst_b, (const float4 *)(state + L.pub.off_geom),
+      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
+  merge_gather_kernel<kThreads><<<grid, kThreads, 0, s>>>(
+      d.P, dT, dgx, items, misc, ranges, inst, (const float4 *)(state + L.pub.off_geom),
+      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
   return cudaGetLastError();
 }
 

@@ -134,8 +134,17 @@ struct Layout {
   size_t t_zero_bytes;         // prefix of temp that must be zeroed before a forward
   size_t t_tile_count, t_cursor, t_misc;   // uint32 per (view, tile) x 2; misc words
   size_t t_inst;               // uint2 (depth bits, view*P + id) per instance, unordered inside a tile
-  size_t t_chunks;             // uint2 (view*T + tile, chunk index) per sort work item
-  size_t n_chunks;             // their upper bound: R_cap / kChunk + V*T
+  size_t t_inst_b;             // the heavy tiles' instances again, partitioned into depth buckets
+  size_t t_chunks;             // uint4 sort items (view*T + tile, offset in the tile list, count, flags)
+  size_t n_chunks;             // their upper bound: 3 R_cap / kChunk + V*T
+  // heavy tiles (more than kChunk instances): depth partition scratch
+  size_t n_heavy, n_hchunks;   // upper bounds: heavy tiles, their kChunk-sized pieces
+  size_t t_dmm;                // uint2 per heavy tile: (max of ~depth bits, max of depth bits), zeroed
+  size_t t_slab_count;         // uint32[256] per heavy tile: slab histogram, then the scatter's cursors, zeroed
+  size_t t_slab_off;           // uint32[256] per heavy tile: slab offsets inside the tile list
+  size_t t_heavy_flag;         // uint32 per heavy tile: 1 = not partitioned (plain chunks + merge)
+  size_t t_heavy, t_heavy_id;  // heavy tile list; heavy index per (view, tile)
+  size_t t_hchunks;            // uint2 (view*T + tile, chunk index) pieces of the heavy tiles
 };
 
 int compute_layout(const GhrDims &d, Layout *L);

@@ -155,6 +155,21 @@ def test_long_tile_lists_with_depth_ties_and_merge(cuda_device):
     _full_compare(sc2, [cam], BG)
 
 
+def test_heavy_tiles_depth_partition(cuda_device):
+    """Tile lists beyond 6 sort chunks (12288 instances) are partitioned by depth into buckets instead of
+    rank-merged (binning.cu heavy_* kernels); the result must be the same total order.  Second scene: all
+    of a heavy tile's depths in two values -- a slab that cannot be cut -- takes the documented fallback."""
+    cam = scenes.simple_camera(40, 40)
+    sc = scenes.random_scene(60000, seed=9, behind_frac=0.02, huge_frac=0)
+    _full_compare(sc, [cam], BG)
+    gout, _, _ = util.run_gpu(sc, [cam], BG)
+    r = gout[0]["ranges"].astype(np.int64)
+    assert (r[:, 1] - r[:, 0]).max() > 6 * 2048
+    sc2 = scenes.random_scene(60000, seed=10, behind_frac=0, huge_frac=0)
+    sc2.means3D[:, 2] = np.where(np.arange(sc2.P) % 2 == 0, 0.3, 0.3000001).astype(np.float32)
+    _full_compare(sc2, [cam], BG)
+
+
 def test_more_tiles_than_shared_memory_counters(cuda_device):
     """> 16384 tiles per view: preprocess / duplicate fall back from per-block shared-memory tile
     counters to one global atomic per instance."""

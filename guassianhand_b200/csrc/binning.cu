@@ -541,6 +541,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_dmin, s_dmax;
   __shared__ unsigned long long s_and, s_or;
+  __shared__ __align__(16) float4 s_stage[kSortWarps][96];   // record staging of the final gather
   if (blockIdx.x >= misc[0]) return;
   const uint4 item = items[blockIdx.x];
   const uint32_t vt = item.x;
@@ -688,11 +689,35 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
     // the whole tile list: gather in sorted order
     const uint32_t ty = dgx.div(tile);
     const int tile_x0 = (int)(tile - ty * dgx.d) * kTile, tile_y0 = (int)ty * kTile;
-#pragma unroll 2
-    for (uint32_t k = tid; k < n; k += kSortThreads) {
-      const uint64_t key = a[k];
-      emit_instance((size_t)cstart + k, (uint32_t)(key >> 32) + dmin, (uint32_t)key, gbase, tile, tile_x0, tile_y0,
-                    geom, records, masks, dbg_keys, dbg_plist);
+    // A warp's 32 records are one contiguous 1536-byte block of the slab: they are staged in shared memory
+    // (48-byte stride: conflict-free 128-bit stores) and leave as three fully coalesced warp stores instead
+    // of three stores that each touch all 48 sectors of the block.
+    float4 *stg = &s_stage[warp][0];
+    for (uint32_t kb = warp * 32; kb < n; kb += kSortThreads) {
+      const uint32_t k = kb + lane;
+      if (k < n) {
+        const uint64_t key = a[k];
+        const uint32_t id = (uint32_t)key;
+        const size_t g = (size_t)gbase + id, r = (size_t)cstart + k;
+        const float4 q0 = geom[4 * g], q1 = geom[4 * g + 1];
+        float4 q2 = geom[4 * g + 2];
+        masks[r] = (uint8_t)subblock_mask(q0, q1, tile_x0, tile_y0);
+        if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | ((uint32_t)(key >> 32) + dmin);
+        if (dbg_plist) dbg_plist[r] = id;
+        q2.w = __uint_as_float(id);
+        stg[3 * lane] = q0;
+        stg[3 * lane + 1] = q1;
+        stg[3 * lane + 2] = q2;
+      }
+      __syncwarp();
+      const uint32_t cnt3 = 3u * min(32u, n - kb);
+      float4 *out = records + 3 * ((size_t)cstart + kb);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const uint32_t idx = i * 32 + lane;
+        if (idx < cnt3) out[idx] = stg[idx];
+      }
+      __syncwarp();
     }
   } else {
     // one of several chunks of its tile: leave the sorted absolute keys in place for merge_gather

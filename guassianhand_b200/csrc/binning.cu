@@ -808,7 +808,10 @@ __global__ void init_status_kernel(GhrStatus *st, GhrStatus v) { *st = v; }
 // Python layer sizes R_cap from the instance counts it has seen): at the two-hand sizes no list reaches
 // kPartMin and four empty launches per forward would be pure overhead.  Either way every list is
 // handled exactly -- the merge has no length limit.  GHR_PARTITION=0/1 forces the choice (A/B).
-constexpr int kPartMin = 6 * kChunk;
+static int part_min() {
+  static const int v = [] { const char *e = getenv("GHR_PART_MIN_CHUNKS"); return (e ? atoi(e) : 1) * kChunk; }();
+  return v;
+}
 static bool use_partition(const GhrDims &d, const Layout &L) {
   static const int forced = [] { const char *e = getenv("GHR_PARTITION"); return e ? atoi(e) : -1; }();
   if (forced >= 0) return forced != 0;
@@ -825,7 +828,7 @@ cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *s
   if (VT == 0) return cudaSuccess;
   tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
       VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (uint32_t)L.n_hchunks, (uint32_t)L.n_heavy,
-      use_partition(d, L) ? (uint32_t)kPartMin : 0xFFFFFFFFu, (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
+      use_partition(d, L) ? (uint32_t)part_min() : 0xFFFFFFFFu, (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
       (uint32_t *)(state + L.pub.off_order), (uint4 *)(temp + L.t_chunks), (uint2 *)(temp + L.t_hchunks),
       (uint32_t *)(temp + L.t_heavy), (uint32_t *)(temp + L.t_heavy_id), (uint32_t *)(temp + L.t_misc),
       (GhrStatus *)(state + L.pub.off_status));

@@ -80,6 +80,61 @@ __device__ __forceinline__ void sh_to_rgb(int D, const float *sh, float px, floa
   *clamp_bits = bits;
 }
 
+// A.3 with the coefficient row read as 128-bit loads (rows of M*3 floats that are a multiple of 16
+// bytes: M = 4, 16).  Same arithmetic as sh_to_rgb, coefficient by coefficient: channel ch accumulates
+// r = C0*sh[0][ch], then r = fma(basis_k, sh[k][ch], r) for k = 1.. in order, with basis_k the very
+// expressions of the scalar version -- the rgb bits are identical.
+__device__ __forceinline__ void sh_to_rgb_vec(int D, const float4 *__restrict__ sh4, float px, float py, float pz,
+                                              const float *campos, float *rgb, uint32_t *clamp_bits) {
+  float dx = fsub(px, campos[0]), dy = fsub(py, campos[1]), dz = fsub(pz, campos[2]);
+  float len = fsqrt(dot3(dx, dx, dy, dy, dz, dz));
+  float x = fdiv(dx, len), y = fdiv(dy, len), z = fdiv(dz, len);
+  float basis[16];
+  basis[0] = SH_C0;
+  {
+    float xx = fmul(x, x), yy = fmul(y, y), zz = fmul(z, z);
+    float xy = fmul(x, y), yz = fmul(y, z), xz = fmul(x, z);
+    basis[1] = -fmul(SH_C1, y);
+    basis[2] = fmul(SH_C1, z);
+    basis[3] = -fmul(SH_C1, x);
+    basis[4] = fmul(SH_C2c[0], xy);
+    basis[5] = fmul(SH_C2c[1], yz);
+    basis[6] = fmul(SH_C2c[2], fsub(ffma(2.0f, zz, -xx), yy));
+    basis[7] = fmul(SH_C2c[3], xz);
+    basis[8] = fmul(SH_C2c[4], fsub(xx, yy));
+    basis[9] = fmul(fmul(SH_C3c[0], y), ffma(3.0f, xx, -yy));
+    basis[10] = fmul(fmul(SH_C3c[1], xy), z);
+    basis[11] = fmul(fmul(SH_C3c[2], y), fsub(ffma(4.0f, zz, -xx), yy));
+    basis[12] = fmul(fmul(SH_C3c[3], z), ffma(-3.0f, yy, ffma(2.0f, zz, -fmul(3.0f, xx))));
+    basis[13] = fmul(fmul(SH_C3c[4], x), fsub(ffma(4.0f, zz, -xx), yy));
+    basis[14] = fmul(fmul(SH_C3c[5], z), fsub(xx, yy));
+    basis[15] = fmul(fmul(SH_C3c[6], x), ffma(-3.0f, yy, xx));
+  }
+  const int nf = 3 * (D + 1) * (D + 1);      // floats of the row that are used
+  float r[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    if (4 * j < nf) {
+      const float4 v = sh4[j];
+      const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int f = 4 * j + c, k = f / 3, ch = f % 3;
+        if (f < nf) r[ch] = k == 0 ? fmul(SH_C0, e[c]) : ffma(basis[k], e[c], r[ch]);
+      }
+    }
+  }
+  uint32_t bits = 0;
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const float t = fadd(r[ch], 0.5f);
+    if (t < 0.f) bits |= (1u << ch);
+    rgb[ch] = fmaxf(t, 0.f);
+  }
+  *clamp_bits = bits;
+}
+
+template <bool kVecSH>
 __global__ void __launch_bounds__(256)
 preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, float scale_modifier, uint32_t flags,
                   Cameras cam, Gaussians g, float4 *__restrict__ geom, uint8_t *__restrict__ clamped,
@@ -105,6 +160,8 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     const float *PV = cam.proj + 16 * v;
     float tanfovx = cam.tanfov ? cam.tanfov[2 * v] : cam.tanfovx;
     float tanfovy = cam.tanfov ? cam.tanfov[2 * v + 1] : cam.tanfovy;
+    // (12-byte rows: the three scalar loads of a warp use every byte of the sectors they touch; staging the
+    // rows through shared memory with 128-bit loads was measured 3 us slower -- the kernel is latency-bound)
     float px = g.means3D[3 * i], py = g.means3D[3 * i + 1], pz = g.means3D[3 * i + 2];
     int radius = 0;
     uint32_t tiles = 0;
@@ -182,6 +239,9 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
             rgb[0] = g.colors_precomp[3 * i];
             rgb[1] = g.colors_precomp[3 * i + 1];
             rgb[2] = g.colors_precomp[3 * i + 2];
+          } else if (kVecSH) {
+            sh_to_rgb_vec(D, reinterpret_cast<const float4 *>(g.shs + (size_t)i * M * 3), px, py, pz,
+                          cam.campos + 3 * v, rgb, &cbits);
           } else {
             sh_to_rgb(D, g.shs + (size_t)i * M * 3, px, py, pz, cam.campos + 3 * v, rgb, &cbits);
           }
@@ -248,15 +308,22 @@ cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &
   dim3 grid(nb, d.V), block(256);
   const int smem_tiles = L.T <= kMaxSmemTiles ? L.T : 0;
   const size_t smem = (size_t)smem_tiles * 4;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
-  preprocess_kernel<<<grid, block, smem, s>>>(
-      d.P, d.V, d.H, d.W, d.M, d.sh_degree, L.gx, L.gy, scale_modifier, flags, cam, g,
-      (float4 *)(state + L.pub.off_geom), d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr, radii,
-      (uint32_t *)(temp + L.t_tile_count), (uint32_t *)(state + L.pub.off_tilemax),
-      (GhrStatus *)(state + L.pub.off_status), L.T, smem_tiles);
+  // SH rows that are a multiple of 16 bytes (M = 4, 16) on a 16-byte aligned base take the 128-bit path
+  const bool vec_sh = g.shs && !g.colors_precomp && (d.M * 3) % 4 == 0 && ((uintptr_t)g.shs & 15) == 0;
+  auto launch = [&](auto kern) -> cudaError_t {
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, block, smem, s>>>(
+        d.P, d.V, d.H, d.W, d.M, d.sh_degree, L.gx, L.gy, scale_modifier, flags, cam, g,
+        (float4 *)(state + L.pub.off_geom), d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr, radii,
+        (uint32_t *)(temp + L.t_tile_count), (uint32_t *)(state + L.pub.off_tilemax),
+        (GhrStatus *)(state + L.pub.off_status), L.T, smem_tiles);
+    return cudaSuccess;
+  };
+  cudaError_t e = vec_sh ? launch(preprocess_kernel<true>) : launch(preprocess_kernel<false>);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

@@ -44,7 +44,9 @@ __device__ __forceinline__ void cov3d_of(const float *sc, float mod, float4 q, f
   c3[5] = dot3(A[2][0], A[2][0], A[2][1], A[2][1], A[2][2], A[2][2]);
 }
 
-template <bool HAS_SH>
+// kVecSH: the SH coefficient row and its gradient row are multiples of 16 bytes on 16-byte aligned bases
+// (M = 4, 16): both are streamed with 128-bit accesses, 12 instead of 48 per view for degree 3.
+template <bool HAS_SH, bool kVecSH>
 __global__ void __launch_bounds__(128)
 preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale_modifier, Cameras cam,
                            Gaussians g, const float4 *__restrict__ geom, const uint8_t *__restrict__ clamped,
@@ -196,6 +198,55 @@ preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale
           }
         }
         const int nb = (D + 1) * (D + 1);
+        if (kVecSH) {
+          // t_k = sum_ch sh[k][ch] * dL/dRGB[ch]: the view-direction gradient needs only these 16 sums
+          float tk[16];
+#pragma unroll
+          for (int k = 0; k < 16; k++) tk[k] = 0.f;
+          const float4 *sh4 = reinterpret_cast<const float4 *>(sh);
+          float4 *dsh4 = reinterpret_cast<float4 *>(dsh_out);
+          const int nf = 3 * nb;
+          const bool fresh = sh_first && !go.accumulate;
+#pragma unroll
+          for (int j = 0; j < 12; j++) {
+            if (4 * j < nf) {
+              const float4 vv = sh4[j];
+              const float e[4] = {vv.x, vv.y, vv.z, vv.w};
+              float4 ov = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (dsh_out && !fresh) ov = dsh4[j];
+              float o[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+              for (int c = 0; c < 4; c++) {
+                const int f = 4 * j + c, k = f / 3, ch = f % 3;
+                if (f < nf) {
+                  o[c] += basis[k] * dRGB[ch];
+                  tk[k] += e[c] * dRGB[ch];
+                }
+              }
+              if (dsh_out) dsh4[j] = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (D > 0) {
+            ddx = -SH_C1 * tk[3]; ddy = -SH_C1 * tk[1]; ddz = SH_C1 * tk[2];
+            if (D > 1) {
+              const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+              ddx += SHB_C2[0] * y * tk[4] + SHB_C2[2] * 2.f * -x * tk[6] + SHB_C2[3] * z * tk[7] + SHB_C2[4] * 2.f * x * tk[8];
+              ddy += SHB_C2[0] * x * tk[4] + SHB_C2[1] * z * tk[5] + SHB_C2[2] * 2.f * -y * tk[6] + SHB_C2[4] * 2.f * -y * tk[8];
+              ddz += SHB_C2[1] * y * tk[5] + SHB_C2[2] * 4.f * z * tk[6] + SHB_C2[3] * x * tk[7];
+              if (D > 2) {
+                ddx += SHB_C3[0] * tk[9] * 6.f * xy + SHB_C3[1] * tk[10] * yz + SHB_C3[2] * tk[11] * -2.f * xy +
+                       SHB_C3[3] * tk[12] * -6.f * xz + SHB_C3[4] * tk[13] * (-3.f * xx + 4.f * zz - yy) +
+                       SHB_C3[5] * tk[14] * 2.f * xz + SHB_C3[6] * tk[15] * 3.f * (xx - yy);
+                ddy += SHB_C3[0] * tk[9] * 3.f * (xx - yy) + SHB_C3[1] * tk[10] * xz +
+                       SHB_C3[2] * tk[11] * (-3.f * yy + 4.f * zz - xx) + SHB_C3[3] * tk[12] * -6.f * yz +
+                       SHB_C3[4] * tk[13] * -2.f * xy + SHB_C3[5] * tk[14] * -2.f * yz + SHB_C3[6] * tk[15] * -6.f * xy;
+                ddz += SHB_C3[1] * tk[10] * xy + SHB_C3[2] * tk[11] * 8.f * yz +
+                       SHB_C3[3] * tk[12] * 3.f * (2.f * zz - xx - yy) + SHB_C3[4] * tk[13] * 8.f * xz +
+                       SHB_C3[5] * tk[14] * (xx - yy);
+              }
+            }
+          }
+        } else {
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
           const float gch = dRGB[ch];
@@ -230,6 +281,7 @@ preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale
           }
 #undef SHV
           ddx += rx * gch; ddy += ry * gch; ddz += rz * gch;
+        }
         }
         sh_first = false;
         const float is32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
@@ -309,12 +361,18 @@ cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const 
   int nb = (d.P + 127) / 128;
   const float4 *geom = (const float4 *)(state + L.pub.off_geom);
   const uint8_t *cl = (const uint8_t *)(state + L.pub.off_clamped);
-  if (g.shs && !g.colors_precomp)
-    preprocess_backward_kernel<true><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier, cam, g,
-                                                        geom, cl, acc, go);
+  const bool has_sh = g.shs && !g.colors_precomp;
+  const bool vec_sh = has_sh && (d.M * 3) % 4 == 0 && ((uintptr_t)g.shs & 15) == 0 &&
+                      (go.dsh == nullptr || ((uintptr_t)go.dsh & 15) == 0);
+  if (vec_sh)
+    preprocess_backward_kernel<true, true><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+                                                              cam, g, geom, cl, acc, go);
+  else if (has_sh)
+    preprocess_backward_kernel<true, false><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+                                                               cam, g, geom, cl, acc, go);
   else
-    preprocess_backward_kernel<false><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier, cam,
-                                                         g, geom, cl, acc, go);
+    preprocess_backward_kernel<false, false><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+                                                                cam, g, geom, cl, acc, go);
   return cudaGetLastError();
 }
 

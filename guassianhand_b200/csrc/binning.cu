@@ -12,15 +12,21 @@
 //                        touches, at a slot taken from the tile's cursor -- unordered inside the tile.
 //                        Slots are reserved per (block, tile) from shared-memory counts, so the global
 //                        atomics are one per touched tile per block, not one per instance.
-//   sort_chunks        : every tile list is cut into chunks of kChunk instances; one CTA sorts one chunk by
-//                        (depth bits, id) in shared memory (two radix passes on the 16 leading significant
-//                        bits + a local fix).  A single-chunk tile is finished here: its 48-byte geometry
-//                        records are gathered in sorted order with their sub-block cull masks.
-//   merge_gather       : for a tile of several chunks, one CTA per chunk ranks its keys in the other
-//                        (sorted) chunks by binary search -- final position = own index + ranks -- and
-//                        gathers its records straight to their final place.
-// No global sort, no cross-block prefix: all work items are uniform chunks, independent after the scan.  Result: bit for
-// bit the upstream order (checked against the oracle's sorted keys / point list / ranges).
+//   sort_chunks        : one CTA sorts one work item of at most kChunk instances by (depth bits, id) in
+//                        shared memory: a counting pass on the 11 leading significant bits, then every key
+//                        ranks itself inside its bin.  An item that is a whole tile list (or a depth bucket,
+//                        below) is finished here: its 48-byte geometry records are gathered in sorted order
+//                        with their sub-block cull masks.
+//   merge_gather       : a list of a few chunks: one CTA per chunk ranks its keys in the other (sorted)
+//                        chunks -- final position = own index + ranks -- and gathers its records straight
+//                        to their final place.  Quadratic in the chunks of a list.
+//   heavy_*            : when long lists are likely, every multi-chunk list is first partitioned by depth
+//                        (min/max, 256-slab histogram, bucket plan, scatter) into depth-disjoint buckets of
+//                        at most kChunk instances, each an ordinary sort item that is final in place:
+//                        linear in the list length; merge_gather is then only the fallback for lists whose
+//                        depths are too degenerate to cut.
+// No global sort, no cross-block prefix: all work items are uniform, independent after the scan.  Result:
+// bit for bit the upstream order (checked against the oracle's sorted keys / point list / ranges).
 #include <cstdlib>
 
 #include "ghr_internal.cuh"

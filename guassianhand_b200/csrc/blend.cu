@@ -3,15 +3,16 @@
 // Forward replaces upstream renderCUDA<3> forward; backward replaces
 // renderCUDA<3> backward (K7, A.6).  One CTA per (view, tile), taken heaviest-first from the tile
 // schedule.  8 consumer warps (one thread per pixel, a warp covers an 8x4 pixel block) + 1 producer
-// warp.  The tile's instance list is a contiguous slab of 48-byte records (written by
-// gather_ranges); the producer streams it into a ring of shared-memory stages with 1-D bulk async
+// warp.  The tile's instance list is a contiguous slab of 48-byte records (written by the chunk
+// sort / merge of binning.cu); the producer streams it into a ring of shared-memory stages with 1-D bulk async
 // copies (cp.async.bulk -> UBLKCP) completing on "full" mbarriers; consumer warps release a stage on
 // its "empty" mbarrier, so warps drift apart by up to kStages-1 stages instead of meeting at a CTA
-// barrier every round.  Inside a stage each warp first culls: lane l tests instance (base+l)'s
-// conservative alpha>=1/255 box against the warp's pixel block, a ballot compacts the survivors,
-// and only those are blended.  Backward: per-instance partial gradients are reduced across the warp
-// through a conflict-free shared-memory transpose (36 issue slots for 9 values) and leave the SM as
-// one RED.ADD per value per warp.
+// barrier every round.  Inside a stage each warp first culls: an instance's precomputed 8-bit mask says
+// which 8x4 sub-blocks it can reach with alpha >= 1/255, a ballot compacts the survivors into a queue,
+// and only those are blended.  Backward: one (tile, 256-instance segment) work unit per two 4-warp CTAs,
+// restarted from the forward's checkpoints; per-instance partial gradients are parked in shared memory
+// three instances at a time, reduced across the warp with conflict-free 128-bit loads and leave the SM
+// as one RED.ADD per value per warp.
 #include <cstdlib>
 
 #include "ghr_internal.cuh"

@@ -131,6 +131,7 @@ __device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt
                                                 uint8_t *q, uint32_t pad) {
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t total = 0;
+  __syncwarp();   // every lane has finished reading the previous stage's queue
 #pragma unroll
   for (int w = 0; w < kStageN / 32; w++) {
     const uint32_t e = w * 32 + lane;
@@ -152,6 +153,7 @@ __device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_
                                                      uint32_t rec_base, uint32_t pad_addr) {
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t total = 0;
+  __syncwarp();   // every lane has finished reading the previous stage's queue
 #pragma unroll
   for (int w = 0; w < kStageN / 32; w++) {
     const uint32_t e = w * 32 + lane;

@@ -63,3 +63,25 @@ def test_null_args_do_not_crash(native):
     a.dims = native.GhrDims(4, 1, 16, 16, 0, 0, 64)
     assert L.ghr_forward(C.byref(a), None) == native.GHR_EINVAL      # required pointers missing
     assert b"required" in L.ghr_last_error()
+
+
+def test_view_group_helpers_cpu():
+    """Host logic of the overlapped schedule: contiguous balanced view groups, camera slicing."""
+    import torch
+    from guassianhand_b200 import api
+    for V in (1, 2, 5, 8, 13):
+        for G in (1, 2, 3, 8):
+            G = min(G, V)
+            gs = api._groups(V, G)
+            assert gs[0][0] == 0 and gs[-1][1] == V and len(gs) == G
+            assert all(a[1] == b[0] for a, b in zip(gs, gs[1:]))
+            sizes = [hi - lo for lo, hi in gs]
+            assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
+    V = 5
+    cams = api._Cams(V=V, H=4, W=6, view=torch.arange(V * 16.).view(V, 16), proj=torch.zeros(V, 16),
+                     campos=torch.zeros(V, 3), tanfov=torch.ones(V, 2), tanfovx=0.0, tanfovy=0.0,
+                     bg=torch.arange(V * 3.).view(V, 3), bg_stride=3)
+    c = api._slice_cams(cams, 2, 4)
+    assert c.V == 2 and torch.equal(c.view, cams.view[2:4]) and torch.equal(c.bg, cams.bg[2:4])
+    shared = cams._replace(bg=torch.zeros(3), bg_stride=0)
+    assert api._slice_cams(shared, 1, 3).bg.shape == (3,)

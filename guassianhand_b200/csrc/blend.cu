@@ -9,7 +9,7 @@
 // its "empty" mbarrier, so warps drift apart by up to kStages-1 stages instead of meeting at a CTA
 // barrier every round.  Inside a stage each warp first culls: an instance's precomputed 8-bit mask says
 // which 8x4 sub-blocks it can reach with alpha >= 1/255, a ballot compacts the survivors into a queue,
-// and only those are blended.  Backward: one (tile, 256-instance segment) work unit per two 4-warp CTAs,
+// and only those are blended.  Backward: one (tile, 128-instance segment) work unit per two 4-warp CTAs,
 // restarted from the forward's checkpoints; per-instance partial gradients are parked in shared memory
 // three instances at a time, reduced across the warp with conflict-free 128-bit loads and leave the SM
 // as one RED.ADD per value per warp.
@@ -672,7 +672,7 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
   };
   if (warps <= 4) {
     if (!ring) launch(blend_backward_kernel<2, false, 8, 4>, 4);
-    else launch(blend_backward_kernel<2, true, 7, 4>, 4);
+    else launch(blend_backward_kernel<2, true, 8, 4>, 4);
   } else if (ring) {
     if (ilp <= 2) launch(blend_backward_kernel<2, true, 4, 8>, 8);
     else launch(blend_backward_kernel<3, true, 4, 8>, 8);

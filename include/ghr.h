@@ -42,7 +42,7 @@ extern "C" {
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
 #define GHR_ABI_VERSION 8
-#define GHR_SEGMENT 256 /* instances per backward work unit / forward checkpoint interval */
+#define GHR_SEGMENT 128 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
 #define GHR_NSTAGES_FWD 5 /* 0 preprocess (+ per-tile counts), 1 tile scan + schedule, 2 duplicate, 3 per-tile sort + gather, 4 blend */

@@ -194,7 +194,27 @@ def run_ours(args):
                  colors_precomp=t(sc.colors))
     n_groups = max(1, len(cams) // (B * world)) if B * world <= len(cams) else 1
 
+    # which rank renders which view of a step: the step's world*B views are dealt to the ranks so that the
+    # per-rank instance counts are even (dist.balanced_shards; costs = instances of every pool view,
+    # counted once here).  The step ends at the slowest rank.
+    assign = None
+    if world > 1 and B * world <= len(cams):
+        from guassianhand_b200.dist import balanced_shards
+        costs = []
+        for c in cams:
+            v1 = util.gpu_views([c], bg, dev)
+            r1 = api.forward_raw(v1.cams(), gauss["means3D"], gauss["opacities"], gauss["scales"], gauss["rotations"],
+                                 None, None, gauss["colors_precomp"], 0, 1.0)
+            costs.append(r1.R)
+        assign = []
+        for g in range(n_groups):
+            blk = list(range(g * B * world, (g + 1) * B * world))
+            sh = balanced_shards([costs[i] for i in blk], world)
+            assign.append([blk[i] for i in sh[rank]])
+
     def group_cams(step):
+        if assign is not None:
+            return [cams[i] for i in assign[step % n_groups]]
         base = (step % n_groups) * B * world + rank * B
         return [cams[(base + j) % len(cams)] for j in range(B)]
 
@@ -615,7 +635,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": _workload(B), "views_per_rank_per_step": B, "gaussians": P, "image": [H, W],
                        "instances_per_step": R_mean, "blend_pairs_per_step": I_mean, "R_cap": R_cap,
-                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"camera-sharded dp{world}",
+                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"camera-sharded dp{world}" + (" (views dealt to ranks by instance count)" if assign else ""),
                        "launch": "eager, one stream" if args.no_graph else
                        f"CUDA graph replay (1 launch/step) + 4 camera copies; the step's views run as {G} "
                        f"independent forward->backward chains on {G} streams inside the graph (stage_ms: the same "

@@ -24,6 +24,23 @@ def shard_views(n_views: int, rank: int, world: int) -> range:
     return range(start, start + base + (1 if rank < rem else 0))
 
 
+def balanced_shards(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Split view indices [0, len(costs)) into `world` shards of equal size (len(costs) must be a
+    multiple of world) whose summed costs are as equal as a sort + snake deal makes them: views in
+    descending cost order go to ranks 0..w-1, w-1..0, 0..w-1, ...  Every rank computes the same
+    assignment from the same costs.  The step ends with an all-reduce, i.e. at the slowest rank: with
+    per-view instance counts as costs the ranks finish together instead of a few percent apart."""
+    n = len(costs)
+    if world < 1 or n % world:
+        raise ValueError(f"{n} views do not split evenly over {world} ranks")
+    order = sorted(range(n), key=lambda i: (-float(costs[i]), i))
+    shards: List[List[int]] = [[] for _ in range(world)]
+    for k, i in enumerate(order):
+        rnd, pos = divmod(k, world)
+        shards[pos if rnd % 2 == 0 else world - 1 - pos].append(i)
+    return [sorted(s) for s in shards]
+
+
 class PackedGrads:
     """One flat fp32 buffer holding every Gaussian-attribute gradient that is summed over views.
 

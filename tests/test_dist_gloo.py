@@ -75,3 +75,22 @@ def test_camera_sharded_allreduce_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert sorted(i for _, _, idx in res for i in idx) == list(range(7))
+
+
+def test_balanced_shards():
+    from guassianhand_b200.dist import balanced_shards
+    import random
+    rnd = random.Random(0)
+    costs = [rnd.uniform(0.8, 1.3) for _ in range(64)]
+    for world in (1, 2, 4, 8):
+        sh = balanced_shards(costs, world)
+        assert sorted(i for s in sh for i in s) == list(range(64)) and all(len(s) == 64 // world for s in sh)
+        sums = [sum(costs[i] for i in s) for s in sh]
+        naive = [sum(costs[r * (64 // world):(r + 1) * (64 // world)]) for r in range(world)]
+        assert max(sums) - min(sums) <= max(naive) - min(naive) + 1e-12
+        assert max(sums) / (sum(costs) / world) < 1.02
+    try:
+        balanced_shards(costs[:63], 2)
+        assert False
+    except ValueError:
+        pass

@@ -104,9 +104,15 @@ class StepResult(NamedTuple):
 
 
 
+_side_streams: Dict[int, list] = {}
+
+
 def _streams(dev: torch.device, n: int):
-    from . import api
-    return api._streams(dev, n)       # one pool of side streams per device, shared with rasterize_views
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _side_streams.setdefault(idx, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=idx))
+    return pool[:n]
 
 
 def _slice_views(views, lo: int, hi: int):

@@ -53,10 +53,6 @@ r = fit_step_grads(gauss, views, dL, grads, overlap=2, group=None)
 caps = [int(x.R * 1.25) + (1 << 14) for x in r.results]
 
 
-class _NoGroup:      # GraphedFitStep without the collective: capture with the process group hidden
-    pass
-
-
 # graph of the LOCAL part only: PackedGrads.all_reduce_ is skipped by capturing on a private buffer whose
 # all_reduce_ is a no-op
 class LocalGrads(PackedGrads):
@@ -99,7 +95,7 @@ for mode in ("no_flush", "flush"):
     out[mode] = {"compute_us_per_rank": [round(float(v[0]), 1) for v in allv],
                  "allreduce_plus_wait_us_per_rank": [round(float(v[1]), 1) for v in allv]}
 if rank == 0:
-    out["world"], out["views_per_rank"], out["instances_per_rank_view_set"] = world, B, None
+    out["world"], out["views_per_rank"] = world, B
     print(json.dumps(out), flush=True)
 torch.cuda.synchronize()
 os._exit(0)

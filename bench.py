@@ -22,6 +22,7 @@ all-reduce of that buffer.  Weak scaling: B views per rank per step.
             so the oracle port is the reference arm (kind "port").
 """
 import argparse
+import contextlib
 import json
 import os
 import sys
@@ -294,7 +295,11 @@ def run_ours(args):
     for i in range(Wm):
         run_step(i)
     sync_all()
-    with ClockSampler(local) as clk:
+    # clocks are sampled on rank 0 only (it prints the line): NVML calls take the driver's lock, and with one
+    # sampler per rank a delayed launch on ANY rank stalls every rank at the step's all-reduce -- a suspect
+    # for the 8-rank step being 240 us longer than the 1-rank step while its kernels are unchanged
+    sampler = ClockSampler(local, period=0.005 if world == 1 else 0.02) if rank == 0 else contextlib.nullcontext()
+    with sampler as clk:
         for i in range(K):
             flush.zero_()                                   # L2 flush, outside the timed events
             ev_s[i].record()

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 8
+GHR_ABI_VERSION = 9
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
 FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
@@ -118,7 +118,7 @@ def lib():
     L.ghr_event_destroy.argtypes = [_vp]
     L.ghr_event_record.argtypes = [_vp, _vp]
     L.ghr_event_elapsed_ms.argtypes = [_vp, _vp, C.POINTER(C.c_float)]
-    L.ghr_fp32_probe.argtypes = [C.c_int32, _vp, C.POINTER(C.c_double), _vp]
+    L.ghr_fp32_probe.argtypes = [C.c_int32, C.c_int32, _vp, _vp, C.POINTER(C.c_double), _vp]
     L.ghr_struct_size.restype = C.c_size_t
     L.ghr_struct_size.argtypes = [C.c_char_p]
     L.ghr_attributes_forward.restype = C.c_int

@@ -28,24 +28,43 @@ def _nvcc():
     return "nvcc"
 
 
-def _stale():
-    if not os.path.exists(OUT):
+def _stale(out=None):
+    out = out or OUT
+    if not os.path.exists(out):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(out)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     deps.append(os.path.join(HERE, "..", "include", "ghr.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return OUT
-    os.makedirs(OBJ, exist_ok=True)
+# Build-time variants (never the shipped library): test / profiling instrumentation selected with -D flags,
+# written next to libghr.so as libghr_<name>.so.  tests and tools load one by setting _native.LIB_PATH
+# before the first _native.lib() call.
+VARIANTS = {
+    "exact": ["-DGHR_EXACT_EXP"],        # libdevice expf + IEEE divide in the blend kernels (parity counting test)
+    "timeline": ["-DGHR_TIMELINE"],      # per-CTA start/stop clocks of the blend kernels (tools/blend_timeline.py)
+    "bwd2": ["-DGHR_BWD_WARPS=2"],       # A/B: two half-tile CTAs per backward unit
+}
+
+
+def variant_path(name: str) -> str:
+    return os.path.join(HERE, f"libghr_{name}.so")
+
+
+def build(force: bool = False, verbose: bool = False, variant: str = None, defines=None) -> str:
+    out, objdir, extra = OUT, OBJ, []
+    if variant:
+        out, objdir = variant_path(variant), os.path.join(OBJ, variant)
+        extra = list(VARIANTS[variant] if defines is None else defines)
+    if not force and not _stale(out):
+        return out
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -54,14 +73,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         res = list(ex.map(one, SOURCES))
     log = "\n".join(r[1] for r in res)
-    with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write(log)
     if verbose:
         print(log)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *[r[0] for r in res], "-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *[r[0] for r in res], "-lcudart"]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    names = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for v in names or [None]:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=v))

@@ -102,16 +102,42 @@ struct StageTimer {
   void stop(int i) { if (ev) cudaEventRecord((cudaEvent_t)ev[2 * i + 1], s); }
 };
 
-__global__ void fp32_probe_kernel(int iters, float *sink) {
-  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
-        a6 = a0 + 6.f, a7 = a0 + 7.f;
-  const float m = 0.999f, c = 1e-3f;
-  for (int i = 0; i < iters; i++) {
-    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
-    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+// FP32 roofline probes: 8 independent dependent-FMA chains per thread, 16x unrolled (128 FMA instructions
+// per loop trip), multiplier and addend in registers (the 3-register form the blend kernels issue).
+// kPacked: the chains are fp32 pairs (FFMA2), two FMAs per instruction.
+template <bool kPacked>
+__global__ void __launch_bounds__(256) fp32_probe_kernel(int iters, const float *__restrict__ in, float *sink) {
+  const float m = in[0], c = in[1];
+  if (kPacked) {
+    f32x2 a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = pk2(threadIdx.x * 1e-3f + j, threadIdx.x * 2e-3f + j);
+    const f32x2 m2 = bc2(m), c2 = bc2(c);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = fma2(a[j], m2, c2);
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r += lo2(a[j]) + hi2(a[j]);
+    if (r == 123.456f) *sink = r;
+  } else {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = threadIdx.x * 1e-3f + j;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 16; u++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = __fmaf_rn(a[j], m, c);
+    }
+    float r = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) r += a[j];
+    if (r == 123.456f) *sink = r;
   }
-  float r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-  if (r == 123.456f) *sink = r;
 }
 
 }  // namespace ghr
@@ -297,13 +323,14 @@ int ghr_event_elapsed_ms(void *start, void *stop, float *ms_out) {
   return GHR_OK;
 }
 
-int ghr_fp32_probe(int32_t iters, float *sink, double *flops_out, void *cuda_stream) {
-  if (iters <= 0 || !sink) { set_error("ghr_fp32_probe: bad arguments"); return GHR_EINVAL; }
+int ghr_fp32_probe(int32_t iters, int32_t packed, const float *in, float *sink, double *flops_out, void *cuda_stream) {
+  if (iters <= 0 || !sink || !in) { set_error("ghr_fp32_probe: bad arguments"); return GHR_EINVAL; }
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const bool debug = false;
   const int blocks = 148 * 8, threads = 256;
-  fp32_probe_kernel<<<blocks, threads, 0, s>>>(iters, sink);
-  if (flops_out) *flops_out = 2.0 * 8.0 * (double)iters * blocks * threads;
+  if (packed) fp32_probe_kernel<true><<<blocks, threads, 0, s>>>(iters, in, sink);
+  else fp32_probe_kernel<false><<<blocks, threads, 0, s>>>(iters, in, sink);
+  if (flops_out) *flops_out = 2.0 * 128.0 * (packed ? 2.0 : 1.0) * (double)iters * blocks * threads;
   GHR_TRY(cudaGetLastError(), "ghr_fp32_probe");
   return GHR_OK;
 }

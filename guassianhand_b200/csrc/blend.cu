@@ -1,20 +1,27 @@
 // Per-tile alpha blending, forward and backward.
 //
 // Forward replaces upstream renderCUDA<3> forward; backward replaces
-// renderCUDA<3> backward (K7, A.6).  One CTA per (view, tile), taken heaviest-first from the tile
-// schedule.  8 consumer warps (one thread per pixel, a warp covers an 8x4 pixel block) + 1 producer
-// warp.  The tile's instance list is a contiguous slab of 48-byte records (written by the chunk
-// sort / merge of binning.cu); the producer streams it into a ring of shared-memory stages with 1-D bulk async
-// copies (cp.async.bulk -> UBLKCP) completing on "full" mbarriers; consumer warps release a stage on
-// its "empty" mbarrier, so warps drift apart by up to kStages-1 stages instead of meeting at a CTA
-// barrier every round.  Inside a stage each warp first culls: an instance's precomputed 8-bit mask says
-// which 8x4 sub-blocks it can reach with alpha >= 1/255, a ballot compacts the survivors into a queue,
-// and only those are blended.  Backward: one (tile, 128-instance segment) work unit per two 4-warp CTAs,
-// restarted from the forward's checkpoints; per-instance partial gradients are parked in shared memory
-// three instances at a time, reduced across the warp with conflict-free 128-bit loads and leave the SM
-// as one RED.ADD per value per warp.
-#include <cstdlib>
-
+// renderCUDA<3> backward (K7, A.6).
+//
+// Thread = TWO pixels of one column, 4 rows apart; a warp covers an 8x8 pixel block, four warps a
+// 16x16 tile.  The two pixels share the instance's record loads, its queue entry and dx; everything
+// that differs per pixel is computed as a packed fp32 pair (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2,
+// IEEE-rn per half: the canonical bits are those of the scalar formulation).  The kernels are bound by
+// instruction issue, so the pair halves the issue slots per (pixel, instance).
+//
+// Forward: one CTA (4 warps) per (view, tile), taken heaviest-first from the tile schedule.  The tile's
+// instance list is a contiguous slab of 48-byte records (written by the chunk sort / merge of
+// binning.cu); it is streamed through a ring of shared-memory stages with 1-D bulk async copies
+// (cp.async.bulk -> UBLKCP) completing on "full" mbarriers.  There is no producer warp: the LAST warp to
+// release a stage refills it (one shared-memory atomic per warp and stage), so warps drift apart by up to
+// kStages-1 stages instead of meeting at a CTA barrier every round, and no warp slot or register budget
+// is spent on polling.  Inside a stage each warp first culls: an instance's precomputed 8-bit mask says
+// which 8x4 sub-blocks it can reach with alpha >= 1/255, a ballot compacts the survivors into a queue, and
+// only those are blended.
+// Backward: one (tile, 128-instance segment) work unit per CTA, restarted from the forward's checkpoints;
+// per-instance partial gradients (already summed over the thread's two pixels) are parked in shared
+// memory three instances at a time, reduced across the warp with conflict-free 128-bit loads and leave
+// the SM as one RED.ADD per value per warp.
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -23,12 +30,38 @@ namespace {
 
 constexpr int kStageN = 128;  // instances per stage (6 KB)
 constexpr int kStages = 4;
-constexpr int kConsumerWarps = 8;
-constexpr int kBlendThreads = (kConsumerWarps + 1) * 32;
+constexpr int kBlendWarps = 4;               // 8x8-pixel blocks of a tile
+constexpr int kBlendThreads = kBlendWarps * 32;
 constexpr float kAlphaMin = 1.0f / 255.0f;
-constexpr int kMaxIlpB = 2;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kIlpF = 4;         // instances per forward iteration (x 2 pixels = 8 independent alpha chains)
+constexpr int kIlpB = 2;         // instances per backward iteration
 constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
+#ifndef GHR_BWD_WARPS
+#define GHR_BWD_WARPS 4          // build-time A/B: 4 = one CTA per unit, 2 = two half-tile CTAs per unit
+#endif
+static_assert(kStageN == kSeg, "a forward stage is one backward segment");
+
+#ifdef GHR_TIMELINE
+// profiling variant only (libghr_timeline.so): {start ns, stop ns, smid, work} per CTA of the blend kernels
+constexpr uint32_t kTimelineCap = 1u << 17;
+__device__ ulonglong4 g_timeline[kTimelineCap];
+__device__ unsigned int g_timeline_n;
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void timeline_put(unsigned long long t0, uint32_t kind, uint32_t a, uint32_t b) {
+  uint32_t smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  const uint32_t i = atomicAdd(&g_timeline_n, 1u);
+  if (i < kTimelineCap)
+    g_timeline[i] = make_ulonglong4(t0, gtime_ns(), ((unsigned long long)kind << 32) | smid,
+                                    ((unsigned long long)a << 32) | b);
+}
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -44,6 +77,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
@@ -51,8 +87,8 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 // Blocking wait: try_wait with a suspend-time hint parks the warp in hardware; between retries the
-// warp sleeps `backoff_ns` (warps that only keep the ring turning -- all their pixels terminated --
-// pass a long backoff so their polling does not take issue slots from warps that still blend).
+// warp sleeps `backoff_ns` (warps whose pixels have all terminated only keep the ring turning and pass a
+// long backoff so their polling does not take issue slots from warps that still blend).
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t backoff_ns = 32u) {
   uint32_t ok;
   do {
@@ -72,14 +108,14 @@ struct __align__(128) StageBuf {
   float4 rec[kStages][kStageN * 3 + 3];   // + one all-zero record (index kStageN): queue padding, alpha = 0
   uint8_t msk[kStages][kMaskBytes];
   uint64_t full[kStages];
-  uint64_t empty[kStages];
+  uint32_t released[kStages];   // warps that have released the stage's current round
   uint32_t done_warps;
   uint32_t stop_round;
-  uint32_t tmax;          // max n_contrib of the tile (forward)
+  uint32_t tmax;                // max n_contrib of the tile
 };
 
-// Producer side of one stage: the contiguous record slab plus the 16-byte-aligned window of the
-// mask byte array that covers the same instances, both completing on the stage's full barrier.
+// One stage: the contiguous record slab plus the 16-byte-aligned window of the mask byte array that
+// covers the same instances, both completing on the stage's full barrier.
 __device__ __forceinline__ void stage_load(StageBuf &sb, int s, const float4 *records, const uint8_t *masks,
                                            size_t first, uint32_t cnt) {
   const size_t m0 = first & ~(size_t)15;
@@ -89,46 +125,64 @@ __device__ __forceinline__ void stage_load(StageBuf &sb, int s, const float4 *re
   bulk_g2s(&sb.msk[s][0], masks + m0, mbytes, &sb.full[s]);
 }
 
-__device__ __forceinline__ void stage_init(StageBuf &sb, int tid) {
-  if (tid == 0) {
-    for (int s = 0; s < kStages; s++) {
-      mbar_init(&sb.full[s], 1);
-      mbar_init(&sb.empty[s], kConsumerWarps);
-    }
-    sb.done_warps = 0;
-    sb.stop_round = 0xFFFFFFFFu;
-    sb.tmax = 0;
-    mbar_fence_init();
-  }
-  if (tid < 3 * kStages) sb.rec[tid / 3][kStageN * 3 + tid % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-}
-
 // exp(x) for x <= 0 as one FMUL + MUFU.EX2 (ex2.approx: <= 2 ulp; argument rounding adds <= 3.3e-7
 // relative at |x| <= 5.6, the largest exponent that can still pass alpha >= 1/255).  libdevice expf
 // costs 9 more issue slots per pair in kernels that are issue-bound.  Forward and backward use the
 // same function, so every alpha / skip decision of the backward replays the forward's exactly.
-__device__ __forceinline__ float exp_fast(float x) {
+__device__ __forceinline__ float ex2_fast(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// thread -> pixel inside the tile: warp w covers the 8x4 block (w&1, w>>1)
-__device__ __forceinline__ void pixel_of_thread(int tid, int &lx, int &ly) {
-  int w = tid >> 5, l = tid & 31;
-  lx = ((w & 1) << 3) + (l & 7);
-  ly = ((w >> 1) << 2) + (l >> 3);
+// thread -> its two pixels inside the tile: warp w covers the 8x8 block (w&1, w>>1); lane l the column
+// l&7 and the rows l>>3 and (l>>3) + 4.  slot(h) = w*64 + h*32 + l indexes the per-tile float4 arrays
+// (tilefinal, checkpoints): a warp's 32 slots of one half are contiguous (coalesced 512-byte accesses).
+__device__ __forceinline__ void pixels_of_thread(int warp, int lane, int &lx, int &ly0) {
+  lx = ((warp & 1) << 3) + (lane & 7);
+  ly0 = ((warp >> 1) << 3) + (lane >> 3);
+}
+// bits of the instance masks (bit = 2*(row/4) + col/8 of an 8x4 sub-block) that fall into warp w's block
+__device__ __forceinline__ uint32_t hitmask_of_warp(int warp) {
+  const uint32_t b0 = 4u * (uint32_t)(warp >> 1) + (uint32_t)(warp & 1);
+  return (1u << b0) | (1u << (b0 + 2u));
 }
 
-// Survivor queue of one warp for one stage: the indices (inside the stage, ascending) of the
-// instances whose sub-block mask (one byte per instance, written by gather_ranges) has this warp's
-// bit set.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the blend loop then
-// takes kIlp indices per iteration from one broadcast LDS instead of peeling bits off a mask.
-// Survivor i is q[kQPad + i]; kQPad entries pad both ends (front: index 0, back: `pad` -- the forward
-// passes kStageN, its all-zero record whose alpha is 0).  Returns the survivor count.
-__device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt, uint32_t limit, int warp, int lane,
-                                                uint8_t *q, uint32_t pad) {
+// alpha of one instance at the thread's two pixels, canonical order, packed:
+//   dx = x - px; dy = y - py; q = fma(A dx, dx, (C dy) dy); power = fma(-0.5, q, -(B dx) dy)
+//   alpha = min(0.99, opacity * exp(power)); skipped (0) if power > 0 or alpha < 1/255
+__device__ __forceinline__ void pair_alpha(const float4 a, const float4 bq, float pxf, f32x2 npy, float &dx,
+                                           f32x2 &dy, float &p0, float &p1, float &G0, float &G1, float &a0,
+                                           float &a1) {
+  dx = fsub(a.x, pxf);
+  dy = add2(bc2(a.y), npy);
+  const f32x2 v = mul2(mul2(bc2(bq.x), dy), dy);
+  const f32x2 qf = fma2(bc2(fmul(a.z, dx)), bc2(dx), v);
+  const f32x2 z = mul2(bc2(fmul(-a.w, dx)), dy);
+  const f32x2 power = fma2(bc2(-0.5f), qf, z);
+  upk2(power, p0, p1);
+#ifdef GHR_EXACT_EXP
+  G0 = expf(p0);
+  G1 = expf(p1);
+#else
+  float e0, e1;
+  upk2(mul2(power, bc2(kLog2e)), e0, e1);
+  G0 = ex2_fast(e0);
+  G1 = ex2_fast(e1);
+#endif
+  upk2(mul2(bc2(bq.y), pk2(G0, G1)), a0, a1);
+  a0 = fminf(0.99f, a0);
+  a1 = fminf(0.99f, a1);
+}
+
+// Survivor queue of one warp for one stage (forward): the 16-bit shared-memory ADDRESSES of the records
+// (the kernel's shared window is far below 64 KB) of the instances, ascending, whose sub-block mask hits
+// the warp's 8x8 block.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the
+// blend loop then takes kIlpF addresses per LDS.64, so an instance costs one extract and no address
+// arithmetic before its three record loads.  Survivor i is q[kQPad + i]; kQPad entries pad the end with
+// the address of the stage's all-zero record (alpha = 0).  Returns the survivor count.
+__device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_t cnt, uint32_t hitmask, int lane,
+                                                     uint16_t *q, uint32_t rec_base, uint32_t pad_addr) {
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t total = 0;
   __syncwarp();   // every lane has finished reading the previous stage's queue
@@ -136,34 +190,31 @@ __device__ __forceinline__ uint32_t build_queue(const uint8_t *msk, uint32_t cnt
   for (int w = 0; w < kStageN / 32; w++) {
     const uint32_t e = w * 32 + lane;
     bool hit = false;
-    if (e < cnt && e < limit) hit = (msk[e] >> warp) & 1u;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hit) q[kQPad + total + __popc(m & lt)] = (uint8_t)e;
-    total += __popc(m);
-  }
-  if (lane < kQPad) q[kQPad + total + lane] = (uint8_t)pad;
-  __syncwarp();
-  return total;
-}
-
-// Forward variant of the survivor queue: entries are the 16-bit shared-memory ADDRESSES of the
-// survivors' records (the kernel's shared window is far below 64 KB), eight of them per LDS.128, so an
-// instance costs one extract and no address arithmetic before its three record loads.
-__device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_t cnt, int warp, int lane, uint16_t *q,
-                                                     uint32_t rec_base, uint32_t pad_addr) {
-  const uint32_t lt = (1u << lane) - 1u;
-  uint32_t total = 0;
-  __syncwarp();   // every lane has finished reading the previous stage's queue
-#pragma unroll
-  for (int w = 0; w < kStageN / 32; w++) {
-    const uint32_t e = w * 32 + lane;
-    bool hit = false;
-    if (e < cnt) hit = (msk[e] >> warp) & 1u;
+    if (e < cnt) hit = (msk[e] & hitmask) != 0u;
     const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
     if (hit) q[kQPad + total + __popc(m & lt)] = (uint16_t)(rec_base + e * kRecBytes);
     total += __popc(m);
   }
   if (lane < kQPad) q[kQPad + total + lane] = (uint16_t)pad_addr;
+  __syncwarp();
+  return total;
+}
+// Backward variant: 8-bit indices inside the segment; `limit` = instances that precede the warp's last
+// contributor; padding = index kSeg, the all-zero record behind the segment.
+__device__ __forceinline__ uint32_t build_queue_idx(const uint8_t *msk, uint32_t cnt, uint32_t limit, uint32_t hitmask,
+                                                    int lane, uint8_t *q) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kSeg / 32; w++) {
+    const uint32_t e = w * 32 + lane;
+    bool hit = false;
+    if (e < cnt && e < limit) hit = (msk[e] & hitmask) != 0u;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (hit) q[kQPad + total + __popc(m & lt)] = (uint8_t)e;
+    total += __popc(m);
+  }
+  if (lane < kQPad) q[kQPad + total + lane] = (uint8_t)kSeg;
   __syncwarp();
   return total;
 }
@@ -173,32 +224,34 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-// kIlpF = instances blended per inner iteration (ILP): 4 or 8
-template <int kIlpF>
-__global__ void __launch_bounds__(kBlendThreads, kIlpF <= 4 ? 4 : 3)
+__global__ void __launch_bounds__(kBlendThreads, 6)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float4 *__restrict__ tilefinal, float4 *__restrict__ ckpt,
                      uint4 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
-                     float *__restrict__ out_mask, uint32_t bo_active, uint32_t bo_done, uint32_t bo_prod) {
+                     float *__restrict__ out_mask) {
   __shared__ StageBuf sb;
-  __shared__ __align__(16) uint16_t s_q[kConsumerWarps][kStageN + 2 * kQPad];
+  __shared__ __align__(16) uint16_t s_q[kBlendWarps][kStageN + 2 * kQPad];
   const uint32_t vt = order[blockIdx.x];
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int lx, ly0;
+  pixels_of_thread(warp, lane, lx, ly0);
+  const int px = (tile % gx) * kTile + lx, py0 = (tile / gx) * kTile + ly0, py1 = py0 + 4;
+  const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
+  const size_t N = (size_t)H * W;
+  const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px;
+  const float *bg = cam.bg + (size_t)cam.bg_stride * v;
 
   const uint2 range = ranges[vt];
   const uint32_t n = range.y - range.x;
   if (n == 0) {
     // empty tile (most of the frame): background only, no barriers, no staging
-    if (warp < kConsumerWarps) {
-      int lx, ly;
-      pixel_of_thread(tid, lx, ly);
-      const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
-      if (px < W && py < H) {
-        const size_t N = (size_t)H * W, pix = (size_t)py * W + px;
-        const float *bg = cam.bg + (size_t)cam.bg_stride * v;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      if (h ? in1 : in0) {
+        const size_t pix = h ? pix1 : pix0;
         final_T[(size_t)v * N + pix] = 1.0f;
         n_contrib[(size_t)v * N + pix] = 0u;
         float *o = out_color + (size_t)v * 3 * N + pix;
@@ -211,125 +264,158 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     return;
   }
   const uint32_t rounds = (n + kStageN - 1) / kStageN;
-  stage_init(sb, tid);
-
-  if (warp == kConsumerWarps) {
-    // ---------------- producer ----------------
-    if (lane == 0) {
-      for (uint32_t r = 0; r < rounds; r++) {
-        const int s = r % kStages;
-        if (r >= kStages) mbar_wait(&sb.empty[s], ((r / kStages) - 1) & 1, bo_prod);
-        if (*(volatile uint32_t *)&sb.done_warps == kConsumerWarps) {
-          // every pixel of the tile has terminated: complete the phase without data ("poison")
-          *(volatile uint32_t *)&sb.stop_round = r;
-          mbar_arrive(&sb.full[s]);
-          break;
-        }
-        const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
-        stage_load(sb, s, records, masks, (size_t)range.x + (size_t)r * kStageN, cnt);
-      }
+#ifdef GHR_TIMELINE
+  const unsigned long long tl0 = gtime_ns();
+#endif
+  if (tid == 0) {
+    for (int s = 0; s < kStages; s++) {
+      mbar_init(&sb.full[s], 1);
+      sb.released[s] = 0;
     }
-    return;
+    sb.done_warps = 0;
+    sb.stop_round = 0xFFFFFFFFu;
+    sb.tmax = 0;
+    mbar_fence_init();
+    for (uint32_t r = 0; r < rounds && r < (uint32_t)kStages; r++)
+      stage_load(sb, (int)r, records, masks, (size_t)range.x + (size_t)r * kStageN,
+                 min((uint32_t)kStageN, n - r * kStageN));
   }
+  if (tid >= 32 && tid < 32 + 3 * kStages)
+    sb.rec[(tid - 32) / 3][kStageN * 3 + (tid - 32) % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
 
-  // ---------------- consumers ----------------
-  int lx, ly;
-  pixel_of_thread(tid, lx, ly);
-  const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
-  const bool inside = px < W && py < H;
-  const size_t N = (size_t)H * W;
-  const float pxf = (float)px, pyf = (float)py;
+  const float pxf = (float)px;
+  const f32x2 npy = pk2(-(float)py0, -(float)py1);
+  const uint32_t hitmask = hitmask_of_warp(warp);
   uint16_t *q = &s_q[warp][0];
 
-  // Tw: transmittance while the pixel is live, 0 once it has terminated (or lies outside the image) --
-  // then test_T = 0 keeps `term` set and every later weight is 0; Tr: the last live value (the output)
-  float Tw = inside ? 1.0f : 0.f, Tr = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-  bool wdone = __all_sync(0xFFFFFFFFu, !inside);
+  // T > 0: live transmittance; T < 0: the pixel has terminated (or lies outside the image), |T| is the
+  // frozen output value -- then test_T < 0 keeps `term` set and every later weight is 0
+  float T0 = in0 ? 1.0f : -1.0f, T1 = in1 ? 1.0f : -1.0f;
+  f32x2 Cr = pk2(0.f, 0.f), Cg = Cr, Cb = Cr;
+  bool wdone = __all_sync(0xFFFFFFFFu, !in0 && !in1);
   if (wdone && lane == 0) atomicAdd(&sb.done_warps, 1u);
-  uint32_t last = 0;
+  uint32_t last0 = 0, last1 = 0;
   for (uint32_t r = 0; r < rounds; r++) {
     const int s = r % kStages;
-    // a consumer that waits here is ahead of the tile's slowest warp by the whole ring: it can sleep long
-    // between polls (its wake-up is not on the critical path), the producer polls `empty` tightly
-    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? bo_done : bo_active);
+    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 1024u : 256u);
     if (r >= *(volatile uint32_t *)&sb.stop_round) break;
     if (!wdone) {
       // running state at every kSeg-instance boundary: the backward restarts from it (one work unit per
       // segment).  A warp whose pixels have all terminated writes nothing: no later unit reads it.
-      if (r > 0 && (r * kStageN) % kSeg == 0)
-        ckpt[((size_t)(range.x / kSeg) + vt + (r * kStageN) / kSeg) * 256 + tid] = make_float4(Tr, C0, C1, C2);
+      if (r > 0) {
+        float c0r, c1r, c0g, c1g, c0b, c1b;
+        upk2(Cr, c0r, c1r);
+        upk2(Cg, c0g, c1g);
+        upk2(Cb, c0b, c1b);
+        float4 *ck = ckpt + ((size_t)(range.x / kSeg) + vt + r) * 256 + warp * 64 + lane;
+        ck[0] = make_float4(fabsf(T0), c0r, c0g, c0b);
+        ck[32] = make_float4(fabsf(T1), c1r, c1g, c1b);
+      }
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const uint32_t rec_base = smem_u32(&sb.rec[s][0]);
-      const uint32_t total = build_queue_addr(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, warp, lane, q, rec_base,
-                                              rec_base + kStageN * kRecBytes);
-      uint32_t lastq = 0;                                     // 1 + queue index of the last blended survivor
+      const uint32_t total = build_queue_addr(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, hitmask, lane, q,
+                                              rec_base, rec_base + kStageN * kRecBytes);
+      uint32_t lastq0 = 0, lastq1 = 0;                      // 1 + queue index of the last blended survivor
       for (uint32_t b = 0; b < total; b += kIlpF) {
-        // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so
-        // the long chains (LDS -> quadratic form -> exp) of several instances overlap; only the
-        // short T / colour update is serial (and branch-free: a rejected pair blends alpha = 0).
-        float al[kIlpF];
+        // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so the
+        // long chains (LDS -> quadratic form -> exp) of several instances overlap; only the short
+        // T / colour update is serial (and branch-free: a rejected pair blends alpha = 0).
+        f32x2 al[kIlpF];
         float4 col[kIlpF];
-        uint32_t packed[kIlpF / 2];
-        if constexpr (kIlpF == 8) {
-          const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
-          packed[0] = p4.x; packed[1] = p4.y; packed[2] = p4.z; packed[3] = p4.w;
-        } else {
-          const uint2 p2 = *reinterpret_cast<const uint2 *>(q + kQPad + b);
-          packed[0] = p2.x; packed[1] = p2.y;
-        }
+        const uint2 p2 = *reinterpret_cast<const uint2 *>(q + kQPad + b);
+        const uint32_t packed[2] = {p2.x, p2.y};
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
           const uint32_t addr = (k & 1) ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu;
           const float4 a = lds128(addr), bq = lds128(addr + 16);
           col[k] = lds128(addr + 32);
-          const float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-          const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
-          const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
-          const float alpha = fminf(0.99f, fmul(bq.y, exp_fast(power)));
-          al[k] = (power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;   // padding: opacity 0 -> alpha 0
+          float dx, p0, p1, G0, G1, a0, a1;
+          f32x2 dy;
+          pair_alpha(a, bq, pxf, npy, dx, dy, p0, p1, G0, G1, a0, a1);
+          al[k] = pk2((p0 <= 0.0f && a0 >= kAlphaMin) ? a0 : 0.f,      // padding: opacity 0 -> alpha 0
+                      (p1 <= 0.0f && a1 >= kAlphaMin) ? a1 : 0.f);
         }
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
-          const float test_T = fmul(Tw, fsub(1.f, al[k]));      // alpha == 0: test_T == Tw exactly
-          // a live Tw is >= 1e-4 (the stopping Gaussian is never applied), so a live pixel terminates only
-          // on alpha != 0; a terminated one (Tw == 0) stays terminated
-          const bool term = test_T < 0.0001f;
-          const float Tm = term ? 0.f : Tw;                     // the stopping Gaussian is not blended
-          C0 = ffma(fmul(col[k].x, al[k]), Tm, C0);             // upstream's order: (c * alpha) * T
-          C1 = ffma(fmul(col[k].y, al[k]), Tm, C1);
-          C2 = ffma(fmul(col[k].z, al[k]), Tm, C2);
-          Tw = term ? 0.f : test_T;
-          Tr = term ? Tr : test_T;
-          lastq = (!term && al[k] != 0.f) ? b + k + 1 : lastq;
+          float a0, a1, t0, t1;
+          upk2(al[k], a0, a1);
+          // test_T = T (1 - alpha); alpha == 0: test_T == T exactly.  A live T is >= 1e-4 (the stopping
+          // Gaussian is never applied), so a live pixel terminates only on alpha != 0; a terminated one
+          // (T < 0) stays terminated.
+          upk2(mul2(pk2(T0, T1), fma2(al[k], bc2(-1.0f), bc2(1.0f))), t0, t1);
+          const bool term0 = t0 < 0.0001f, term1 = t1 < 0.0001f;
+          const f32x2 Tm = pk2(term0 ? 0.f : T0, term1 ? 0.f : T1);   // the stopping Gaussian is not blended
+          Cr = fma2(mul2(bc2(col[k].x), al[k]), Tm, Cr);               // upstream's order: (c * alpha) * T
+          Cg = fma2(mul2(bc2(col[k].y), al[k]), Tm, Cg);
+          Cb = fma2(mul2(bc2(col[k].z), al[k]), Tm, Cb);
+          T0 = term0 ? -fabsf(T0) : t0;
+          T1 = term1 ? -fabsf(T1) : t1;
+          lastq0 = (!term0 && a0 != 0.f) ? b + k + 1 : lastq0;
+          lastq1 = (!term1 && a1 != 0.f) ? b + k + 1 : lastq1;
         }
-        if (__all_sync(0xFFFFFFFFu, Tw == 0.f)) {
+        if (__all_sync(0xFFFFFFFFu, T0 < 0.f && T1 < 0.f)) {
           wdone = true;
           if (lane == 0) atomicAdd(&sb.done_warps, 1u);
           break;
         }
       }
-      if (lastq) last = r * kStageN + ((uint32_t)q[kQPad + lastq - 1] - rec_base) / kRecBytes + 1;
+      if (lastq0) last0 = r * kStageN + ((uint32_t)q[kQPad + lastq0 - 1] - rec_base) / kRecBytes + 1;
+      if (lastq1) last1 = r * kStageN + ((uint32_t)q[kQPad + lastq1 - 1] - rec_base) / kRecBytes + 1;
     }
+    // release the stage; the last warp to do so refills it with round r + kStages
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sb.empty[s]);
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&sb.released[s], 1u) == (uint32_t)kBlendWarps - 1u) {
+        *(volatile uint32_t *)&sb.released[s] = 0u;
+        const uint32_t nr = r + kStages;
+        if (nr < rounds) {
+          if (*(volatile uint32_t *)&sb.done_warps == (uint32_t)kBlendWarps) {
+            // every pixel of the tile has terminated: complete the phase without data ("poison")
+            atomicMin(&sb.stop_round, nr);
+            __threadfence_block();
+            mbar_arrive(&sb.full[s]);
+          } else {
+            fence_proxy_async();
+            stage_load(sb, s, records, masks, (size_t)range.x + (size_t)nr * kStageN,
+                       min((uint32_t)kStageN, n - nr * kStageN));
+          }
+        }
+      }
+    }
   }
 
-  if (inside) {
-    const float *bg = cam.bg + (size_t)cam.bg_stride * v;
-    size_t pix = (size_t)py * W + px;
-    final_T[(size_t)v * N + pix] = Tr;
-    n_contrib[(size_t)v * N + pix] = last;
-    float *o = out_color + (size_t)v * 3 * N + pix;
-    o[0] = ffma(Tr, bg[0], C0);
-    o[N] = ffma(Tr, bg[1], C1);
-    o[2 * N] = ffma(Tr, bg[2], C2);
-    if (out_mask) out_mask[(size_t)v * N + pix] = 1.0f - Tr;   // = sum_j alpha_j T_j
+  float c0r, c1r, c0g, c1g, c0b, c1b;
+  upk2(Cr, c0r, c1r);
+  upk2(Cg, c0g, c1g);
+  upk2(Cb, c0b, c1b);
+  const float Tr0 = fabsf(T0), Tr1 = fabsf(T1);
+  if (in0) {
+    final_T[(size_t)v * N + pix0] = Tr0;
+    n_contrib[(size_t)v * N + pix0] = last0;
+    float *o = out_color + (size_t)v * 3 * N + pix0;
+    o[0] = ffma(Tr0, bg[0], c0r);
+    o[N] = ffma(Tr0, bg[1], c0g);
+    o[2 * N] = ffma(Tr0, bg[2], c0b);
+    if (out_mask) out_mask[(size_t)v * N + pix0] = 1.0f - Tr0;   // = sum_j alpha_j T_j
   }
-  tilefinal[(size_t)vt * 256 + tid] = make_float4(C0, C1, C2, Tr);
+  if (in1) {
+    final_T[(size_t)v * N + pix1] = Tr1;
+    n_contrib[(size_t)v * N + pix1] = last1;
+    float *o = out_color + (size_t)v * 3 * N + pix1;
+    o[0] = ffma(Tr1, bg[0], c1r);
+    o[N] = ffma(Tr1, bg[1], c1g);
+    o[2 * N] = ffma(Tr1, bg[2], c1b);
+    if (out_mask) out_mask[(size_t)v * N + pix1] = 1.0f - Tr1;
+  }
+  float4 *tf = tilefinal + (size_t)vt * 256 + warp * 64 + lane;
+  tf[0] = make_float4(c0r, c0g, c0b, Tr0);
+  tf[32] = make_float4(c1r, c1g, c1b, Tr1);
   // backward work units of this tile: one per kSeg instances up to the tile's last contributor
-  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
+  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, max(last0, last1));
   if (lane == 0 && wmax) atomicMax(&sb.tmax, wmax);
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory");
+  __syncthreads();
   if (warp == 0) {
     const uint32_t tmax = sb.tmax, nseg = (tmax + kSeg - 1) / kSeg;
     if (nseg) {
@@ -342,40 +428,17 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       for (uint32_t i = lane; i < nseg; i += 32) units[base + i] = make_uint4(vt, i, range.x, tmax);
     }
   }
+#ifdef GHR_TIMELINE
+  if (tid == 0) timeline_put(tl0, 0u, vt, n);
+#endif
 }
 
-// Warp reduction of 9 values per lane through shared memory: lane L stores its 9 partials as row L
-// of a 32x9 tile (stride 9 is odd: conflict-free), then lane (g,c) = (L/9, L%9), L < 27, sums column
-// c over 12 (8 for g=2) rows and the three row groups are combined with two shuffles.  36 issue slots
-// per instance instead of 62 for a register reduce-scatter butterfly (16 SHFL + 16 FADD + 30 FSEL) or
-// 90 for five plain xor steps.  On return lanes 0..8 hold the warp totals of values 0..8.
-__device__ __forceinline__ void warp_store9(float *buf, const float (&v)[9], int lane) {
-#pragma unroll
-  for (int t = 0; t < 9; t++) buf[lane * 9 + t] = v[t];
-}
-__device__ __forceinline__ float warp_colsum9(const float *buf, int lane) {
-  const int g = lane / 9, c = lane - 9 * g;
-  float sum = 0.f;
-  if (lane < 27) {
-    const float *col = buf + (g * 12) * 9 + c;
-#pragma unroll
-    for (int i = 0; i < 8; i++) sum += col[i * 9];
-    if (g < 2) {
-#pragma unroll
-      for (int i = 8; i < 12; i++) sum += col[i * 9];
-    }
-  }
-  const float s1 = __shfl_down_sync(0xFFFFFFFFu, sum, 9);
-  const float s2 = __shfl_down_sync(0xFFFFFFFFu, sum, 18);
-  return sum + s1 + s2;
-}
-
-// Ring reduction (kRing): instead of reducing every instance on its own, a warp parks the 9 partials
-// of up to kRingSlots instances as rows of 32 floats (row stride 36 floats: lane l writes column l,
+// Ring reduction: instead of reducing every instance on its own, a warp parks the 9 partials of up to
+// kRingSlots instances as rows of 32 floats (row stride 36 floats: lane l writes column l,
 // conflict-free) and reduces the slots together: the 27 rows are cut into 54 half-rows, lane l sums
 // half-row l (then 32 + l) with four LDS.128 + 15 FADD, one xor-shuffle joins the halves, and the even
 // lanes send the totals as REDs -- two rounds for three instances (~16 issue slots per instance
-// instead of ~40 for the per-instance column sum).  Eight consecutive half-rows start in eight
+// instead of ~40 for a per-instance column sum).  Eight consecutive half-rows start in eight
 // different 4-bank groups, so the 128-bit loads are conflict-free as well.
 constexpr int kRingSlots = 3;
 constexpr int kRowStride = 36;
@@ -411,45 +474,37 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
 // upstream's  dL/dalpha_j = T_j (c_j - A_j).dL/dpix - T_final/(1-alpha_j) bg.dL/dpix  (A_j = suffix colour
 // normalised by T_{j+1}) becomes  T_j (c_j.dL/dpix) - (D_j + T_final bg.dL/dpix) / (1-alpha_j):  two scalar
 // recurrences (T, D) instead of the back-to-front vector one, and T replays the forward's products exactly.
-// kW warps per CTA: 8 (the whole tile) or 4 (half a tile: two CTAs per unit, each staging the slab).
-// Warps of a CTA finish at very different times (a sub-block outside the hands has few survivors) and the
-// CTA keeps its registers and shared memory until the slowest one is done; smaller CTAs give those
-// resources back sooner.
-template <int kIlpB, bool kRing, int kMinCtas, int kW>
-__global__ void __launch_bounds__(kW * 32, kMinCtas)
+// The kernel tracks Dn = -D and TbN = -T_final bg.dL/dpix so that every update is a plain packed fma.
+// kW warps per CTA: 4 (the whole tile) or 2 (half a tile: two CTAs per unit, each staging the slab).
+template <int kW>
+__global__ void __launch_bounds__(kW * 32, kW == 4 ? 6 : 12)
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const GhrStatus *__restrict__ status,
                       const uint4 *__restrict__ units, const float4 *__restrict__ records,
                       const uint8_t *__restrict__ masks, const float4 *__restrict__ tilefinal,
                       const float4 *__restrict__ ckpt, const uint32_t *__restrict__ n_contrib,
                       const float *__restrict__ dL_dout, const float *__restrict__ dL_dmask,
-                      float *__restrict__ acc, int direct_max, int reverse) {
-  constexpr int kRedBufs = kIlpB < kMaxIlpB ? kIlpB : kMaxIlpB;
-  __shared__ __align__(128) float4 s_rec[kSeg * 3];
+                      float *__restrict__ acc) {
+  __shared__ __align__(128) float4 s_rec[kSeg * 3 + 3];   // + the all-zero padding record (index kSeg)
   __shared__ __align__(16) uint8_t s_msk[kSeg + 16];
   __shared__ __align__(8) uint64_t s_bar;
-  __shared__ __align__(16) float s_red[kW][kRing ? kRingSlots * kSlotFloats : kRedBufs * 32 * 9];
+  __shared__ __align__(16) float s_red[kW][kRingSlots * kSlotFloats];
   __shared__ uint32_t s_ids[kW][4];
-  __shared__ __align__(16) uint8_t s_q[kW][kStageN + 2 * kQPad];
-  constexpr uint32_t kParts = kConsumerWarps / kW;       // CTAs per unit
+  __shared__ __align__(16) uint8_t s_q[kW][kSeg + 2 * kQPad];
+  constexpr uint32_t kParts = kBlendWarps / kW;       // CTAs per unit
   const uint32_t bid = blockIdx.x / kParts, part = blockIdx.x % kParts;
   // The unit record {view*T + tile, segment, start of the tile's slab, instances up to the tile's last
   // contributor} carries everything the copy needs, and it is read together with the unit count (the
   // list is allocated to its upper bound): one memory round trip between CTA start and the bulk copy.
-  // `reverse`: the forward appends a tile's units when the tile completes, so the heaviest tiles sit at
-  // the end of the list; walking it backwards starts their (long, dense) units first and leaves the
-  // short ones to fill the tail of the launch.
+  // The forward appends a tile's units when the tile completes, so the heaviest tiles sit at the end of
+  // the list; walking it backwards starts their (long, dense) units first and leaves the short ones to
+  // fill the tail of the launch.
   const uint32_t n_units = (uint32_t)status->reserved[1];
-  uint32_t uidx = bid;
-  if (reverse) {
-    if (bid >= n_units) return;
-    uidx = n_units - 1u - bid;
-  }
-  const uint4 unit = units[uidx];
   if (bid >= n_units) return;
+  const uint4 unit = units[n_units - 1u - bid];
   const uint32_t vt = unit.x, first = unit.y * kSeg;      // first = position of the segment in the tile list
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int lane = threadIdx.x & 31, wloc = threadIdx.x >> 5;      // warp inside the CTA
-  const int warp = (int)part * kW + wloc, tid = warp * 32 + lane;   // warp / thread inside the tile
+  const int warp = (int)part * kW + wloc;                           // warp inside the tile
   uint8_t *q = &s_q[wloc][0];
   const uint32_t cnt = min((uint32_t)kSeg, unit.w - first);   // instances past the last contributor never matter
   const size_t g0 = (size_t)unit.z + first;
@@ -463,188 +518,190 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
     bulk_g2s(s_rec, records + 3 * g0, cnt * kRecBytes, &s_bar);
     bulk_g2s(s_msk, masks + m0, mbytes, &s_bar);
   }
-  if (lane < kQPad) q[lane] = 0;
+  if (threadIdx.x >= 32 && threadIdx.x < 35) s_rec[kSeg * 3 + threadIdx.x - 32] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // per-pixel state while the segment is in flight (all loads independent of each other)
-  int lx, ly;
-  pixel_of_thread(tid, lx, ly);
-  const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
-  const bool inside = px < W && py < H;
+  int lx, ly0;
+  pixels_of_thread(warp, lane, lx, ly0);
+  const int px = (tile % gx) * kTile + lx, py0 = (tile / gx) * kTile + ly0, py1 = py0 + 4;
+  const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
   const size_t N = (size_t)H * W;
-  const float pxf = (float)px, pyf = (float)py;
-  float dLp0 = 0.f, dLp1 = 0.f, dLp2 = 0.f, dLm = 0.f;
-  uint32_t last = 0;
-  const float4 fin = tilefinal[(size_t)vt * 256 + tid];
-  float4 c = make_float4(1.f, 0.f, 0.f, 0.f);
+  const float pxf = (float)px;
+  const f32x2 npy = pk2(-(float)py0, -(float)py1);
+  const size_t slot0 = (size_t)warp * 64 + lane;
+  const float4 fin0 = tilefinal[(size_t)vt * 256 + slot0], fin1 = tilefinal[(size_t)vt * 256 + slot0 + 32];
+  float4 c0 = make_float4(1.f, 0.f, 0.f, 0.f), c1 = c0;
   // (a checkpoint no later unit needs was never written: whatever is read there is not used)
-  if (first) c = ckpt[((size_t)(unit.z / kSeg) + vt + unit.y) * 256 + tid];
-  if (inside) {
-    const size_t pix = (size_t)py * W + px;
-    last = n_contrib[(size_t)v * N + pix];
-    const float *g = dL_dout + (size_t)v * 3 * N + pix;
-    dLp0 = g[0];
-    dLp1 = g[N];
-    dLp2 = g[2 * N];
-    if (dL_dmask) dLm = dL_dmask[(size_t)v * N + pix];
+  if (first) {
+    const float4 *ck = ckpt + ((size_t)(unit.z / kSeg) + vt + unit.y) * 256 + slot0;
+    c0 = ck[0];
+    c1 = ck[32];
   }
-  float Tr = 0.f, Drem = 0.f, Tb = 0.f;
-  if (last > first) {
-    Tr = c.x;
-    Drem = (fin.x - c.y) * dLp0 + (fin.y - c.z) * dLp1 + (fin.z - c.w) * dLp2;
-    const float *bg = cam.bg + (size_t)cam.bg_stride * v;
+  float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f}, dm0 = 0.f, dm1 = 0.f;
+  uint32_t last0 = 0, last1 = 0;
+  if (in0) {
+    const size_t pix = (size_t)py0 * W + px;
+    last0 = n_contrib[(size_t)v * N + pix];
+    const float *g = dL_dout + (size_t)v * 3 * N + pix;
+    d0[0] = g[0]; d0[1] = g[N]; d0[2] = g[2 * N];
+    if (dL_dmask) dm0 = dL_dmask[(size_t)v * N + pix];
+  }
+  if (in1) {
+    const size_t pix = (size_t)py1 * W + px;
+    last1 = n_contrib[(size_t)v * N + pix];
+    const float *g = dL_dout + (size_t)v * 3 * N + pix;
+    d1[0] = g[0]; d1[1] = g[N]; d1[2] = g[2 * N];
+    if (dL_dmask) dm1 = dL_dmask[(size_t)v * N + pix];
+  }
+  const float *bg = cam.bg + (size_t)cam.bg_stride * v;
+  float tr0 = 0.f, tr1 = 0.f, dn0 = 0.f, dn1 = 0.f, tb0 = 0.f, tb1 = 0.f;
+  if (last0 > first) {
+    tr0 = c0.x;
+    dn0 = -((fin0.x - c0.y) * d0[0] + (fin0.y - c0.z) * d0[1] + (fin0.z - c0.w) * d0[2]);
     // coverage output m = 1 - T_final: dm/dalpha_j = +T_final/(1-alpha_j), the background term with
     // the opposite sign, so its gradient folds into the same product
-    Tb = fin.w * (bg[0] * dLp0 + bg[1] * dLp1 + bg[2] * dLp2 - dLm);
+    tb0 = -(fin0.w * (bg[0] * d0[0] + bg[1] * d0[1] + bg[2] * d0[2] - dm0));
   }
-  const bool owner = lane < 9;      // lanes 0..8 own the warp totals of the 9 accumulated values
+  if (last1 > first) {
+    tr1 = c1.x;
+    dn1 = -((fin1.x - c1.y) * d1[0] + (fin1.y - c1.z) * d1[1] + (fin1.z - c1.w) * d1[2]);
+    tb1 = -(fin1.w * (bg[0] * d1[0] + bg[1] * d1[1] + bg[2] * d1[2] - dm1));
+  }
+  f32x2 Tr = pk2(tr0, tr1), Dn = pk2(dn0, dn1);
+  const f32x2 TbN = pk2(tb0, tb1);
+  const f32x2 dLr = pk2(d0[0], d1[0]), dLg = pk2(d0[1], d1[1]), dLb = pk2(d0[2], d1[2]);
   float *accb = acc + (size_t)v * P * kAccStride;
-  const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, last);
+  const uint32_t wlast = __reduce_max_sync(0xFFFFFFFFu, max(last0, last1));
   __syncthreads();                  // barrier initialised before anyone polls it
   if (wlast <= first) return;
   mbar_wait(&s_bar, 0);
   float *ring = &s_red[wloc][0];
   uint32_t *ids = &s_ids[wloc][0];
   uint32_t pend = 0;                // instances parked in the ring (warp-uniform)
-  const float4 *s_rec_cur = s_rec;
-  const uint8_t *s_msk_cur = s_msk;
-  const uint32_t g0lo = (uint32_t)g0 & 15u;
 
-  for (uint32_t sub = 0; sub * kStageN < cnt; sub++) {
-    const uint32_t pos0 = first + sub * kStageN;
-    if (pos0 >= wlast) break;
-    const uint32_t scnt = min((uint32_t)kStageN, cnt - sub * kStageN);
-    const float4 *rec = s_rec_cur + 3 * sub * kStageN;
-    // survivors of this warp's sub-block among the instances that precede the warp's last contributor
-    const uint32_t total = build_queue(&s_msk_cur[g0lo + sub * kStageN], scnt, wlast - pos0, warp, lane, q, 0u);
-    for (uint32_t b = 0; b < total; b += kIlpB) {
-      // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
-      float al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dxk[kIlpB], dyk[kIlpB], cdk[kIlpB];
-      uint32_t idk[kIlpB];
+  // survivors of this warp's block among the instances that precede the warp's last contributor
+  const uint32_t total = build_queue_idx(&s_msk[(uint32_t)g0 & 15u], cnt, wlast - first, hitmask_of_warp(warp), lane, q);
+  for (uint32_t b = 0; b < total; b += kIlpB) {
+    // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
+    f32x2 al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dyk[kIlpB], cdk[kIlpB];
+    float dxk[kIlpB];
+    uint32_t idk[kIlpB];
 #pragma unroll
-      for (int k = 0; k < kIlpB; k++) {
-        const uint32_t jj = q[kQPad + b + k];                // tail pad (index 0) when b + k >= total
-        const float4 a = rec[3 * jj], bq = rec[3 * jj + 1], col = rec[3 * jj + 2];
-        const float dx = fsub(a.x, pxf), dy = fsub(a.y, pyf);
-        const float qf = ffma(fmul(a.z, dx), dx, fmul(fmul(bq.x, dy), dy));
-        const float power = ffma(-0.5f, qf, -fmul(fmul(a.w, dx), dy));
-        const float G = exp_fast(power);
-        const float alpha = fminf(0.99f, fmul(bq.y, G));
-        const bool c = b + k < total && pos0 + jj < last && power <= 0.0f && alpha >= kAlphaMin;
-        al[k] = c ? alpha : 0.f;
-        Gk[k] = c ? G : 0.f;
-        omk[k] = fsub(1.f, al[k]);
-        rck[k] = rcp_fast(omk[k]);
-        dxk[k] = dx;
-        dyk[k] = dy;
-        cdk[k] = col.x * dLp0 + col.y * dLp1 + col.z * dLp2;
-        idk[k] = __float_as_uint(col.w);
-      }
-      // phase 2 (serial, short, branch-free: a rejected pair has alpha = G = 0 and adds zeros)
-      float vals[kIlpB][9];
-      bool contrib[kIlpB];
+    for (int k = 0; k < kIlpB; k++) {
+      const uint32_t jj = q[kQPad + b + k];                // tail pad: the all-zero record (alpha = 0)
+      const float4 a = s_rec[3 * jj], bq = s_rec[3 * jj + 1], col = s_rec[3 * jj + 2];
+      float p0, p1, G0, G1, a0, a1;
+      pair_alpha(a, bq, pxf, npy, dxk[k], dyk[k], p0, p1, G0, G1, a0, a1);
+      const uint32_t pos = first + jj;
+      const bool ok0 = pos < last0 && p0 <= 0.0f && a0 >= kAlphaMin;
+      const bool ok1 = pos < last1 && p1 <= 0.0f && a1 >= kAlphaMin;
+      al[k] = pk2(ok0 ? a0 : 0.f, ok1 ? a1 : 0.f);
+      Gk[k] = pk2(ok0 ? G0 : 0.f, ok1 ? G1 : 0.f);
+      omk[k] = fma2(al[k], bc2(-1.0f), bc2(1.0f));
+      float o0, o1;
+      upk2(omk[k], o0, o1);
+      rck[k] = pk2(rcp_fast(o0), rcp_fast(o1));
+      cdk[k] = fma2(bc2(col.z), dLb, fma2(bc2(col.y), dLg, mul2(bc2(col.x), dLr)));
+      idk[k] = __float_as_uint(col.w);
+    }
+    // phase 2 (serial, short, branch-free: a rejected pair has alpha = G = 0 and adds zeros), then the
+    // thread's own two pixels are summed: per instance 9 values per thread
+    float vals[kIlpB][9];
+    bool contrib[kIlpB];
 #pragma unroll
-      for (int k = 0; k < kIlpB; k++) {
-        contrib[k] = al[k] != 0.f;
-        const float wgt = al[k] * Tr;
-        Drem = fmaf(-cdk[k], wgt, Drem);
-        const float dL_dalpha = fmaf(Tr, cdk[k], -(Drem + Tb) * rck[k]);
-        Tr = fmul(Tr, omk[k]);                                 // the forward's own product
-        const float wG = Gk[k] * dL_dalpha;
-        const float m10 = wG * dxk[k], m01 = wG * dyk[k];
-        vals[k][0] = wgt * dLp0; vals[k][1] = wgt * dLp1; vals[k][2] = wgt * dLp2;
-        vals[k][3] = wG; vals[k][4] = m10; vals[k][5] = m01;
-        vals[k][6] = m10 * dxk[k]; vals[k][7] = m10 * dyk[k]; vals[k][8] = m01 * dyk[k];
-      }
-      // phase 3: slots with few contributing lanes send their partials straight to L2 (9 REDs for the
-      // warp); the others are reduced through shared memory first and leave as one RED per value
-      if constexpr (kRing) {
+    for (int k = 0; k < kIlpB; k++) {
+      float a0, a1;
+      upk2(al[k], a0, a1);
+      contrib[k] = a0 != 0.f || a1 != 0.f;
+      const f32x2 wgt = mul2(al[k], Tr);
+      Dn = fma2(cdk[k], wgt, Dn);
+      const f32x2 dL_dalpha = fma2(Tr, cdk[k], mul2(add2(Dn, TbN), rck[k]));
+      Tr = mul2(Tr, omk[k]);                                 // the forward's own product
+      const f32x2 wG = mul2(Gk[k], dL_dalpha);
+      const f32x2 t01 = mul2(wG, dyk[k]), t02 = mul2(t01, dyk[k]);
+      const f32x2 cr = mul2(wgt, dLr), cg = mul2(wgt, dLg), cb = mul2(wgt, dLb);
+      const float wGs = lo2(wG) + hi2(wG), m01 = lo2(t01) + hi2(t01), m10 = wGs * dxk[k];
+      vals[k][0] = lo2(cr) + hi2(cr);
+      vals[k][1] = lo2(cg) + hi2(cg);
+      vals[k][2] = lo2(cb) + hi2(cb);
+      vals[k][3] = wGs;
+      vals[k][4] = m10;
+      vals[k][5] = m01;
+      vals[k][6] = m10 * dxk[k];
+      vals[k][7] = m01 * dxk[k];
+      vals[k][8] = lo2(t02) + hi2(t02);
+    }
+    // phase 3: slots with few contributing lanes send their partials straight to L2 (9 REDs per lane);
+    // the others are reduced through shared memory first and leave as one RED per value
 #pragma unroll
-        for (int k = 0; k < kIlpB; k++) {
-          const uint32_t cm = __ballot_sync(0xFFFFFFFFu, contrib[k]);
-          if (cm == 0u) continue;
-          if (__popc(cm) <= direct_max) {
-            if (contrib[k]) {
-              float *dst = accb + (size_t)idk[k] * kAccStride;
+    for (int k = 0; k < kIlpB; k++) {
+      const uint32_t cm = __ballot_sync(0xFFFFFFFFu, contrib[k]);
+      if (cm == 0u) continue;
+      if (__popc(cm) <= kDirectMax) {
+        if (contrib[k]) {
+          float *dst = accb + (size_t)idk[k] * kAccStride;
 #pragma unroll
-              for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
-            }
-          } else {
-            float *row = ring + pend * kSlotFloats + lane;
-#pragma unroll
-            for (int t = 0; t < 9; t++) row[t * kRowStride] = vals[k][t];
-            if (lane == 0) ids[pend] = idk[k];
-            if (++pend == kRingSlots) {
-              __syncwarp();
-              ring_flush(ring, ids, kRingSlots, accb, lane);
-              __syncwarp();
-              pend = 0;
-            }
-          }
+          for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
         }
       } else {
+        float *row = ring + pend * kSlotFloats + lane;
 #pragma unroll
-        for (int k0 = 0; k0 < kIlpB; k0 += kRedBufs) {
-          int mode[kRedBufs];     // 0 nothing, 1 direct, 2 reduce
-#pragma unroll
-          for (int qi = 0; qi < kRedBufs; qi++) {
-            const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-            const uint32_t cm = k0 + qi < kIlpB ? __ballot_sync(0xFFFFFFFFu, contrib[k]) : 0u;
-            mode[qi] = cm == 0u ? 0 : (__popc(cm) <= direct_max ? 1 : 2);
-            if (mode[qi] == 2) warp_store9(&s_red[wloc][qi * 32 * 9], vals[k], lane);
-            if (mode[qi] == 1 && contrib[k]) {
-              float *dst = accb + (size_t)idk[k] * kAccStride;
-#pragma unroll
-              for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
-            }
-          }
+        for (int t = 0; t < 9; t++) row[t * kRowStride] = vals[k][t];
+        if (lane == 0) ids[pend] = idk[k];
+        if (++pend == kRingSlots) {
           __syncwarp();
-#pragma unroll
-          for (int qi = 0; qi < kRedBufs; qi++) {
-            const int k = k0 + qi < kIlpB ? k0 + qi : 0;
-            if (mode[qi] != 2) continue;
-            float tot = warp_colsum9(&s_red[wloc][qi * 32 * 9], lane);
-            if (owner) atomicAdd(accb + (size_t)idk[k] * kAccStride + lane, tot);
-          }
+          ring_flush(ring, ids, kRingSlots, accb, lane);
           __syncwarp();
+          pend = 0;
         }
       }
     }
   }
-  if constexpr (kRing) {
-    if (pend) {
-      __syncwarp();
-      ring_flush(ring, ids, pend, accb, lane);
-    }
+  if (pend) {
+    __syncwarp();
+    ring_flush(ring, ids, pend, accb, lane);
   }
 }
 
-int env_int(const char *name, int dflt) {
-  const char *e = getenv(name);
-  return e ? atoi(e) : dflt;
+// shared-memory carveout preference, set once per device and kernel
+template <typename K>
+void prefer_shared(K kern) {
+  static bool done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || done[dev]) return;
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  done[dev] = true;
 }
 
 }  // namespace
 
+#ifdef GHR_TIMELINE
+extern "C" int ghr_debug_timeline(unsigned long long *host_out, unsigned int cap, unsigned int *count) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_timeline_n, sizeof(n));
+  if (n > kTimelineCap) n = kTimelineCap;
+  if (n > cap) n = cap;
+  if (n) cudaMemcpyFromSymbol(host_out, g_timeline, (size_t)n * sizeof(ulonglong4));
+  const unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_timeline_n, &zero, sizeof(zero));
+  *count = n;
+  return 0;
+}
+#endif
+
 cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Cameras &cam, char *state,
                                  float *out_color, float *out_mask, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
-  dim3 grid(L.T * d.V), block(kBlendThreads);
-  static const int ilp = env_int("GHR_ILPF", 8);
-  static const int bo_active = env_int("GHR_BO_ACTIVE", 256), bo_done = env_int("GHR_BO_DONE", 1024);
-  static const int bo_prod = env_int("GHR_BO_PROD", 256);
-  auto launch = [&](auto kern) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order),
-                                (const uint2 *)(state + L.pub.off_ranges),
-                                (const float4 *)(state + L.pub.off_records),
-                                (const uint8_t *)(state + L.pub.off_masks), (float *)(state + L.pub.off_final_T),
-                                (uint32_t *)(state + L.pub.off_ncontrib), (uint32_t *)(state + L.pub.off_tilemax),
-                                (float4 *)(state + L.pub.off_tilefinal), (float4 *)(state + L.pub.off_ckpt),
-                                (uint4 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
-                                out_color, out_mask, (uint32_t)bo_active, (uint32_t)bo_done, (uint32_t)bo_prod);
-  };
-  if (ilp <= 4) launch(blend_forward_kernel<4>);
-  else launch(blend_forward_kernel<8>);
+  prefer_shared(blend_forward_kernel);
+  blend_forward_kernel<<<L.T * d.V, kBlendThreads, 0, s>>>(
+      d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order), (const uint2 *)(state + L.pub.off_ranges),
+      (const float4 *)(state + L.pub.off_records), (const uint8_t *)(state + L.pub.off_masks),
+      (float *)(state + L.pub.off_final_T), (uint32_t *)(state + L.pub.off_ncontrib),
+      (uint32_t *)(state + L.pub.off_tilemax), (float4 *)(state + L.pub.off_tilefinal),
+      (float4 *)(state + L.pub.off_ckpt), (uint4 *)(state + L.pub.off_units), (GhrStatus *)(state + L.pub.off_status),
+      out_color, out_mask);
   return cudaGetLastError();
 }
 
@@ -653,34 +710,15 @@ cudaError_t launch_blend_backward(const GhrDims &d, const Layout &L, const Camer
   if (L.T == 0 || d.V == 0 || d.R_cap <= 0) return cudaSuccess;
   // upper bound of the unit count (the forward wrote the exact one to GhrStatus.reserved[1]); surplus
   // CTAs exit on their first instructions
-  static const int ilp = env_int("GHR_ILPB", 2);
-  static const int direct = env_int("GHR_DIRECT", kDirectMax);
-  static const int ring = env_int("GHR_RING", 1);
-  static const int reverse = env_int("GHR_BWD_REV", 1);
-  static const int warps = env_int("GHR_BWD_WARPS", 4);
-  auto launch = [&](auto kern, int kw) {
-    dim3 grid((unsigned)((L.n_slots - 1) * (kConsumerWarps / kw))), block(kw * 32);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    kern<<<grid, block, 0, s>>>(d.H, d.W, L.gx, L.T, d.P, cam, (const GhrStatus *)(state + L.pub.off_status),
-                                (const uint4 *)(state + L.pub.off_units),
-                                (const float4 *)(state + L.pub.off_records),
-                                (const uint8_t *)(state + L.pub.off_masks),
-                                (const float4 *)(state + L.pub.off_tilefinal),
-                                (const float4 *)(state + L.pub.off_ckpt),
-                                (const uint32_t *)(state + L.pub.off_ncontrib), dL_dout, dL_dmask, acc, direct,
-                                reverse);
-  };
-  if (warps <= 4) {
-    if (!ring) launch(blend_backward_kernel<2, false, 8, 4>, 4);
-    else launch(blend_backward_kernel<2, true, 8, 4>, 4);
-  } else if (ring) {
-    if (ilp <= 2) launch(blend_backward_kernel<2, true, 4, 8>, 8);
-    else launch(blend_backward_kernel<3, true, 4, 8>, 8);
-  } else {
-    if (ilp <= 1) launch(blend_backward_kernel<1, false, 4, 8>, 8);
-    else if (ilp <= 2) launch(blend_backward_kernel<2, false, 4, 8>, 8);
-    else launch(blend_backward_kernel<3, false, 4, 8>, 8);
-  }
+  constexpr int kW = GHR_BWD_WARPS;
+  prefer_shared(blend_backward_kernel<kW>);
+  const unsigned grid = (unsigned)((L.n_slots - 1) * (kBlendWarps / kW));
+  blend_backward_kernel<kW><<<grid, kW * 32, 0, s>>>(
+      d.H, d.W, L.gx, L.T, d.P, cam, (const GhrStatus *)(state + L.pub.off_status),
+      (const uint4 *)(state + L.pub.off_units), (const float4 *)(state + L.pub.off_records),
+      (const uint8_t *)(state + L.pub.off_masks), (const float4 *)(state + L.pub.off_tilefinal),
+      (const float4 *)(state + L.pub.off_ckpt), (const uint32_t *)(state + L.pub.off_ncontrib), dL_dout, dL_dmask,
+      acc);
   return cudaGetLastError();
 }
 

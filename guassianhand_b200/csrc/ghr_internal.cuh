@@ -33,10 +33,49 @@ __device__ __forceinline__ float dot3a(float a0, float b0, float a1, float b1, f
   return fadd(dot3(a0, b0, a1, b1, a2, b2), c);
 }
 
+#ifdef GHR_EXACT_EXP
+// Test-only build variant (libghr_exact.so, tests/test_gpu_exact_variant.py): libdevice expf and an IEEE
+// divide in the blend kernels instead of ex2.approx / rcp.approx, to COUNT the pixels whose threshold
+// decisions the fast functions change.  Never the shipped library.
+__device__ __forceinline__ float rcp_fast(float x) { return __fdiv_rn(1.0f, x); }
+#else
 __device__ __forceinline__ float rcp_fast(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+#endif
+
+// ---- packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2) ----
+// Two IEEE round-to-nearest fp32 operations per instruction, one per half: the bits of every half are
+// those of the scalar __fmaf_rn / __fmul_rn / __fadd_rn, so the canonical arithmetic does not change.
+// ptxas folds a {x, x} pair into a scalar-broadcast operand and immediates likewise (no extra moves).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 bc2(float x) { return pk2(x, x); }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ float lo2(f32x2 v) { float a, b; upk2(v, a, b); return a; }
+__device__ __forceinline__ float hi2(f32x2 v) { float a, b; upk2(v, a, b); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // Sub-block culling (never part of the canonical arithmetic).

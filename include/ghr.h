@@ -41,7 +41,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 8
+#define GHR_ABI_VERSION 9
 #define GHR_SEGMENT 128 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
@@ -188,9 +188,11 @@ int ghr_event_destroy(void *event);
 int ghr_event_record(void *event, void *cuda_stream);
 int ghr_event_elapsed_ms(void *start, void *stop, float *ms_out); /* both must have completed */
 
-/* FP32 roofline denominator: launches a dependent-FMA kernel (8 chains/thread) on `cuda_stream`;
- * *flops_out = floating-point operations it executes.  Time it with events. `sink` = 4 device bytes. */
-int ghr_fp32_probe(int32_t iters, float *sink, double *flops_out, void *cuda_stream);
+/* FP32 roofline denominator: launches a dependent-FMA kernel (8 chains/thread, 128 FMA instructions per
+ * loop trip, all three operands in registers) on `cuda_stream`; packed != 0 issues fp32 pairs (FFMA2, the
+ * form the blend kernels use).  `in` = 2 device floats (multiplier, addend), `sink` = 4 device bytes;
+ * *flops_out = floating-point operations the launch executes.  Time it with events. */
+int ghr_fp32_probe(int32_t iters, int32_t packed, const float *in, float *sink, double *flops_out, void *cuda_stream);
 
 /* ---- fused attribute head ----
  * Activations of GSLayer.forward (/root/reference/tgs/models/renderer_one_shot.py:191-214: normalize,

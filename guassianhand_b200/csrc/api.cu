@@ -42,7 +42,7 @@ int compute_layout(const GhrDims &d, Layout *L) {
   L->pub.off_geom = o;     o = align_up(o + VP * 64);
   L->pub.off_clamped = o;  o = align_up(o + (d.M > 0 ? VP : 0));
   L->pub.off_ranges = o;   o = align_up(o + VT * 8);
-  L->pub.off_tilemax = o;  o = align_up(o + VT * 4);
+  L->pub.off_tilemax = o;  o = align_up(o + VT * 8);
   L->pub.off_records = o;  o = align_up(o + (size_t)d.R_cap * kRecBytes);
   L->pub.off_final_T = o;  o = align_up(o + VN * 4);
   L->pub.off_ncontrib = o; o = align_up(o + VN * 4);

@@ -515,8 +515,10 @@ __device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uin
   if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | depth_bits;
   if (dbg_plist) dbg_plist[r] = id;
   q2.w = __uint_as_float(id);
-  records[3 * r] = q0;
-  records[3 * r + 1] = q1;
+  // record layout: {x, y, A, C} {B, opacity, thr, 0} {r, g, b, id} -- (x, y) and (A, C) are the operand
+  // pairs of the blend kernels' packed (dx, dy) math
+  records[3 * r] = make_float4(q0.x, q0.y, q0.z, q1.x);
+  records[3 * r + 1] = make_float4(q0.w, q1.y, q1.z, 0.f);
   records[3 * r + 2] = q2;
 }
 
@@ -711,8 +713,8 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
         if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | ((uint32_t)(key >> 32) + dmin);
         if (dbg_plist) dbg_plist[r] = id;
         q2.w = __uint_as_float(id);
-        stg[3 * lane] = q0;
-        stg[3 * lane + 1] = q1;
+        stg[3 * lane] = make_float4(q0.x, q0.y, q0.z, q1.x);       // {x, y, A, C}
+        stg[3 * lane + 1] = make_float4(q0.w, q1.y, q1.z, 0.f);   // {B, opacity, thr, 0}
         stg[3 * lane + 2] = q2;
       }
       __syncwarp();

@@ -3,23 +3,23 @@
 // Forward replaces upstream renderCUDA<3> forward; backward replaces
 // renderCUDA<3> backward (K7, A.6).
 //
-// Thread = TWO pixels of one column, 4 rows apart; a warp covers an 8x8 pixel block, four warps a
-// 16x16 tile.  The two pixels share the instance's record loads, its queue entry and dx; everything
-// that differs per pixel is computed as a packed fp32 pair (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2,
-// IEEE-rn per half: the canonical bits are those of the scalar formulation).  The kernels are bound by
-// instruction issue, so the pair halves the issue slots per (pixel, instance).
+// Both kernels are bound by instruction issue, not by FP32 throughput or memory, so both evaluate the
+// per-(pixel, instance) math as packed fp32 pairs (fma/mul/add.rn.f32x2 -> FFMA2/FMUL2/FADD2; IEEE-rn per
+// half: the canonical bits are those of the scalar formulation) -- but they pair different things:
 //
-// Forward: one CTA (4 warps) per (view, tile), taken heaviest-first from the tile schedule.  The tile's
+// Forward: one CTA (8 warps) per (view, tile), taken heaviest-first from the tile schedule; thread = one
+// pixel, warp = one 8x4 sub-block, the pair = TWO INSTANCES (see the forward section for why).  The tile's
 // instance list is a contiguous slab of 48-byte records (written by the chunk sort / merge of
 // binning.cu); it is streamed through a ring of shared-memory stages with 1-D bulk async copies
 // (cp.async.bulk -> UBLKCP) completing on "full" mbarriers.  There is no producer warp: the LAST warp to
 // release a stage refills it (one shared-memory atomic per warp and stage), so warps drift apart by up to
 // kStages-1 stages instead of meeting at a CTA barrier every round, and no warp slot or register budget
 // is spent on polling.  Inside a stage each warp first culls: an instance's precomputed 8-bit mask says
-// which 8x4 sub-blocks it can reach with alpha >= 1/255, a ballot compacts the survivors into a queue, and
-// only those are blended.
+// which 8x4 sub-blocks it can reach with alpha >= 1/255; only the survivors are blended.
 // Backward: one (tile, 128-instance segment) work unit per CTA, restarted from the forward's checkpoints;
-// per-instance partial gradients (already summed over the thread's two pixels) are parked in shared
+// thread = TWO PIXELS of one column, 4 rows apart (a warp covers an 8x8 block, four warps the tile): the
+// two pixels share the instance's record loads, its queue entry and dx, and the thread sums its two
+// pixels' partial gradients before the warp reduction.  Per-instance partials are parked in shared
 // memory three instances at a time, reduced across the warp with conflict-free 128-bit loads and leave
 // the SM as one RED.ADD per value per warp.
 #include "ghr_internal.cuh"
@@ -29,12 +29,10 @@ namespace ghr {
 namespace {
 
 constexpr int kStageN = 128;  // instances per stage (6 KB)
-constexpr int kStages = 4;
-constexpr int kBlendWarps = 4;               // 8x8-pixel blocks of a tile
-constexpr int kBlendThreads = kBlendWarps * 32;
+constexpr int kStages = 6;      // forward stage ring
+constexpr int kBlendWarps = 4;               // backward: 8x8-pixel blocks of a tile
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kIlpF = 4;         // instances per forward iteration (x 2 pixels = 8 independent alpha chains)
 constexpr int kIlpB = 2;         // instances per backward iteration
 constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
@@ -156,9 +154,10 @@ __device__ __forceinline__ void pair_alpha(const float4 a, const float4 bq, floa
                                            float &a1) {
   dx = fsub(a.x, pxf);
   dy = add2(bc2(a.y), npy);
-  const f32x2 v = mul2(mul2(bc2(bq.x), dy), dy);
+  // record layout: a = {x, y, A, C}, bq = {B, opacity, thr, 0}
+  const f32x2 v = mul2(mul2(bc2(a.w), dy), dy);
   const f32x2 qf = fma2(bc2(fmul(a.z, dx)), bc2(dx), v);
-  const f32x2 z = mul2(bc2(fmul(-a.w, dx)), dy);
+  const f32x2 z = mul2(bc2(fmul(-bq.x, dx)), dy);
   const f32x2 power = fma2(bc2(-0.5f), qf, z);
   upk2(power, p0, p1);
 #ifdef GHR_EXACT_EXP
@@ -175,32 +174,10 @@ __device__ __forceinline__ void pair_alpha(const float4 a, const float4 bq, floa
   a1 = fminf(0.99f, a1);
 }
 
-// Survivor queue of one warp for one stage (forward): the 16-bit shared-memory ADDRESSES of the records
-// (the kernel's shared window is far below 64 KB) of the instances, ascending, whose sub-block mask hits
-// the warp's 8x8 block.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the
-// blend loop then takes kIlpF addresses per LDS.64, so an instance costs one extract and no address
-// arithmetic before its three record loads.  Survivor i is q[kQPad + i]; kQPad entries pad the end with
-// the address of the stage's all-zero record (alpha = 0).  Returns the survivor count.
-__device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_t cnt, uint32_t hitmask, int lane,
-                                                     uint16_t *q, uint32_t rec_base, uint32_t pad_addr) {
-  const uint32_t lt = (1u << lane) - 1u;
-  uint32_t total = 0;
-  __syncwarp();   // every lane has finished reading the previous stage's queue
-#pragma unroll
-  for (int w = 0; w < kStageN / 32; w++) {
-    const uint32_t e = w * 32 + lane;
-    bool hit = false;
-    if (e < cnt) hit = (msk[e] & hitmask) != 0u;
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (hit) q[kQPad + total + __popc(m & lt)] = (uint16_t)(rec_base + e * kRecBytes);
-    total += __popc(m);
-  }
-  if (lane < kQPad) q[kQPad + total + lane] = (uint16_t)pad_addr;
-  __syncwarp();
-  return total;
-}
-// Backward variant: 8-bit indices inside the segment; `limit` = instances that precede the warp's last
-// contributor; padding = index kSeg, the all-zero record behind the segment.
+// Survivor queue of one backward warp: 8-bit indices inside the segment (ascending) of the instances whose
+// sub-block mask hits the warp's 8x8 block.  Each lane tests 4 instances (one byte LDS each), 4 ballots
+// compact them.  Survivor i is q[kQPad + i]; `limit` = instances that precede the warp's last
+// contributor; kQPad entries pad the end with index kSeg, the all-zero record behind the segment.
 __device__ __forceinline__ uint32_t build_queue_idx(const uint8_t *msk, uint32_t cnt, uint32_t limit, uint32_t hitmask,
                                                     int lane, uint8_t *q) {
   const uint32_t lt = (1u << lane) - 1u;
@@ -218,48 +195,153 @@ __device__ __forceinline__ uint32_t build_queue_idx(const uint8_t *msk, uint32_t
   __syncwarp();
   return total;
 }
+// ---- forward ----
+// Thread = ONE pixel, a warp = one 8x4 sub-block, 8 warps per tile in two CTAs.  A tile's list is a serial
+// chain per warp (the transmittance recursion), and a launch has only a few hundred non-empty tiles: its
+// duration is set by the longest chains, i.e. by how fast ONE scheduler issues what a warp does per stage
+// and per instance (per-warp clocks, tools/blend_timeline.py: with all 8 warps of a tile in one CTA the two
+// busiest sub-blocks shared a scheduler and the tile ran at half speed while most of the GPU was idle).
+// Hence:
+//  - the tile is spread over as many warps as it has 32-pixel blocks, four per CTA (one per scheduler, and
+//    the two CTAs of a tile usually land on different SMs); the packed pair is the pixel's
+//    (dx, dy): records carry (x, y) and (A, C) as aligned pairs, so d = (x, y) - p and (A dx, C dy) are one
+//    instruction each, (r, g) * alpha likewise -- every half in the canonical order;
+//  - per stage a warp only builds a queue of the 16-bit shared-memory addresses of its survivors (mask
+//    bit of its sub-block; 4 ballots) and reads their records in place: three LDS.128 per instance;
+//  - eight instances per iteration: their alphas do not depend on the running transmittance, so the long
+//    chains (LDS -> quadratic form -> exp -> thresholds, ~150 cycles) of 8 instances overlap;
+//  - the serial part is ONE multiply per instance: tc <- tc * (1 - alpha) runs on as a pure product even
+//    past the pixel's termination (1 - alpha <= 1, so tc < 1e-4 is sticky without a select in the chain);
+//    the frozen output value, the weight mask and the last-contributor index hang off it as selects.
+constexpr int kFwdWarps = 4;                  // warps per CTA: one per scheduler
+constexpr int kFwdParts = 2;                  // CTAs per tile (upper / lower half), each staging the slab
+constexpr int kFwdThreads = kFwdWarps * 32;
+constexpr int kIlpF = 8;                      // instances per iteration
+struct __align__(128) FwdSmem {
+  StageBuf sb;
+  uint16_t q[kFwdWarps][kStageN + 2 * kQPad];
+};
+
+// Survivor queue of one warp for one stage: the 16-bit shared-memory ADDRESSES of the records (the
+// kernel's shared window is below 64 KB) of the instances, ascending, whose sub-block mask has the warp's
+// bit.  Each lane tests 4 instances (one byte LDS each), 4 ballots compact them; the blend loop then takes
+// kIlpF addresses per LDS.128, so an instance costs one extract and no address arithmetic before its
+// three record loads.  Survivor i is q[kQPad + i]; kQPad entries pad the end with the address of the
+// stage's all-zero record (alpha = 0).  Returns the survivor count.
+__device__ __forceinline__ uint32_t build_queue_addr(const uint8_t *msk, uint32_t cnt, uint32_t hitbit, int lane,
+                                                     uint16_t *q, uint32_t rec_base, uint32_t pad_addr) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t mb[kStageN / 32], m[kStageN / 32];
+  __syncwarp();   // every lane has finished reading the previous stage's queue
+#pragma unroll
+  for (int w = 0; w < kStageN / 32; w++) mb[w] = msk[w * 32 + lane];     // (bytes past cnt are stale, not out of bounds)
+#pragma unroll
+  for (int w = 0; w < kStageN / 32; w++)
+    m[w] = __ballot_sync(0xFFFFFFFFu, (uint32_t)(w * 32 + lane) < cnt && (mb[w] & hitbit) != 0u);
+  uint32_t total = 0;
+#pragma unroll
+  for (int w = 0; w < kStageN / 32; w++) {
+    if ((m[w] >> lane) & 1u) q[kQPad + total + __popc(m[w] & lt)] = (uint16_t)(rec_base + (w * 32 + lane) * kRecBytes);
+    total += __popc(m[w]);
+  }
+  if (lane < kQPad) q[kQPad + total + lane] = (uint16_t)pad_addr;
+  __syncwarp();
+  return total;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 
-__global__ void __launch_bounds__(kBlendThreads, 6)
+// alpha and (colour * alpha) of one instance at the thread's pixel, canonical order:
+//   dx = x - px; dy = y - py; q = fma(A dx, dx, (C dy) dy); power = fma(-0.5, q, (-B dx) dy);
+//   alpha = min(0.99, opacity * exp(power)), 0 if power > 0 or alpha < 1/255
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float fwd_alpha(const float4 a, const float2 bo, f32x2 npxy) {
+  const f32x2 d = add2(pk2(a.x, a.y), npxy);
+  float dx, dy, mA, mC;
+  upk2(d, dx, dy);
+  upk2(mul2(pk2(a.z, a.w), d), mA, mC);
+  const float qf = ffma(mA, dx, fmul(mC, dy));
+  const float power = ffma(-0.5f, qf, fmul(fmul(-bo.x, dx), dy));
+#ifdef GHR_EXACT_EXP
+  const float G = expf(power);
+#else
+  const float G = ex2_fast(power * kLog2e);
+#endif
+  const float alpha = fminf(0.99f, fmul(bo.y, G));
+  return (power <= 0.0f && alpha >= kAlphaMin) ? alpha : 0.f;   // padding: opacity 0 -> alpha 0
+}
+
+// One instance of the serial part, branch-free (written in PTX so that it stays a select chain):
+//   t = tc * (1 - alpha)   test_T; alpha == 0: t == tc exactly.  A live tc is >= 1e-4 (the stopping
+//                          Gaussian is never applied), so a live pixel terminates only on alpha != 0
+//   term = t < 1e-4        sticky: tc keeps shrinking after the pixel's termination
+//   C += (c alpha) * (term ? 0 : tc)         the stopping Gaussian is not blended
+//   Tr = term ? Tr : t                       the output transmittance freezes at its last live value
+//   last = (!term && alpha != 0) ? idx : last
+__device__ __forceinline__ void fwd_blend_step(float &tc, float &Tr, float &Cr, float &Cg, float &Cb, uint32_t &last,
+                                               float om, float a, float r, float g, float b, uint32_t idx) {
+  asm("{\n\t"
+      ".reg .pred pt, pc;\n\t"
+      ".reg .f32 t, tm;\n\t"
+      "mul.rn.f32 t, %0, %6;\n\t"
+      "setp.lt.f32 pt, t, 0f38D1B717;\n\t"
+      "setp.neu.and.f32 pc, %7, 0f00000000, !pt;\n\t"
+      "selp.f32 tm, 0f00000000, %0, pt;\n\t"
+      "fma.rn.f32 %2, %8, tm, %2;\n\t"
+      "fma.rn.f32 %3, %9, tm, %3;\n\t"
+      "fma.rn.f32 %4, %10, tm, %4;\n\t"
+      "selp.f32 %1, %1, t, pt;\n\t"
+      "selp.b32 %5, %11, %5, pc;\n\t"
+      "mov.f32 %0, t;\n\t"
+      "}"
+      : "+f"(tc), "+f"(Tr), "+f"(Cr), "+f"(Cg), "+f"(Cb), "+r"(last)
+      : "f"(om), "f"(a), "f"(r), "f"(g), "f"(b), "r"(idx));
+}
+
+__device__ __forceinline__ void pixel_of_thread(int warp, int lane, int &lx, int &ly) {
+  lx = ((warp & 1) << 3) + (lane & 7);
+  ly = ((warp >> 1) << 2) + (lane >> 3);
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 4)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                      uint32_t *__restrict__ tilemax, float4 *__restrict__ tilefinal, float4 *__restrict__ ckpt,
                      uint4 *__restrict__ units, GhrStatus *__restrict__ status, float *__restrict__ out_color,
                      float *__restrict__ out_mask) {
-  __shared__ StageBuf sb;
-  __shared__ __align__(16) uint16_t s_q[kBlendWarps][kStageN + 2 * kQPad];
-  const uint32_t vt = order[blockIdx.x];
+  __shared__ FwdSmem sm;
+  StageBuf &sb = sm.sb;
+  const uint32_t vt = order[blockIdx.x / kFwdParts], part = blockIdx.x % kFwdParts;
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int lx, ly0;
-  pixels_of_thread(warp, lane, lx, ly0);
-  const int px = (tile % gx) * kTile + lx, py0 = (tile / gx) * kTile + ly0, py1 = py0 + 4;
-  const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
-  const size_t N = (size_t)H * W;
-  const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px;
+  const int lane = threadIdx.x & 31, wloc = threadIdx.x >> 5;
+  const int warp = (int)part * kFwdWarps + wloc, tid = warp * 32 + lane;   // warp / thread inside the tile
+  int lx, ly;
+  pixel_of_thread(warp, lane, lx, ly);
+  const int px = (tile % gx) * kTile + lx, py = (tile / gx) * kTile + ly;
+  const bool inside = px < W && py < H;
+  const size_t N = (size_t)H * W, pix = (size_t)py * W + px;
   const float *bg = cam.bg + (size_t)cam.bg_stride * v;
 
   const uint2 range = ranges[vt];
   const uint32_t n = range.y - range.x;
   if (n == 0) {
     // empty tile (most of the frame): background only, no barriers, no staging
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      if (h ? in1 : in0) {
-        const size_t pix = h ? pix1 : pix0;
-        final_T[(size_t)v * N + pix] = 1.0f;
-        n_contrib[(size_t)v * N + pix] = 0u;
-        float *o = out_color + (size_t)v * 3 * N + pix;
-        o[0] = ffma(1.0f, bg[0], 0.f);
-        o[N] = ffma(1.0f, bg[1], 0.f);
-        o[2 * N] = ffma(1.0f, bg[2], 0.f);
-        if (out_mask) out_mask[(size_t)v * N + pix] = 0.f;
-      }
+    if (inside) {
+      final_T[(size_t)v * N + pix] = 1.0f;
+      n_contrib[(size_t)v * N + pix] = 0u;
+      float *o = out_color + (size_t)v * 3 * N + pix;
+      o[0] = ffma(1.0f, bg[0], 0.f);
+      o[N] = ffma(1.0f, bg[1], 0.f);
+      o[2 * N] = ffma(1.0f, bg[2], 0.f);
+      if (out_mask) out_mask[(size_t)v * N + pix] = 0.f;
     }
     return;
   }
@@ -267,7 +349,7 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
 #ifdef GHR_TIMELINE
   const unsigned long long tl0 = gtime_ns();
 #endif
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; s++) {
       mbar_init(&sb.full[s], 1);
       sb.released[s] = 0;
@@ -280,98 +362,96 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       stage_load(sb, (int)r, records, masks, (size_t)range.x + (size_t)r * kStageN,
                  min((uint32_t)kStageN, n - r * kStageN));
   }
-  if (tid >= 32 && tid < 32 + 3 * kStages)
-    sb.rec[(tid - 32) / 3][kStageN * 3 + (tid - 32) % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + 3 * kStages)
+    sb.rec[(threadIdx.x - 32) / 3][kStageN * 3 + (threadIdx.x - 32) % 3] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
 
-  const float pxf = (float)px;
-  const f32x2 npy = pk2(-(float)py0, -(float)py1);
-  const uint32_t hitmask = hitmask_of_warp(warp);
-  uint16_t *q = &s_q[warp][0];
+  const f32x2 npxy = pk2(-(float)px, -(float)py);
+  const uint32_t hitbit = 1u << warp;
+  uint16_t *q = &sm.q[wloc][0];
 
-  // T > 0: live transmittance; T < 0: the pixel has terminated (or lies outside the image), |T| is the
-  // frozen output value -- then test_T < 0 keeps `term` set and every later weight is 0
-  float T0 = in0 ? 1.0f : -1.0f, T1 = in1 ? 1.0f : -1.0f;
-  f32x2 Cr = pk2(0.f, 0.f), Cg = Cr, Cb = Cr;
-  bool wdone = __all_sync(0xFFFFFFFFu, !in0 && !in1);
+  // tc: running product of (1 - alpha); live while >= 1e-4 (0 from the start outside the image).
+  // Tr: the output transmittance, frozen at the pixel's last live value.
+  float tc = inside ? 1.0f : 0.f, Tr = 1.0f, Cr = 0.f, Cg = 0.f, Cb = 0.f;
+  bool wdone = __all_sync(0xFFFFFFFFu, !inside);
   if (wdone && lane == 0) atomicAdd(&sb.done_warps, 1u);
-  uint32_t last0 = 0, last1 = 0;
+  uint32_t last = 0;
+#ifdef GHR_TIMELINE
+  uint32_t tl_surv = 0, tl_iter = 0, tl_pass = 0, tl_rounds = 0;
+  long long tl_wait = 0, tl_comp = 0, tl_blend = 0, tl_c0 = 0;
+#endif
   for (uint32_t r = 0; r < rounds; r++) {
     const int s = r % kStages;
-    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 1024u : 256u);
+#ifdef GHR_TIMELINE
+    tl_c0 = clock64();
+#endif
+    mbar_wait(&sb.full[s], (r / kStages) & 1, wdone ? 256u : 32u);
+#ifdef GHR_TIMELINE
+    tl_wait += clock64() - tl_c0;
+    if (!wdone) tl_rounds = r + 1;
+    tl_c0 = clock64();
+#endif
     if (r >= *(volatile uint32_t *)&sb.stop_round) break;
     if (!wdone) {
       // running state at every kSeg-instance boundary: the backward restarts from it (one work unit per
       // segment).  A warp whose pixels have all terminated writes nothing: no later unit reads it.
-      if (r > 0) {
-        float c0r, c1r, c0g, c1g, c0b, c1b;
-        upk2(Cr, c0r, c1r);
-        upk2(Cg, c0g, c1g);
-        upk2(Cb, c0b, c1b);
-        float4 *ck = ckpt + ((size_t)(range.x / kSeg) + vt + r) * 256 + warp * 64 + lane;
-        ck[0] = make_float4(fabsf(T0), c0r, c0g, c0b);
-        ck[32] = make_float4(fabsf(T1), c1r, c1g, c1b);
-      }
+      if (r > 0) ckpt[((size_t)(range.x / kSeg) + vt + r) * 256 + tid] = make_float4(Tr, Cr, Cg, Cb);
       const uint32_t cnt = min((uint32_t)kStageN, n - r * kStageN);
       const uint32_t rec_base = smem_u32(&sb.rec[s][0]);
-      const uint32_t total = build_queue_addr(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, hitmask, lane, q,
-                                              rec_base, rec_base + kStageN * kRecBytes);
-      uint32_t lastq0 = 0, lastq1 = 0;                      // 1 + queue index of the last blended survivor
+      const uint32_t total = build_queue_addr(&sb.msk[s][(range.x + r * kStageN) & 15u], cnt, hitbit, lane, q, rec_base,
+                                              rec_base + kStageN * kRecBytes);
+#ifdef GHR_TIMELINE
+      tl_surv += total;
+      tl_iter += (total + kIlpF - 1u) / kIlpF;
+      tl_pass++;
+      tl_comp += clock64() - tl_c0;
+      tl_c0 = clock64();
+#endif
+      uint32_t lastq = 0;                                     // 1 + queue index of the last blended survivor
       for (uint32_t b = 0; b < total; b += kIlpF) {
-        // kIlpF survivors at a time: their alphas do not depend on the running transmittance, so the
-        // long chains (LDS -> quadratic form -> exp) of several instances overlap; only the short
-        // T / colour update is serial (and branch-free: a rejected pair blends alpha = 0).
-        f32x2 al[kIlpF];
-        float4 col[kIlpF];
-        const uint2 p2 = *reinterpret_cast<const uint2 *>(q + kQPad + b);
-        const uint32_t packed[2] = {p2.x, p2.y};
+        const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
+        const uint32_t packed[4] = {p4.x, p4.y, p4.z, p4.w};
+        uint32_t addr[kIlpF];
+        float4 ga[kIlpF];
+        float2 gb[kIlpF];
+        float al[kIlpF];
+        // phase 1: the geometry of all kIlpF instances is requested before any of it is used, so the eight
+        // alpha chains run side by side; phase 2 fetches the colours as the serial update reaches them
 #pragma unroll
         for (int k = 0; k < kIlpF; k++) {
-          const uint32_t addr = (k & 1) ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu;
-          const float4 a = lds128(addr), bq = lds128(addr + 16);
-          col[k] = lds128(addr + 32);
-          float dx, p0, p1, G0, G1, a0, a1;
-          f32x2 dy;
-          pair_alpha(a, bq, pxf, npy, dx, dy, p0, p1, G0, G1, a0, a1);
-          al[k] = pk2((p0 <= 0.0f && a0 >= kAlphaMin) ? a0 : 0.f,      // padding: opacity 0 -> alpha 0
-                      (p1 <= 0.0f && a1 >= kAlphaMin) ? a1 : 0.f);
+          addr[k] = (k & 1) ? packed[k >> 1] >> 16 : packed[k >> 1] & 0xFFFFu;
+          ga[k] = lds128(addr[k]);
+          gb[k] = lds64(addr[k] + 16);
         }
 #pragma unroll
+        for (int k = 0; k < kIlpF; k++) al[k] = fwd_alpha(ga[k], gb[k], npxy);
+#pragma unroll
         for (int k = 0; k < kIlpF; k++) {
-          float a0, a1, t0, t1;
-          upk2(al[k], a0, a1);
-          // test_T = T (1 - alpha); alpha == 0: test_T == T exactly.  A live T is >= 1e-4 (the stopping
-          // Gaussian is never applied), so a live pixel terminates only on alpha != 0; a terminated one
-          // (T < 0) stays terminated.
-          upk2(mul2(pk2(T0, T1), fma2(al[k], bc2(-1.0f), bc2(1.0f))), t0, t1);
-          const bool term0 = t0 < 0.0001f, term1 = t1 < 0.0001f;
-          const f32x2 Tm = pk2(term0 ? 0.f : T0, term1 ? 0.f : T1);   // the stopping Gaussian is not blended
-          Cr = fma2(mul2(bc2(col[k].x), al[k]), Tm, Cr);               // upstream's order: (c * alpha) * T
-          Cg = fma2(mul2(bc2(col[k].y), al[k]), Tm, Cg);
-          Cb = fma2(mul2(bc2(col[k].z), al[k]), Tm, Cb);
-          T0 = term0 ? -fabsf(T0) : t0;
-          T1 = term1 ? -fabsf(T1) : t1;
-          lastq0 = (!term0 && a0 != 0.f) ? b + k + 1 : lastq0;
-          lastq1 = (!term1 && a1 != 0.f) ? b + k + 1 : lastq1;
+          const float4 c = lds128(addr[k] + 32);
+          float r0, g0;
+          upk2(mul2(pk2(c.x, c.y), bc2(al[k])), r0, g0);               // upstream's order: (c * alpha) * T
+          fwd_blend_step(tc, Tr, Cr, Cg, Cb, lastq, fsub(1.0f, al[k]), al[k], r0, g0, fmul(c.z, al[k]), b + k + 1);
         }
-        if (__all_sync(0xFFFFFFFFu, T0 < 0.f && T1 < 0.f)) {
+        if (__all_sync(0xFFFFFFFFu, tc < 0.0001f)) {
           wdone = true;
           if (lane == 0) atomicAdd(&sb.done_warps, 1u);
           break;
         }
       }
-      if (lastq0) last0 = r * kStageN + ((uint32_t)q[kQPad + lastq0 - 1] - rec_base) / kRecBytes + 1;
-      if (lastq1) last1 = r * kStageN + ((uint32_t)q[kQPad + lastq1 - 1] - rec_base) / kRecBytes + 1;
+      if (lastq) last = r * kStageN + ((uint32_t)q[kQPad + lastq - 1] - rec_base) / kRecBytes + 1;
+#ifdef GHR_TIMELINE
+      tl_blend += clock64() - tl_c0;
+#endif
     }
-    // release the stage; the last warp to do so refills it with round r + kStages
+    // release the stage; the last warp to do so refills it with round r + kStages.  (A relaxed counter:
+    // the warp's loads of the stage have completed -- their values were consumed above.)
     __syncwarp();
     if (lane == 0) {
-      __threadfence_block();
-      if (atomicAdd(&sb.released[s], 1u) == (uint32_t)kBlendWarps - 1u) {
+      if (atomicAdd(&sb.released[s], 1u) == (uint32_t)kFwdWarps - 1u) {
         *(volatile uint32_t *)&sb.released[s] = 0u;
         const uint32_t nr = r + kStages;
         if (nr < rounds) {
-          if (*(volatile uint32_t *)&sb.done_warps == (uint32_t)kBlendWarps) {
+          if (*(volatile uint32_t *)&sb.done_warps == (uint32_t)kFwdWarps) {
             // every pixel of the tile has terminated: complete the phase without data ("poison")
             atomicMin(&sb.stop_round, nr);
             __threadfence_block();
@@ -386,50 +466,47 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
     }
   }
 
-  float c0r, c1r, c0g, c1g, c0b, c1b;
-  upk2(Cr, c0r, c1r);
-  upk2(Cg, c0g, c1g);
-  upk2(Cb, c0b, c1b);
-  const float Tr0 = fabsf(T0), Tr1 = fabsf(T1);
-  if (in0) {
-    final_T[(size_t)v * N + pix0] = Tr0;
-    n_contrib[(size_t)v * N + pix0] = last0;
-    float *o = out_color + (size_t)v * 3 * N + pix0;
-    o[0] = ffma(Tr0, bg[0], c0r);
-    o[N] = ffma(Tr0, bg[1], c0g);
-    o[2 * N] = ffma(Tr0, bg[2], c0b);
-    if (out_mask) out_mask[(size_t)v * N + pix0] = 1.0f - Tr0;   // = sum_j alpha_j T_j
+  if (inside) {
+    final_T[(size_t)v * N + pix] = Tr;
+    n_contrib[(size_t)v * N + pix] = last;
+    float *o = out_color + (size_t)v * 3 * N + pix;
+    o[0] = ffma(Tr, bg[0], Cr);
+    o[N] = ffma(Tr, bg[1], Cg);
+    o[2 * N] = ffma(Tr, bg[2], Cb);
+    if (out_mask) out_mask[(size_t)v * N + pix] = 1.0f - Tr;   // = sum_j alpha_j T_j
   }
-  if (in1) {
-    final_T[(size_t)v * N + pix1] = Tr1;
-    n_contrib[(size_t)v * N + pix1] = last1;
-    float *o = out_color + (size_t)v * 3 * N + pix1;
-    o[0] = ffma(Tr1, bg[0], c1r);
-    o[N] = ffma(Tr1, bg[1], c1g);
-    o[2 * N] = ffma(Tr1, bg[2], c1b);
-    if (out_mask) out_mask[(size_t)v * N + pix1] = 1.0f - Tr1;
-  }
-  float4 *tf = tilefinal + (size_t)vt * 256 + warp * 64 + lane;
-  tf[0] = make_float4(c0r, c0g, c0b, Tr0);
-  tf[32] = make_float4(c1r, c1g, c1b, Tr1);
-  // backward work units of this tile: one per kSeg instances up to the tile's last contributor
-  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, max(last0, last1));
+  tilefinal[(size_t)vt * 256 + tid] = make_float4(Cr, Cg, Cb, Tr);
+  // backward work units of this tile: one per kSeg instances up to the tile's last contributor, emitted by
+  // the CTA of the tile that finishes last
+  const uint32_t wmax = __reduce_max_sync(0xFFFFFFFFu, last);
   if (lane == 0 && wmax) atomicMax(&sb.tmax, wmax);
   __syncthreads();
-  if (warp == 0) {
-    const uint32_t tmax = sb.tmax, nseg = (tmax + kSeg - 1) / kSeg;
+  if (wloc == 0) {
+    uint32_t tmax = 0;
+    if (lane == 0) {
+      if (sb.tmax) atomicMax(&tilemax[2 * vt], sb.tmax);
+      __threadfence();
+      if (atomicAdd(&tilemax[2 * vt + 1], 1u) == (uint32_t)kFwdParts - 1u) {
+        __threadfence();
+        tmax = atomicMax(&tilemax[2 * vt], 0u);
+      }
+    }
+    tmax = __shfl_sync(0xFFFFFFFFu, tmax, 0);
+    const uint32_t nseg = (tmax + kSeg - 1) / kSeg;
     if (nseg) {
       uint32_t base = 0;
-      if (lane == 0) {
-        tilemax[vt] = tmax;
-        base = (uint32_t)atomicAdd((unsigned long long *)&status->reserved[1], (unsigned long long)nseg);
-      }
+      if (lane == 0) base = (uint32_t)atomicAdd((unsigned long long *)&status->reserved[1], (unsigned long long)nseg);
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
       for (uint32_t i = lane; i < nseg; i += 32) units[base + i] = make_uint4(vt, i, range.x, tmax);
     }
   }
 #ifdef GHR_TIMELINE
-  if (tid == 0) timeline_put(tl0, 0u, vt, n);
+  if (threadIdx.x == 0) timeline_put(tl0, 0u, vt, n);
+  // per warp: survivors evaluated, iterations, compaction passes, stages it was live in
+  if (lane == 0) {
+    timeline_put(tl0, 1u + (uint32_t)warp, (tl_surv << 12) | tl_iter, (tl_pass << 12) | tl_rounds);
+    timeline_put(tl0, 16u + (uint32_t)warp, (uint32_t)(tl_wait >> 4), ((uint32_t)(tl_comp >> 4) << 16) | (uint32_t)(tl_blend >> 4));
+  }
 #endif
 }
 
@@ -528,14 +605,16 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   const size_t N = (size_t)H * W;
   const float pxf = (float)px;
   const f32x2 npy = pk2(-(float)py0, -(float)py1);
-  const size_t slot0 = (size_t)warp * 64 + lane;
-  const float4 fin0 = tilefinal[(size_t)vt * 256 + slot0], fin1 = tilefinal[(size_t)vt * 256 + slot0 + 32];
+  // per-tile float4 arrays are indexed by the FORWARD's thread id (8x4 sub-block * 32 + lane): the
+  // thread's upper pixel lies in sub-block 4*(warp>>1) + (warp&1), the lower one two sub-blocks on
+  const size_t slot0 = (size_t)(4 * (warp >> 1) + (warp & 1)) * 32 + lane;
+  const float4 fin0 = tilefinal[(size_t)vt * 256 + slot0], fin1 = tilefinal[(size_t)vt * 256 + slot0 + 64];
   float4 c0 = make_float4(1.f, 0.f, 0.f, 0.f), c1 = c0;
   // (a checkpoint no later unit needs was never written: whatever is read there is not used)
   if (first) {
     const float4 *ck = ckpt + ((size_t)(unit.z / kSeg) + vt + unit.y) * 256 + slot0;
     c0 = ck[0];
-    c1 = ck[32];
+    c1 = ck[64];
   }
   float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f}, dm0 = 0.f, dm1 = 0.f;
   uint32_t last0 = 0, last1 = 0;
@@ -695,7 +774,7 @@ cudaError_t launch_blend_forward(const GhrDims &d, const Layout &L, const Camera
                                  float *out_color, float *out_mask, cudaStream_t s) {
   if (L.T == 0 || d.V == 0) return cudaSuccess;
   prefer_shared(blend_forward_kernel);
-  blend_forward_kernel<<<L.T * d.V, kBlendThreads, 0, s>>>(
+  blend_forward_kernel<<<L.T * d.V * kFwdParts, kFwdThreads, 0, s>>>(
       d.H, d.W, L.gx, L.T, cam, (const uint32_t *)(state + L.pub.off_order), (const uint2 *)(state + L.pub.off_ranges),
       (const float4 *)(state + L.pub.off_records), (const uint8_t *)(state + L.pub.off_masks),
       (float *)(state + L.pub.off_final_T), (uint32_t *)(state + L.pub.off_ncontrib),

@@ -150,7 +150,7 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
   {
     size_t gtid = ((size_t)v * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
     size_t gsz = (size_t)gridDim.x * gridDim.y * blockDim.x;
-    for (size_t t = gtid; t < (size_t)T * V; t += gsz) tilemax[t] = 0u;
+    for (size_t t = gtid; t < (size_t)2 * T * V; t += gsz) tilemax[t] = 0u;
   }
   __syncthreads();
 

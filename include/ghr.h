@@ -68,9 +68,9 @@ typedef struct GhrLayout {
                           opacity) + margin: bound on d^T Q d for alpha >= 1/255 (culling only) */
   size_t off_clamped;  /* uint8 per (view, Gaussian): bit c set if SH colour channel c was clamped */
   size_t off_ranges;   /* uint32[2] per (view, tile): [start,end) into the sorted instances */
-  size_t off_tilemax;  /* uint32 per (view, tile): max n_contrib in the tile */
+  size_t off_tilemax;  /* uint32[2] per (view, tile): {max n_contrib in the tile, forward CTAs of the tile that have finished} */
   size_t off_records;  /* 48-byte instance records in sorted order:
-                          {x,y,conic.x,conic.y} {conic.z,opacity,thr,0} {r,g,b,id(uint bits)} */
+                          {x,y,conic.x,conic.z} {conic.y,opacity,thr,0} {r,g,b,id(uint bits)} */
   size_t off_final_T;  /* float per (view, pixel) */
   size_t off_ncontrib; /* uint32 per (view, pixel) */
   size_t off_order;    /* uint32 per (view, tile): blend launch order, longest instance list first */

@@ -150,6 +150,17 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous()
 
 
+def _f32a(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """_f32c plus 16-byte alignment: the kernels read rotations (and SH rows) with 128-bit loads; a contiguous
+    view into a packed parameter buffer (flat[6P:10P].view(P, 4) with odd P) is only 4-byte aligned."""
+    if t is None:
+        return None
+    t = _f32c(t)
+    if t.numel() and t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and t.numel() and not t.is_cuda:
@@ -196,12 +207,14 @@ class ForwardResult(NamedTuple):
 
 def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
                 scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
-                R_cap: Optional[int] = None, stage_events=None, want_mask: bool = False, out=None) -> ForwardResult:
+                R_cap: Optional[int] = None, stage_events=None, want_mask: bool = False, out=None,
+                temp: Optional[torch.Tensor] = None) -> ForwardResult:
     """Enqueue one libghr forward (V views).  check: "poll" (exact: the host waits for the instance
     count, which arrives while the GPU is still sorting/blending, and re-runs on overflow),
     "deferred" (no host wait: the report is verified at the next call on this stream or by
     check_deferred(); an overflow raises there), "none" (caller checks GhrStatus itself; needed
-    under CUDA-graph capture)."""
+    under CUDA-graph capture).  temp: caller-owned scratch (uint8, >= layout temp_bytes) instead of the
+    per-(device, stream) workspace -- required for anything whose pointers outlive the call (CUDA graphs)."""
     L = N.lib()
     dev = means3D.device
     stream = _raw_stream(dev)
@@ -215,7 +228,12 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
     while True:
         lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
         state = torch.empty(lay.state_bytes, dtype=torch.uint8, device=dev)
-        temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+        if temp is None:
+            tmp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+        else:
+            tmp = temp
+            if tmp.numel() < lay.temp_bytes:
+                raise RuntimeError(f"forward_raw: temp has {tmp.numel()} bytes, the layout needs {lay.temp_bytes}")
         if out is not None:
             # caller-owned outputs (contiguous [V,3,H,W] / [V,max(P,1)] / [V,H,W] blocks of a larger batch)
             color, radii, mask = out
@@ -230,7 +248,7 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
         a.out_color, a.radii = color.data_ptr(), radii.data_ptr()
         a.out_mask = _ptr(mask)
         a.state, a.state_bytes = state.data_ptr(), lay.state_bytes
-        a.temp, a.temp_bytes = temp.data_ptr(), temp.numel()
+        a.temp, a.temp_bytes = tmp.data_ptr(), tmp.numel()
         if want_debug:
             dbg = dict(keys=torch.zeros(max(cap, 1), dtype=torch.int64, device=dev),
                        point_list=torch.zeros(max(cap, 1), dtype=torch.int32, device=dev), layout=lay)
@@ -276,7 +294,7 @@ def check_deferred(device=None):
 
 def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, scales, rotations, cov3D, shs,
                  colors, sh_degree, scale_modifier, flags=0, want_means2D=True, accumulate_into=None,
-                 want_conic=False, accumulate=True, stage_events=None, dL_dmask=None):
+                 want_conic=False, accumulate=True, stage_events=None, dL_dmask=None, temp=None):
     """Enqueue one libghr backward.  Returns dict of gradient tensors (summed over views, except
     dL_dmeans2D which is per view)."""
     L = N.lib()
@@ -286,7 +304,10 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     P = means3D.shape[0]
     M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
     lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
-    temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+    if temp is None:
+        temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
+    elif temp.numel() < lay.temp_bwd_bytes:
+        raise RuntimeError(f"backward_raw: temp has {temp.numel()} bytes, the layout needs {lay.temp_bwd_bytes}")
     a = N.GhrBackwardArgs()
     _fill_common(a, cams, P, M, sh_degree, R_cap, scale_modifier, flags, means3D, opacities, scales, rotations, cov3D,
                  shs, colors)
@@ -337,7 +358,7 @@ def _flags(rs) -> int:
 
 
 def _opt(t):
-    return None if t is None or t.numel() == 0 else _f32c(t)
+    return None if t is None or t.numel() == 0 else _f32a(t)
 
 
 class _RasterizeGaussians(torch.autograd.Function):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libghr.so")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "preprocess_bwd.cu", "attributes.cu"]
+SOURCES = ["api.cu", "preprocess.cu", "binning.cu", "blend.cu", "preprocess_bwd.cu", "attributes.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v",
@@ -45,6 +45,10 @@ VARIANTS = {
     "exact": ["-DGHR_EXACT_EXP"],        # libdevice expf + IEEE divide in the blend kernels (parity counting test)
     "timeline": ["-DGHR_TIMELINE"],      # per-CTA start/stop clocks of the blend kernels (tools/blend_timeline.py)
     "bwd2": ["-DGHR_BWD_WARPS=2"],       # A/B: two half-tile CTAs per backward unit
+    "bwdilp3": ["-DGHR_BWD_ILP=3"],      # A/B: instances per backward iteration
+    "bwdilp4": ["-DGHR_BWD_ILP=4"],
+    "bwdocc8": ["-DGHR_BWD_MINCTAS=8"],  # A/B: 64 registers, 8 CTAs per SM
+    "nored": ["-DGHR_NO_RED"],           # experiment: backward blend without its global reductions (wrong results)
 }
 
 

@@ -33,7 +33,13 @@ constexpr int kStages = 6;      // forward stage ring
 constexpr int kBlendWarps = 4;               // backward: 8x8-pixel blocks of a tile
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kIlpB = 2;         // instances per backward iteration
+#ifndef GHR_BWD_ILP
+#define GHR_BWD_ILP 2
+#endif
+#ifndef GHR_BWD_MINCTAS
+#define GHR_BWD_MINCTAS 6
+#endif
+constexpr int kIlpB = GHR_BWD_ILP;   // instances per backward iteration (build-time A/B)
 constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
 #ifndef GHR_BWD_WARPS
@@ -537,7 +543,11 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
     sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
     if (t < ntask && !(t & 1u)) {
       const uint32_t slot = (r * 57u) >> 9, val = r - 9u * slot;      // r / 9 for r < 27
+#ifdef GHR_NO_RED   // experiment only: what the kernel costs without its global reductions
+      if (sum == 123.456f) accb[(size_t)ids[slot] * kAccStride + val] = sum;
+#else
       atomicAdd(accb + (size_t)ids[slot] * kAccStride + val, sum);
+#endif
     }
   }
 }
@@ -554,7 +564,7 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
 // The kernel tracks Dn = -D and TbN = -T_final bg.dL/dpix so that every update is a plain packed fma.
 // kW warps per CTA: 4 (the whole tile) or 2 (half a tile: two CTAs per unit, each staging the slab).
 template <int kW>
-__global__ void __launch_bounds__(kW * 32, kW == 4 ? 6 : 12)
+__global__ void __launch_bounds__(kW * 32, kW == 4 ? GHR_BWD_MINCTAS : 2 * GHR_BWD_MINCTAS)
 blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const GhrStatus *__restrict__ status,
                       const uint4 *__restrict__ units, const float4 *__restrict__ records,
                       const uint8_t *__restrict__ masks, const float4 *__restrict__ tilefinal,
@@ -720,7 +730,11 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
         if (contrib[k]) {
           float *dst = accb + (size_t)idk[k] * kAccStride;
 #pragma unroll
+#ifdef GHR_NO_RED
+          for (int t = 0; t < 9; t++) if (vals[k][t] == 123.456f) dst[t] = vals[k][t];
+#else
           for (int t = 0; t < 9; t++) atomicAdd(dst + t, vals[k][t]);
+#endif
         }
       } else {
         float *row = ring + pend * kSlotFloats + lane;

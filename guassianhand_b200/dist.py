@@ -41,6 +41,66 @@ def balanced_shards(costs: Sequence[float], world: int) -> List[List[int]]:
     return [sorted(s) for s in shards]
 
 
+class _RawCuda:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, nfloats: int):
+        self.__cuda_array_interface__ = {"shape": (int(nfloats),), "typestr": "<f4", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerAllReduce:
+    """Sum of one float buffer over the ranks of ONE node by libghr's own kernel over NVLink peer memory
+    (include/ghr.h ghr_comm_*, csrc/comm.cu): two-shot, in place, deterministic, one launch per call,
+    CUDA-graph capturable.  torch.distributed is used once, to exchange the 128-byte IPC handles.
+
+    `flat` is the buffer (a torch view of the library's allocation): write into it, call all_reduce_().
+    Every rank must issue the same sequence of all_reduce_ calls."""
+
+    def __init__(self, nfloats: int, group=None, device=None):
+        import ctypes as C
+        from . import _native as N
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerAllReduce needs an initialised torch.distributed process group")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > N.GHR_COMM_MAX_RANKS:
+            raise RuntimeError(f"PeerAllReduce: at most {N.GHR_COMM_MAX_RANKS} ranks (one NVLink node)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nfloats = (int(nfloats) + 3) // 4 * 4
+        self._N, self._comm = N, C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib().ghr_comm_create(self.rank, self.world, self.nfloats * 4, C.byref(self._comm)), "ghr_comm_create")
+            mine = C.create_string_buffer(N.GHR_COMM_HANDLE_BYTES)
+            N.check(N.lib().ghr_comm_handle(self._comm, mine), "ghr_comm_handle")
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+            N.check(N.lib().ghr_comm_connect(self._comm, b"".join(gathered)), "ghr_comm_connect")
+        ptr = N.lib().ghr_comm_buffer(self._comm)
+        self._raw = _RawCuda(ptr, self.nfloats)
+        self.flat = torch.as_tensor(self._raw, device=self.device)
+        dist.barrier(group=group)       # every rank has mapped every buffer before anyone launches
+
+    def all_reduce_(self, nfloats: Optional[int] = None):
+        n = self.nfloats if nfloats is None else (int(nfloats) + 3) // 4 * 4
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._N.check(self._N.lib().ghr_comm_allreduce(self._comm, n, stream), "ghr_comm_allreduce")
+
+    def status(self) -> Tuple[int, int]:
+        """(all-reduces completed, error word); synchronises the device."""
+        import ctypes as C
+        ep, err = C.c_uint32(), C.c_uint32()
+        torch.cuda.synchronize(self.device)
+        self._N.check(self._N.lib().ghr_comm_status(self._comm, C.byref(ep), C.byref(err)), "ghr_comm_status")
+        return int(ep.value), int(err.value)
+
+    def close(self):
+        if self._comm:
+            torch.cuda.synchronize(self.device)
+            self.flat = None
+            self._N.lib().ghr_comm_destroy(self._comm)
+            self._comm = None
+
+
 class PackedGrads:
     """One flat fp32 buffer holding every Gaussian-attribute gradient that is summed over views.
 
@@ -48,26 +108,35 @@ class PackedGrads:
     colors 3 (colors_precomp path) or sh 3*M (SH path).  `views()` returns tensors aliasing the
     buffer with the shapes ghr_backward writes."""
 
-    def __init__(self, P: int, M: int = 0, device="cpu", with_cov3D: bool = False):
+    def __init__(self, P: int, M: int = 0, device="cpu", with_cov3D: bool = False, peer: bool = False, group=None):
+        """peer=True (N > 1 ranks on one node): the buffer lives in a PeerAllReduce allocation and
+        all_reduce_() is libghr's NVLink kernel instead of NCCL."""
         self.P, self.M = int(P), int(M)
+        self.comm: Optional[PeerAllReduce] = None
         segs: List[Tuple[str, Tuple[int, ...]]] = [
             ("dL_dmeans3D", (P, 3)), ("dL_dscales", (P, 3)), ("dL_drotations", (P, 4)), ("dL_dopacity", (P, 1))]
         segs.append(("dL_dsh", (P, M, 3)) if M > 0 else ("dL_dcolors", (P, 3)))
         if with_cov3D:
             segs.append(("dL_dcov3D", (P, 6)))
         self.segments = segs
-        n = sum(int(torch.Size(s).numel()) for _, s in segs)
-        self.flat = torch.zeros(n, dtype=torch.float32, device=device)
+        # every segment starts on a 16-byte boundary (the kernels write rotations and SH rows with 128-bit
+        # stores): sizes are rounded up to 4 floats, the padding floats stay zero and are all-reduced along
+        sizes = [(int(torch.Size(s).numel()) + 3) // 4 * 4 for _, s in segs]
+        self.offsets = [sum(sizes[:i]) for i in range(len(sizes))]
+        if peer and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self.comm = PeerAllReduce(sum(sizes), group=group, device=device)
+            self.flat = self.comm.flat[:sum(sizes)]
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
         self._views: Dict[str, torch.Tensor] = {}
-        o = 0
-        for name, shape in segs:
+        for (name, shape), o in zip(segs, self.offsets):
             k = int(torch.Size(shape).numel())
             self._views[name] = self.flat[o:o + k].view(*shape)
-            o += k
 
     @property
     def floats_per_gaussian(self) -> int:
-        return self.flat.numel() // max(self.P, 1)
+        return sum(int(torch.Size(s).numel()) for _, s in self.segments) // max(self.P, 1)
 
     @property
     def nbytes(self) -> int:
@@ -84,6 +153,8 @@ class PackedGrads:
         """Sum over ranks, in place.  No-op without an initialised process group (N=1)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
+        if self.comm is not None:
+            return self.comm.all_reduce_(self.flat.numel())
         return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
@@ -124,11 +195,13 @@ def _slice_views(views, lo: int, hi: int):
 def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, grads: PackedGrads,
                    group=None, sh_degree: int = 0, scale_modifier: float = 1.0,
                    R_cap=None, check: str = "poll", fwd_events=None, bwd_events=None,
-                   overlap: int = 1, partials: Optional[Sequence[PackedGrads]] = None):
+                   overlap: int = 1, partials: Optional[Sequence[PackedGrads]] = None,
+                   temps: Optional[Sequence[torch.Tensor]] = None):
     """One camera-sharded step on this rank: forward + backward of the LOCAL views, gradients written
     into `grads` (overwritten), then the all-reduce.  Returns the api.ForwardResult (color, radii, state).
 
     gauss: dict with means3D, opacities, scales, rotations and colors_precomp or shs (CUDA fp32).
+    group: the process group of the all-reduce (None = default), or False to skip the all-reduce.
     views: guassianhand_b200.api.ViewBatch of the local shard.  dL_dout: [V,3,H,W].
 
     overlap = G > 1 cuts the local views into G contiguous groups and runs each group's forward ->
@@ -137,11 +210,12 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
     kernels of one group are filled with the other groups' work.  Group g > 0 writes into
     `partials[g-1]` (allocated when absent; pass static buffers under CUDA-graph capture), which are
     added into `grads` after the join.  `R_cap` may then be a list (one capacity per group).  Returns a
-    StepResult."""
+    StepResult.  `temps`: one caller-owned scratch buffer per group (see step_temp_bytes) instead of the
+    per-stream workspace -- GraphedFitStep passes its own so that the captured pointers stay valid."""
     from . import api
     f32 = api._f32c
     means3D, opac = f32(gauss["means3D"]), f32(gauss["opacities"])
-    sc, rot = f32(gauss["scales"]), f32(gauss["rotations"])
+    sc, rot = f32(gauss["scales"]), api._f32a(gauss["rotations"])
     shs = f32(gauss["shs"]) if gauss.get("shs") is not None else None
     col = f32(gauss["colors_precomp"]) if gauss.get("colors_precomp") is not None else None
     V = int(views.viewmatrix.shape[0])
@@ -149,12 +223,14 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
     if G == 1:
         cams = views.cams()
         cap = R_cap[0] if isinstance(R_cap, (list, tuple)) else R_cap
+        tmp = temps[0] if temps else None
         res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier, check=check,
-                              R_cap=cap, stage_events=fwd_events)
+                              R_cap=cap, stage_events=fwd_events, temp=tmp)
         api.backward_raw(cams, res.state, res.R_cap, dL_dout, means3D, opac, sc, rot, None, shs, col, sh_degree,
                          scale_modifier, want_means2D=False, accumulate_into=grads.views(), accumulate=False,
-                         stage_events=bwd_events)
-        grads.all_reduce_(group)
+                         stage_events=bwd_events, temp=tmp)
+        if group is not False:
+            grads.all_reduce_(group)
         return res
     if fwd_events is not None or bwd_events is not None:
         raise ValueError("per-stage events need overlap=1 (stages of different groups run concurrently)")
@@ -175,19 +251,29 @@ def fit_step_grads(gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor,
         with torch.cuda.stream(st):
             cams = _slice_views(views, rng.start, rng.stop).cams()
             cap = R_cap[g] if isinstance(R_cap, (list, tuple)) else R_cap
+            tmp = temps[g] if temps else None
             res = api.forward_raw(cams, means3D, opac, sc, rot, None, shs, col, sh_degree, scale_modifier,
-                                  check=check, R_cap=cap, out=(color[rng.start:rng.stop], radii[rng.start:rng.stop], None))
+                                  check=check, R_cap=cap, out=(color[rng.start:rng.stop], radii[rng.start:rng.stop], None),
+                                  temp=tmp)
             target = grads if g == 0 else partials[g - 1]
             api.backward_raw(cams, res.state, res.R_cap, dL_dout[rng.start:rng.stop], means3D, opac, sc, rot, None,
                              shs, col, sh_degree, scale_modifier, want_means2D=False,
-                             accumulate_into=target.views(), accumulate=False)
+                             accumulate_into=target.views(), accumulate=False, temp=tmp)
         results.append(res)
     for g in range(1, G):
         main.wait_stream(streams[g])
     for p in partials[:G - 1]:
         grads.flat.add_(p.flat)
-    grads.all_reduce_(group)
+    if group is not False:
+        grads.all_reduce_(group)
     return StepResult(results, bounds, color, radii[:, :P])
+
+
+def step_temp_bytes(P: int, V: int, H: int, W: int, M: int, sh_degree: int, R_cap: int) -> int:
+    """Scratch bytes one forward + backward of V views needs (max of the two layouts)."""
+    from . import _native as N
+    lay = N.layout(P, V, H, W, M, sh_degree, int(R_cap))
+    return int(max(lay.temp_bytes, lay.temp_bwd_bytes))
 
 
 class GraphedFitStep:
@@ -206,8 +292,18 @@ class GraphedFitStep:
         V = int(views.viewmatrix.shape[0])
         self.overlap = max(1, min(int(overlap), V))
         self.partials = [PackedGrads(grads.P, grads.M, device=grads.flat.device) for _ in range(self.overlap - 1)]
+        # the graph bakes in raw pointers: its scratch is its own (one buffer per view group), never the
+        # shared per-stream workspace, which another call may regrow (= free) later
+        P = int(gauss["means3D"].shape[0])
+        H, W = int(views.image_height), int(views.image_width)
+        bounds = [shard_views(V, g, self.overlap) for g in range(self.overlap)]
+        caps = list(R_cap) if isinstance(R_cap, (list, tuple)) else [R_cap] * self.overlap
+        if any(c is None for c in caps):
+            raise ValueError("GraphedFitStep needs a fixed R_cap (per view group)")
+        self.temps = [torch.empty(step_temp_bytes(P, len(b), H, W, grads.M, sh_degree, c), dtype=torch.uint8,
+                                  device=grads.flat.device) for b, c in zip(bounds, caps)]
         kw = dict(group=group, sh_degree=sh_degree, scale_modifier=scale_modifier, R_cap=self.R_cap, check="none",
-                  overlap=self.overlap, partials=self.partials)
+                  overlap=self.overlap, partials=self.partials, temps=self.temps)
         torch.cuda.synchronize()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -239,6 +239,27 @@ typedef struct GhrAttributeGrads {
 int ghr_attributes_forward(const GhrAttributeArgs *args, void *cuda_stream);
 int ghr_attributes_backward(const GhrAttributeArgs *args, const GhrAttributeGrads *grads, void *cuda_stream);
 
+/* ---- gradient all-reduce over NVLink peer memory (SURVEY.md §8(e) stage 2) ----
+ * Replaces the NCCL all-reduce Lightning DDP performs for the reference (/root/reference/infer_one_shot.py:631,638)
+ * for ranks of ONE node (one process per GPU): a two-shot, in-place, deterministic sum of a float buffer that
+ * lives in an allocation of this library (the one exception to "the library never allocates": the buffer must
+ * be exportable through CUDA IPC).  Set-up, once: every rank creates its communicator, the host side
+ * all-gathers the GHR_COMM_HANDLE_BYTES-byte handles (any transport: torch.distributed, MPI, a file) and
+ * connects.  Per step: the backward writes its packed gradients into ghr_comm_buffer() and
+ * ghr_comm_allreduce() enqueues ONE kernel on the stream (CUDA-graph capturable, no host argument changes
+ * between calls); every rank must enqueue the same sequence of all-reduces.  A peer that never arrives makes
+ * the kernel give up after ~2 s and sets the error word (ghr_comm_status) instead of hanging the GPU. */
+#define GHR_COMM_MAX_RANKS 8
+#define GHR_COMM_HANDLE_BYTES 128
+typedef struct GhrComm GhrComm;
+int ghr_comm_create(int32_t rank, int32_t world, size_t bytes, GhrComm **out);   /* current device */
+int ghr_comm_handle(GhrComm *comm, void *handle_out /* GHR_COMM_HANDLE_BYTES, host */);
+int ghr_comm_connect(GhrComm *comm, const void *all_handles /* world handles in rank order, host */);
+void *ghr_comm_buffer(GhrComm *comm);                                           /* device pointer, `bytes` long */
+int ghr_comm_allreduce(GhrComm *comm, size_t nfloats /* multiple of 4 */, void *cuda_stream);
+int ghr_comm_status(GhrComm *comm, uint32_t *epochs_done, uint32_t *error /* 0 ok, 1/2 = timed out in barrier A/B */);
+int ghr_comm_destroy(GhrComm *comm);
+
 /* Enqueue an async copy of GhrStatus from `state` into pinned host memory `host_status`. */
 int ghr_read_status_async(const void *state, GhrStatus *host_status, void *cuda_stream);
 

@@ -24,6 +24,10 @@ def cuda_device():
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from guassianhand_b200 import _native
+    from guassianhand_b200 import _native, build
+    # a stale binary would pass or fail against old kernels: libghr.so must be newer than every source
+    # (the box has the sources and the prebuilt .so of the same snapshot; nvcc is there too)
+    if build._stale():
+        build.build()
     _native.lib()     # raises if libghr.so is missing: the GPU tests must never pass on a fallback
     return "cuda:0"

@@ -24,10 +24,18 @@ def test_shard_views_partitions_exactly():
 
 def test_packed_grads_layout():
     g = PackedGrads(P=10, M=0)
-    assert g.floats_per_gaussian == 14 and g.nbytes == 10 * 14 * 4      # 56 B x P
+    assert g.floats_per_gaussian == 14                                  # 56 B x P
+    # every segment is padded to a multiple of 4 floats: 32 + 32 + 40 + 12 + 32 floats for P = 10
+    assert g.offsets == [0, 32, 64, 104, 116] and g.nbytes == 148 * 4
     v = g.views()
     v["dL_dscales"][3, 1] = 5.0
-    assert g.flat[10 * 3 + 3 * 3 + 1] == 5.0                           # aliasing, segment order
+    assert g.flat[32 + 3 * 3 + 1] == 5.0                               # aliasing, segment order
+    # odd Gaussian counts (one reference hand has 49,281 points): every segment still starts 16-byte aligned
+    for P in (1, 7, 49281):
+        go = PackedGrads(P=P, M=0)
+        assert all(o % 4 == 0 for o in go.offsets)
+        assert all(t.data_ptr() % 16 == 0 for t in go.views().values())
+        assert go.views()["dL_drotations"].shape == (P, 4)
     gs = PackedGrads(P=4, M=16)
     assert gs.floats_per_gaussian == 11 + 48 and gs.views()["dL_dsh"].shape == (4, 16, 3)
     assert g.all_reduce_() is None                                      # no process group: no-op

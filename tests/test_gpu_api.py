@@ -220,3 +220,81 @@ def test_overlapped_view_groups_equal_single_chain(cuda_device):
     R, overflow = step.status()
     assert R == r1.R and not overflow
     assert util.rel_err(g3.flat.cpu().numpy(), g1.flat.cpu().numpy().astype(np.float64)) <= 1e-5
+
+
+def test_odd_gaussian_count_packed_grads_and_graph(cuda_device):
+    """One reference hand has 49,281 points (odd): every PackedGrads segment must stay 16-byte aligned (the
+    backward writes rotations with 128-bit stores), eagerly and through the CUDA graph; the graph owns its
+    scratch, so a later call that regrows the shared workspace must not disturb a replay."""
+    from guassianhand_b200 import api
+    from guassianhand_b200.dist import GraphedFitStep, PackedGrads, fit_step_grads
+    dev = cuda_device
+    P = 3001
+    sc = scenes.two_hand_scene(P, seed=21)
+    cams = scenes.fibonacci_cameras(3, 80, 96, seed=21)
+    bg = np.array([0.1, 0.0, 0.2], np.float32)
+    views = util.gpu_views(cams, bg, dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    w = t((np.random.default_rng(6).normal(size=(3, 3, 80, 96)) / 7680).astype(np.float32))
+    # rotations as a 4-byte-aligned view into a packed parameter buffer (flat[6P:10P] with odd P)
+    flat = torch.zeros(14 * P + 1, device=dev)
+    rot_view = flat[6 * P + 1: 10 * P + 1].view(P, 4)
+    rot_view.copy_(t(sc.rotations))
+    assert rot_view.data_ptr() % 16 != 0
+    gauss = dict(means3D=t(sc.means3D), opacities=t(sc.opacities), scales=t(sc.scales), rotations=rot_view,
+                 colors_precomp=t(sc.colors))
+    g1, g2 = PackedGrads(P, 0, device=dev), PackedGrads(P, 0, device=dev)
+    r1 = fit_step_grads(gauss, views, w, g1)
+    tot = {}
+    for v, cam in enumerate(cams):
+        _, g = util.run_oracle(sc, cam, bg, w[v].cpu().numpy())
+        for k, a in g.items():
+            tot[k] = tot.get(k, 0) + a.astype(np.float64)
+    for name, key in (("dL_dmeans3D", "dL_dmeans3D"), ("dL_dscales", "dL_dscales"), ("dL_drotations", "dL_drots"),
+                      ("dL_dcolors", "dL_dcolors")):
+        assert util.rel_err(g1.views()[name].cpu().numpy(), tot[key]) <= 1e-4, name
+    caps = [int(x.R * 1.25) + 1024 for x in fit_step_grads(gauss, views, w, g2, overlap=2).results]
+    step = GraphedFitStep(gauss, views, w, g2, R_cap=caps, overlap=2)
+    step.replay()
+    torch.cuda.synchronize()
+    ref = g2.flat.clone()
+    # force the shared per-stream workspaces to regrow, then replay again: same result
+    big = scenes.two_hand_scene(20000, seed=22)
+    bviews = util.gpu_views(scenes.fibonacci_cameras(2, 160, 160, seed=22), bg, dev)
+    for st in [torch.cuda.current_stream()] + api._streams(torch.device(dev), 1):
+        with torch.cuda.stream(st):
+            api.forward_raw(bviews.cams(), t(big.means3D), t(big.opacities), t(big.scales), t(big.rotations), None, None,
+                            t(big.colors), 0, 1.0)
+    torch.cuda.synchronize()
+    g2.zero_()
+    step.replay()
+    torch.cuda.synchronize()
+    assert not step.status()[1]
+    assert util.rel_err(g2.flat.cpu().numpy(), ref.cpu().numpy().astype(np.float64)) <= 1e-5
+    assert util.rel_err(g2.flat.cpu().numpy(), g1.flat.cpu().numpy().astype(np.float64)) <= 1e-5
+
+
+def test_misaligned_rotations_through_drop_in(cuda_device):
+    """A contiguous [P,4] rotation view that is only 4-byte aligned must render (cloned to an aligned buffer)
+    and receive its gradient."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = cuda_device
+    P = 777
+    sc = scenes.two_hand_scene(P, seed=23)
+    cam = scenes.fibonacci_cameras(1, 64, 64, seed=23)[0]
+    bg = np.zeros(3, np.float32)
+    leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+    xyz, opacity, scaling, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.colors))
+    packed = torch.zeros(4 * P + 1, device=dev)
+    packed[1:] = torch.from_numpy(sc.rotations).to(dev).reshape(-1)
+    packed.requires_grad_(True)
+    rotation = packed[1:].view(P, 4)
+    assert rotation.data_ptr() % 16 != 0
+    m2d = torch.zeros_like(xyz, requires_grad=True)
+    r = GaussianRasterizer(raster_settings=_settings(cam, bg, dev))
+    img, _ = r(means3D=xyz, means2D=m2d, colors_precomp=colors, opacities=opacity, scales=scaling, rotations=rotation)
+    wgt = torch.from_numpy((np.random.default_rng(8).normal(size=(3, 64, 64)) / 4096).astype(np.float32)).to(dev)
+    (img * wgt).sum().backward()
+    f, g = util.run_oracle(sc, cam, bg, wgt.cpu().numpy())
+    assert np.abs(img.detach().cpu().numpy() - f["out_color"]).max() <= 1e-5
+    assert util.rel_err(packed.grad[1:].view(P, 4).cpu().numpy(), g["dL_drots"]) <= 1e-4

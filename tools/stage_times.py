@@ -11,7 +11,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from guassianhand_b200 import _native as NV, scenes  # noqa: E402
+from guassianhand_b200 import _native as NV, build as _build, scenes  # noqa: E402
+if os.environ.get("GHR_TOOL_VARIANT"):      # A/B of a build variant (guassianhand_b200/build.py VARIANTS); tools only
+    NV.LIB_PATH = _build.variant_path(os.environ["GHR_TOOL_VARIANT"])
 from guassianhand_b200.dist import GraphedFitStep, PackedGrads, fit_step_grads  # noqa: E402
 import util  # noqa: E402
 

@@ -78,6 +78,8 @@ def _worker(rank, world, port, out):
         import traceback
         res["error"] = traceback.format_exc()
     out.put((rank, res))
+    out.close()
+    out.join_thread()          # the result has left this process before it exits hard
     # leave without tearing NCCL down: destroy_process_group() with NCCL captured in live graphs can block
     torch.cuda.synchronize()
     os._exit(0)
@@ -94,7 +96,7 @@ def test_sharded_step_allreduce_matches_single_rank(cuda_device, world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(out.get(timeout=300) for _ in range(world))
+    results = dict(out.get(timeout=150) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
     for rank, res in results.items():

@@ -1,35 +1,43 @@
 #!/usr/bin/env python
 """Benchmark of the rasterizer hot path: fwd+bwd views/s on the BASELINE.json C2 scene
-(two-hand, 60k Gaussians, 512x334, precomputed colours), camera-sharded over N GPUs.
+(two-hand, 60k Gaussians, 512x334, precomputed colours), camera-sharded over N GPUs (config 3).
 
-    python bench.py [--gpus N --steps K --warmup W] [--views B] [--impl reference]
+    python bench.py [--gpus N --steps K --warmup W] [--views B] [--impl reference] [--config c2|c1|c4|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one pass of the hot path over one batch: B distinct views (default 8 = the per-GPU share
 of BASELINE config 3, a 64-view fitting step on 8 GPUs) rendered forward + backward by ONE batched
-call chain on every rank, gradients summed over views in the packed buffer, then (N>1) one NCCL
-all-reduce of that buffer.  Weak scaling: B views per rank per step.
-  value   : views/s over all ranks, inputs resident in HBM, CUDA events, max over ranks, L2 flushed
-            between steps.
-  e2e     : same metric through the public autograd API (guassianhand_b200.rasterize_views) with
-            host buffers: H2D of Gaussian attributes + cameras and D2H of gradients + loss inside
-            the timed region (wall clock, max over ranks).
-  roofline: dominant kernel's algorithmic bytes / its live CUDA-event duration vs the measured HBM
-            peak (MEASURED_PEAKS.json), plus an FP32 view of the blend kernels.
-  cpu_baseline / --impl reference: the CPU oracle (oracle/gs_oracle.c, OpenMP, all host threads)
-            on a bounded sample of the same workload.  The reference's own implementation of this
+call chain on every rank, gradients summed over views in the packed buffer, then (N>1) one all-reduce
+of that buffer -- libghr's own NVLink peer-memory kernel (--allreduce peer, default) or NCCL.  Weak
+scaling: B views per rank per step.
+  value   : views/s over all ranks, inputs resident in HBM, CUDA events per step, max over ranks, L2
+            flushed between steps.  `step_ms` carries the per-step distribution of every rank.
+  e2e     : same metric through the graphed step API with host buffers: H2D of Gaussian attributes +
+            cameras and D2H of gradients + loss inside the timed region (wall clock, max over ranks).
+  roofline: SURVEY.md §8(d): the dominant kernel against ITS roof (FP32 for the blend kernels, HBM for
+            the streaming ones), a per-stage table, and the max-sum model of the whole step
+            t_roof = bytes / hbm_peak + 94 I / fp32_peak against the measured step.
+  cpu_baseline / --impl reference: the CPU oracle (oracle/gs_oracle.c, OpenMP, all host threads,
+            pinned) on a bounded sample of the same workload.  The reference's own implementation of this
             path (pip diff-gaussian-rasterization) is absent from /root/reference and from the box,
             so the oracle port is the reference arm (kind "port").
+  --config c1 | c4 | c5: the other BASELINE.json configurations (CPU plumbing case, 1M-Gaussian SH3
+            stress case, 1080p forward-only drive render) as single lines of the same shape.
 """
 import argparse
 import contextlib
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
 
-import numpy as np
+# the CPU arm's OpenMP threads stay where they start (set before any OpenMP runtime is loaded)
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -37,6 +45,8 @@ sys.path.insert(0, ROOT)
 C2 = dict(P=60000, H=512, W=334, pool_views=64, seed=0)
 METRIC = "fwd+bwd views/s @512x334 two-hand Gaussians"
 UNIT = "views/s"
+FP32_NOMINAL_TFLOPS = 74.4      # 148 SMs x 128 lanes x 2 x 1.965 GHz
+CPU_VIEWS_PER_STEP = 4          # the CPU arm's step: a bounded sample of the GPU arm's step
 
 
 def _workload(B):
@@ -96,8 +106,9 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU arm
 
-def cpu_views_per_s(n_views, threads=None, budget_s=None):
-    """fwd+bwd of `n_views` C2 views through the CPU oracle; returns (views/s, views done, threads)."""
+def cpu_views_per_s(n_views, threads=None, budget_s=None, P=None, H=None, W=None, hands=2, sh_degree=None):
+    """fwd+bwd of `n_views` views through the CPU oracle (C2 scene unless P/H/W given); returns
+    (views/s, views done, threads)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from guassianhand_b200 import scenes
     from oracle import oracle_lib as ol
@@ -106,10 +117,11 @@ def cpu_views_per_s(n_views, threads=None, budget_s=None):
     if threads:
         L.gso_set_num_threads(int(threads))
     nthr = L.gso_num_threads()
-    sc = scenes.two_hand_scene(C2["P"], seed=C2["seed"])
-    cams = scenes.fibonacci_cameras(C2["pool_views"], C2["H"], C2["W"], seed=C2["seed"])
+    P, H, W = P or C2["P"], H or C2["H"], W or C2["W"]
+    sc = scenes.two_hand_scene(P, seed=C2["seed"], hands=hands, sh_degree=sh_degree)
+    cams = scenes.fibonacci_cameras(C2["pool_views"], H, W, seed=C2["seed"])
     rng = np.random.default_rng(1)
-    dL = (rng.normal(size=(3, C2["H"], C2["W"])) / (C2["H"] * C2["W"])).astype(np.float32)
+    dL = (rng.normal(size=(3, H, W)) / (H * W)).astype(np.float32)
     bg = np.zeros(3, np.float32)
     done, t0 = 0, time.perf_counter()
     for v in range(n_views):
@@ -127,27 +139,30 @@ def run_reference(args):
     if rank != 0:
         return
     ncpu = os.cpu_count()
-    # warm-up (also builds/loads the oracle), then K steps of one view each
+    # warm-up (also builds/loads the oracle), then K steps of CPU_VIEWS_PER_STEP views each
     for _ in range(max(args.warmup, 1)):
         cpu_views_per_s(1, threads=ncpu)
     t0 = time.perf_counter()
-    vps, done, nthr = cpu_views_per_s(args.steps, threads=ncpu, budget_s=240.0)
+    vps, done, nthr = cpu_views_per_s(args.steps * CPU_VIEWS_PER_STEP, threads=ncpu, budget_s=240.0)
     dt = time.perf_counter() - t0
+    steps_done = max(done // CPU_VIEWS_PER_STEP, 1)
+    sample = (f"{done} single views of the C2 scene ({CPU_VIEWS_PER_STEP} per step: a bounded sample of the GPU arm's "
+              f"{args.views}-view step), oracle/gs_oracle.c with OpenMP on {nthr} pinned threads (upstream "
+              f"diff-gaussian-rasterization is not installable here)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(done, 1), "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": vps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps_done,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * dt / steps_done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": _workload(args.views), "sample": "1 view fwd+bwd per step on the host CPU"},
-        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
-                         "sample": f"{done} single views of the C2 scene, oracle/gs_oracle.c with OpenMP on "
-                                   f"{nthr} threads (upstream diff-gaussian-rasterization is not installable here)"},
+        "config": {"workload": _workload(args.views), "views_per_rank_per_step": args.views, "gaussians": C2["P"],
+                   "image": [C2["H"], C2["W"]], "sample": sample},
+        "cpu_baseline": {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port", "sample": sample},
         "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-# ----------------------------------------------------------------------------- GPU arm
+# ----------------------------------------------------------------------------- roofline
 
 def algorithmic_bytes(stage, P, V, N, T, R, M=0):
     """SURVEY.md §8(d) per-stage algorithmic bytes, for V views with R instances in total."""
@@ -163,6 +178,108 @@ def algorithmic_bytes(stage, P, V, N, T, R, M=0):
         "preprocess_backward": 120 * P * V + sh_b,
     }[stage]
 
+
+BLEND_FLOPS_PER_PAIR = {"blend_forward": 24.0, "blend_backward": 70.0}    # SURVEY.md §8(d); pair = upstream loop trip
+
+
+def roofline_report(stage_ms, step_ms, P, V, N, T, R, I, hbm_peak, fp32_peak, peak_src, traffic_json, M=0):
+    """Per-stage table, the dominant kernel against its own roof, and the max-sum model of the step."""
+    table = {}
+    for k, ms in stage_ms.items():
+        b = algorithmic_bytes(k, P, V, N, T, R, M)
+        row = {"launch_ms": ms, "algorithmic_bytes": b, "hbm_GBps": b / (ms * 1e-3) / 1e9,
+               "hbm_frac": b / (ms * 1e-3) / 1e9 / hbm_peak}
+        if k in BLEND_FLOPS_PER_PAIR:
+            f = BLEND_FLOPS_PER_PAIR[k] * I
+            row.update(bound="fp32", algorithmic_flops=f, fp32_TFLOPs=f / (ms * 1e-3) / 1e12,
+                       fp32_frac=f / (ms * 1e-3) / 1e12 / fp32_peak)
+        else:
+            row["bound"] = "hbm"
+        table[k] = row
+    dom = max(stage_ms, key=stage_ms.get)
+    d = table[dom]
+    if d["bound"] == "fp32":
+        main = {"bound": "fp32", "kernel": dom, "achieved": d["fp32_TFLOPs"], "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": d["fp32_frac"], "algorithmic_flops_per_launch": d["algorithmic_flops"],
+                "flops_per_pair": BLEND_FLOPS_PER_PAIR[dom], "pairs_per_launch": I,
+                "peak_source": f"nominal FP32 FMA ceiling {FP32_NOMINAL_TFLOPS} TFLOP/s (148 SMs x 128 lanes x 2 x 1.965 GHz); "
+                               f"the library's register-operand FFMA / FFMA2 probes measure it live (roofline_fp32)"}
+    else:
+        main = {"bound": "hbm", "kernel": dom, "achieved": d["hbm_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": d["hbm_frac"], "peak_source": peak_src}
+    main.update(traffic=(traffic_json or {}).get(dom), algorithmic_bytes_per_launch=d["algorithmic_bytes"],
+                launch_ms=stage_ms[dom])
+    step_bytes = sum(r["algorithmic_bytes"] for r in table.values())
+    t_roof_ms = (step_bytes / (hbm_peak * 1e9) + 94.0 * I / (fp32_peak * 1e12)) * 1e3
+    main["step"] = {"model": "max-sum (SURVEY.md §8d): t_roof = bytes / hbm_peak + 94 I / fp32_peak; stages are sequential",
+                    "algorithmic_bytes_per_step": step_bytes, "algorithmic_flops_per_step": 94.0 * I,
+                    "t_roof_ms": t_roof_ms, "t_measured_ms": step_ms, "achieved": t_roof_ms / step_ms,
+                    "hbm_peak_GBps": hbm_peak, "fp32_peak_TFLOPs": fp32_peak}
+    main["stages"] = table
+    return main
+
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    return hbm, src, traffic
+
+
+def fp32_probes(NV, torch, dev, stream):
+    """Register-operand dependent-FMA probes of the library: scalar FFMA and packed FFMA2 (TFLOP/s)."""
+    import ctypes as C
+    sink = torch.zeros(1, device=dev)
+    probe_in = torch.tensor([0.999, 1e-3], device=dev)
+    flops = C.c_double()
+
+    def probe(packed):
+        best = 0.0
+        for _ in range(3):
+            ps, pe = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ps.record()
+            NV.check(NV.lib().ghr_fp32_probe(1 << 11, packed, probe_in.data_ptr(), sink.data_ptr(), C.byref(flops),
+                                             stream.cuda_stream), "probe")
+            pe.record()
+            torch.cuda.synchronize()
+            best = max(best, flops.value / (ps.elapsed_time(pe) * 1e-3) / 1e12)
+        return best
+    return probe(0), probe(1)
+
+
+def cull_stats(views):
+    """Evaluated / contributing (pixel, instance) pairs of the blend kernels, from the counting build variant
+    (a separate process: the variant library must not be the one this process measures)."""
+    try:
+        from guassianhand_b200 import build
+        if not os.path.exists(build.variant_path("count")):
+            return None
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cull_stats.py"), "--views", str(views)],
+                           capture_output=True, text=True, timeout=120)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
+def deal_views(costs, block, g, n_blocks, world):
+    """The g-th deal of one block of the view pool to the ranks, balanced on `costs` (every rank computes the
+    same deal).  When one step uses the whole pool (n_blocks == 1) the deals differ by a rotation of the
+    tie-breaking order.  Returns one list of pool indices per rank."""
+    from guassianhand_b200.dist import balanced_shards
+    rot = block[g:] + block[:g] if n_blocks == 1 else block
+    return [[rot[i] for i in sh] for sh in balanced_shards([costs[i] for i in rot], world)]
+
+
+# ----------------------------------------------------------------------------- GPU arm
 
 def run_ours(args):
     import torch
@@ -183,6 +300,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     NV.lib()
+    peer = world > 1 and args.allreduce == "peer"
     B, K, Wm = args.views, args.steps, max(args.warmup, 3)
     P, H, W = C2["P"], C2["H"], C2["W"]
     N, T = H * W, ((W + 15) // 16) * ((H + 15) // 16)
@@ -193,67 +311,71 @@ def run_ours(args):
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
     gauss = dict(means3D=t(sc.means3D), opacities=t(sc.opacities), scales=t(sc.scales), rotations=t(sc.rotations),
                  colors_precomp=t(sc.colors))
-    n_groups = max(1, len(cams) // (B * world)) if B * world <= len(cams) else 1
+    fits = B * world <= len(cams)
+    n_blocks = max(1, len(cams) // (B * world)) if fits else 1
 
-    # which rank renders which view of a step: the step's world*B views are dealt to the ranks so that the
-    # per-rank instance counts are even (dist.balanced_shards; costs = instances of every pool view,
-    # counted once here).  The step ends at the slowest rank.
-    assign = None
-    if world > 1 and B * world <= len(cams):
-        from guassianhand_b200.dist import balanced_shards
+    # ---- which rank renders which view of a step.  The step ends at the slowest rank (the all-reduce), and a
+    # view's time follows its blend pairs (sum of n_contrib), not its instance count: the step's world*B
+    # views are dealt to the ranks so that the per-rank pair sums are even (deal_views; every rank computes
+    # the same deal from the same costs, measured once here).  When one step uses the whole pool (8 GPUs x
+    # 8 views), several different balanced deals rotate so that no rank keeps the same 8 views.
+    deals, costs = None, None
+    if world > 1 and fits:
         costs = []
         for c in cams:
             v1 = util.gpu_views([c], bg, dev)
             r1 = api.forward_raw(v1.cams(), gauss["means3D"], gauss["opacities"], gauss["scales"], gauss["rotations"],
                                  None, None, gauss["colors_precomp"], 0, 1.0)
-            costs.append(r1.R)
-        assign = []
-        for g in range(n_groups):
-            blk = list(range(g * B * world, (g + 1) * B * world))
-            sh = balanced_shards([costs[i] for i in blk], world)
-            assign.append([blk[i] for i in sh[rank]])
+            lay1 = NV.layout(P, 1, H, W, 0, 0, r1.R_cap)
+            nc = r1.state[lay1.off_ncontrib: lay1.off_ncontrib + N * 4].view(torch.int32)
+            costs.append(float(nc.sum(dtype=torch.int64).item()))
+        n_deals = n_blocks if n_blocks > 1 else 4
+        deals = []
+        for g in range(n_deals):
+            b0 = (g % n_blocks) * B * world
+            deals.append(deal_views(costs, list(range(b0, b0 + B * world)), g, n_blocks, world))
+    n_groups = len(deals) if deals is not None else n_blocks
 
-    def group_cams(step):
-        if assign is not None:
-            return [cams[i] for i in assign[step % n_groups]]
-        base = (step % n_groups) * B * world + rank * B
+    def group_cams(g, r=rank):
+        if deals is not None:
+            return [cams[i] for i in deals[g % n_groups][r]]
+        base = (g % n_groups) * B * world + r * B
         return [cams[(base + j) % len(cams)] for j in range(B)]
 
     view_groups = [util.gpu_views(group_cams(g), bg, dev) for g in range(n_groups)]
-    rng = np.random.default_rng(1 + rank)
-    dL = t((rng.normal(size=(B, 3, H, W)) / N).astype(np.float32))
-    grads = PackedGrads(P, 0, device=dev)
+
+    def dL_of(r):
+        return t((np.random.default_rng(1 + r).normal(size=(B, 3, H, W)) / N).astype(np.float32))
+    dL = dL_of(rank)
+    grads = PackedGrads(P, 0, device=dev, peer=peer)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    # ---- calibration: instance counts per view group (poll mode, exact) ----
+    # ---- calibration: instance counts and blend pairs per view group (poll mode, exact) ----
     Rs, pairs = [], []
     for g in range(n_groups):
-        res = fit_step_grads(gauss, view_groups[g], dL, grads)
+        res = fit_step_grads(gauss, view_groups[g], dL, grads, group=False)
         Rs.append(res.R)
         lay = NV.layout(P, B, H, W, 0, 0, res.R_cap)
         nc = res.state[lay.off_ncontrib: lay.off_ncontrib + B * N * 4].view(torch.int32)
         pairs.append(int(nc.sum(dtype=torch.int64).item()))
     R_cap = int(max(Rs) * 1.25) + (1 << 14)
-    lay = NV.layout(P, B, H, W, 0, 0, R_cap)
     # view groups of a step on concurrent streams (dist.fit_step_grads overlap): per-group capacities
     G = max(1, min(int(args.overlap), B))
     caps = R_cap
     if G > 1:
         per_group = [[] for _ in range(G)]
         for g in range(n_groups):
-            r = fit_step_grads(gauss, view_groups[g], dL, grads, overlap=G)
+            r = fit_step_grads(gauss, view_groups[g], dL, grads, overlap=G, group=False)
             for j, x in enumerate(r.results):
                 per_group[j].append(x.R)
         caps = [int(max(v) * 1.25) + (1 << 14) for v in per_group]
-    # per group: init, preprocess, tile scan, duplicate, chunk sort, merge+gather, blend | 2 bwd; + partial-sum adds
-    launches_per_step = (1 + 1 + 1 + 1 + 2 + 1 + 2) * G + (G - 1)
-
-    status_pin = torch.zeros(K + Wm, G, 4, dtype=torch.int64).pin_memory()
+    # per group: init, preprocess, tile scan, duplicate, chunk sort, merge+gather, blend | 2 bwd; + partial-sum
+    # adds; + the all-reduce kernel
+    launches_per_step = (1 + 1 + 1 + 1 + 2 + 1 + 2) * G + (G - 1) + (1 if world > 1 else 0)
 
     def step(i, fe=None, be=None):
-        res = fit_step_grads(gauss, view_groups[i % n_groups], dL, grads, R_cap=R_cap, check="none",
-                             fwd_events=fe, bwd_events=be)
-        return res
+        return fit_step_grads(gauss, view_groups[i % n_groups], dL, grads, R_cap=R_cap, check="none",
+                              fwd_events=fe, bwd_events=be)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -271,7 +393,7 @@ def run_ours(args):
     ev_s = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev_e = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stream = torch.cuda.current_stream()
-    gstep = None
+    status_pin = torch.zeros(K, G, 4, dtype=torch.int64).pin_memory()
     if not args.no_graph:
         # the graph's static camera inputs are blocks of ONE flat buffer, so a step's cameras arrive with a
         # single device-to-device copy
@@ -292,32 +414,72 @@ def run_ours(args):
     else:
         def run_step(i):
             return step(i)
-    for i in range(Wm):
+    # multi-GPU: the first replays of a graph that holds a collective pay one-time costs on some rank (and
+    # every rank waits for it at the all-reduce): at least 20 untimed replays
+    for i in range(max(Wm, 20) if world > 1 else Wm):
         run_step(i)
-    sync_all()
     # clocks are sampled on rank 0 only (it prints the line): NVML calls take the driver's lock, and with one
-    # sampler per rank a delayed launch on ANY rank stalls every rank at the step's all-reduce -- a suspect
-    # for the 8-rank step being 240 us longer than the 1-rank step while its kernels are unchanged
+    # sampler per rank a delayed launch on ANY rank stalls every rank at the step's all-reduce.  The sampler is
+    # created and started BEFORE the barrier (nvmlInit takes milliseconds: started inside the timed loop it made
+    # rank 0 late for its first step, and the other ranks' first interval absorbed the wait in the all-reduce).
     sampler = ClockSampler(local, period=0.005 if world == 1 else 0.02) if rank == 0 else contextlib.nullcontext()
+    n_states = 1
     with sampler as clk:
+        for i in range(2):
+            run_step(i)
+        sync_all()
         for i in range(K):
             flush.zero_()                                   # L2 flush, outside the timed events
             ev_s[i].record()
             res = run_step(i)
             ev_e[i].record()
             states = [x.state for x in res.results] if hasattr(res, "results") else [res.state]
+            n_states = len(states)
             for j, st in enumerate(states):
                 NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), status_pin[i, j].data_ptr(),
                                                         stream.cuda_stream), "status")
         sync_all()
-    total_ms = sum(s.elapsed_time(e) for s, e in zip(ev_s, ev_e))
-    if int((status_pin[:K, :, 1] & 0xFFFFFFFF).sum()) != 0:
+    got_last = grads.flat.double().clone()                  # the last timed step's (all-reduced) gradients
+    per_step = np.array([s.elapsed_time(e) for s, e in zip(ev_s, ev_e)], np.float64)
+    if int((status_pin[:K, :n_states, 1] & 0xFFFFFFFF).sum()) != 0:
         raise RuntimeError("bench: instance capacity overflow inside the timed region; result invalid")
-    tmax = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if peer and grads.comm.status()[1]:
+        raise RuntimeError("bench: the peer all-reduce timed out waiting for a rank")
+    all_steps = torch.tensor(per_step, device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+        gathered = [torch.zeros_like(all_steps) for _ in range(world)]
+        dist.all_gather(gathered, all_steps)
+        all_steps = torch.stack(gathered)
+    else:
+        all_steps = all_steps[None]
+    all_steps = all_steps.cpu().numpy()                       # [world, K] ms
+    total_ms_max = float(all_steps.sum(axis=1).max())
     value = world * B * K / (total_ms_max / 1000.0)
+    med = np.median(all_steps, axis=1)
+    step_stats = {
+        "per_rank": [{"median": float(np.median(r)), "p10": float(np.percentile(r, 10)), "p90": float(np.percentile(r, 90)),
+                      "max": float(r.max()), "mean": float(r.mean())} for r in all_steps],
+        "value_from_median": world * B / (float(med.max()) / 1000.0),
+        "steps": [[round(float(x), 4) for x in r] for r in all_steps] if world > 1 else None,
+        "note": "ms per step, CUDA events around every step on every rank (the all-reduce ends a step at the slowest rank)"}
+
+    # ---- N>1: the all-reduced gradients of the LAST timed step against rank 0 rendering all its views ----
+    ar_check = None
+    if world > 1 and deals is not None:
+        g_last = (K - 1) % n_groups
+        if rank == 0:
+            ref = PackedGrads(P, 0, device=dev)
+            tot = torch.zeros_like(ref.flat, dtype=torch.float64)
+            for r_ in range(world):
+                vr = util.gpu_views(group_cams(g_last, r_), bg, dev)
+                fit_step_grads(gauss, vr, dL_of(r_), ref, group=False)
+                tot += ref.flat.double()
+            err = float((got_last - tot).abs().max() / tot.abs().max())
+            ar_check = {"max_rel_err": err, "ok": bool(err <= 1e-5),
+                        "what": f"packed gradients after the {world}-rank step vs rank 0 rendering all "
+                                f"{world * B} views itself (max |a-b| / max |b|)"}
+        torch.cuda.synchronize()
+        dist.barrier()
 
     # ---- per-stage durations: the same K steps again, launched eagerly with the library's
     # per-stage CUDA events (events cannot be timed from inside a replayed graph) ----
@@ -327,7 +489,6 @@ def run_ours(args):
         flush.zero_()
         step(i, fwd_ev[i], bwd_ev[i])
     sync_all()
-
     stage_ms = {}
     for si, name in enumerate(NV.FWD_STAGES):
         stage_ms[name] = float(np.mean([fwd_ev[i].elapsed_ms(si) for i in range(K)]))
@@ -335,10 +496,232 @@ def run_ours(args):
         stage_ms[name] = float(np.mean([bwd_ev[i].elapsed_ms(si) for i in range(K)]))
     for e in fwd_ev + bwd_ev:
         e.close()
-    n_states = G if not args.no_graph else 1
     R_mean = float(np.mean(status_pin[:K, :n_states, 0].numpy().sum(axis=1)))
     I_mean = float(np.mean(pairs))
 
+    line_extra = {}
+    if world == 1 and not args.quick:
+        line_extra.update(single_gpu_extras(args, torch, api, scenes, util, gauss, cams, bg, dL, grads, dev, t,
+                                            fit_step_grads, GraphedFitStep))
+    fp32_scalar, fp32_packed = fp32_probes(NV, torch, dev, stream)
+
+    # ---- e2e through the graphed step API (GraphedFitStep) with host buffers: the headline e2e ----
+    # Every step uploads ITS Gaussian attributes + cameras from pinned host memory into the step's static
+    # input buffers (two H2D copies), replays the captured forward+backward(+all-reduce), and downloads the
+    # packed gradients + the loss (two D2H copies).  Two graph instances with their own static buffers
+    # alternate, so step i+1 uploads while step i runs; the host reads step i's results after it has
+    # launched step i+1.
+    names = list(gauss.keys())
+    sizes = {k: gauss[k].numel() for k in names}
+    host_flat = torch.cat([gauss[k].detach().reshape(-1).cpu() for k in names]).pin_memory()
+    cam_names = ["viewmatrix", "projmatrix", "campos", "tanfov"]
+    cam_sizes = {k: getattr(view_groups[0], k).numel() for k in cam_names}
+    host_cams = [torch.cat([getattr(vg, k).reshape(-1).cpu() for k in cam_names]).pin_memory() for vg in view_groups]
+
+    def carve(flat, names_, sizes_, like):
+        out, o = {}, 0
+        for k in names_:
+            out[k] = flat[o:o + sizes_[k]].view(like(k).shape)
+            o += sizes_[k]
+        return out
+
+    bg_dev = t(bg)
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    NG = max(1, int(os.environ.get('GHR_BENCH_E2E_SLOTS', '2')))      # (diagnostics: number of alternating graph instances)
+    gslots = []
+    for sl in range(NG):
+        flat, camflat = torch.empty_like(host_flat, device=dev), torch.empty_like(host_cams[0], device=dev)
+        flat.copy_(host_flat)
+        camflat.copy_(host_cams[0])
+        gin = carve(flat, names, sizes, lambda k: gauss[k])
+        cin = carve(camflat, cam_names, cam_sizes, lambda k: getattr(view_groups[0], k))
+        sviews = api.ViewBatch(image_height=H, image_width=W, viewmatrix=cin["viewmatrix"],
+                               projmatrix=cin["projmatrix"], campos=cin["campos"], tanfov=cin["tanfov"], bg=bg_dev)
+        ggr = PackedGrads(P, 0, device=dev, peer=peer)
+        gs = GraphedFitStep(gin, sviews, dL, ggr, R_cap=caps, overlap=G)
+        gslots.append(dict(flat=flat, camflat=camflat, step=gs, grads=ggr,
+                           host_grads=torch.empty(ggr.flat.numel()).pin_memory(), host_loss=torch.zeros(1).pin_memory(),
+                           host_status=torch.zeros(G, 4, dtype=torch.int64).pin_memory(),
+                           ev_up=torch.cuda.Event(), ev_used=torch.cuda.Event(), ev_down=torch.cuda.Event()))
+    g_h2d = host_flat.numel() * 4 + host_cams[0].numel() * 4
+    g_d2h = gslots[0]["host_grads"].numel() * 4 + 4
+    dL_flat = dL.reshape(-1)
+
+    def g_upload(i):
+        sl = gslots[i % NG]
+        with torch.cuda.stream(up):
+            up.wait_event(sl["ev_used"])
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(up)
+            sl["flat"].copy_(host_flat, non_blocking=True)
+            sl["camflat"].copy_(host_cams[i % n_groups], non_blocking=True)
+            c1.record(up)
+            g_copy["h2d"].append((c0, c1))
+            sl["ev_up"].record(up)
+
+    def g_render(i):
+        sl = gslots[i % NG]
+        main.wait_event(sl["ev_up"])
+        main.wait_event(sl["ev_down"])              # the slot's previous results have left the device
+        ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ge0.record(main)
+        res = sl["step"].replay()
+        ge1.record(main)
+        g_gpu.append((ge0, ge1))
+        loss = torch.vdot(res.color.reshape(-1), dL_flat)
+        for j, st in enumerate(sl["step"].states()):
+            NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
+                                                    main.cuda_stream), "status")
+        sl["ev_used"].record(main)
+        down.wait_stream(main)
+        with torch.cuda.stream(down):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(down)
+            sl["host_grads"].copy_(sl["grads"].flat, non_blocking=True)
+            loss.record_stream(down)
+            sl["host_loss"].copy_(loss.reshape(1), non_blocking=True)
+            c1.record(down)
+            g_copy["d2h"].append((c0, c1))
+            sl["ev_down"].record(down)
+
+    def g_collect(i):
+        sl = gslots[i % NG]
+        sl["ev_down"].synchronize()
+        if int((sl["host_status"][:, 1] & 0xFFFFFFFF).sum()) != 0:
+            raise RuntimeError("bench: instance capacity overflow in the e2e graph leg")
+        return float(sl["host_loss"][0])
+
+    g_base = []
+    g_marks, g_host, g_gpu, g_copy = [], {"upload": [], "render": [], "collect": []}, [], {"h2d": [], "d2h": []}
+
+    def g_timed(name, fn, i):
+        t_ = time.perf_counter()
+        r_ = fn(i)
+        g_host[name].append((time.perf_counter() - t_) * 1e3)
+        return r_
+
+    def g_run(n):
+        del g_marks[:]
+        del g_gpu[:]
+        for v_ in g_copy.values():
+            del v_[:]
+        for v_ in g_host.values():
+            del v_[:]
+        for sl in gslots:
+            sl["ev_used"].record(main)
+            sl["ev_down"].record(main)
+        del g_base[:]
+        g_base.append(torch.cuda.Event(enable_timing=True))
+        g_base[0].record(main)
+        g_upload(0)
+        last = None
+        for i in range(n):
+            if i + 1 < n:
+                g_timed("upload", g_upload, i + 1)
+            g_timed("render", g_render, i)
+            if i >= 1:
+                last = g_timed("collect", g_collect, i - 1)
+                g_marks.append(time.perf_counter())
+        last = g_collect(n - 1)
+        g_marks.append(time.perf_counter())
+        torch.cuda.synchronize()
+        return last
+
+    g_run(8 if world > 1 else 4)
+    sync_all()
+    t0 = time.perf_counter()
+    g_loss = g_run(K)
+    g_s = time.perf_counter() - t0
+    g_steps = np.diff(np.array([t0] + g_marks)) * 1e3          # wall ms between consecutive results on this rank
+    g_gpu_ms = [a_.elapsed_time(b_) for a_, b_ in g_gpu]       # device ms of every replay on this rank
+    def rel(ev):
+        return round(g_base[0].elapsed_time(ev), 3)
+    g_mine = {"timeline_ms": [{"h2d": [rel(g_copy["h2d"][i][0]), rel(g_copy["h2d"][i][1])] if i < len(g_copy["h2d"]) else None,
+                               "replay": [rel(g_gpu[i][0]), rel(g_gpu[i][1])],
+                               "d2h": [rel(g_copy["d2h"][i][0]), rel(g_copy["d2h"][i][1])]} for i in range(len(g_gpu))],
+              "replay": [round(float(x), 3) for x in g_gpu_ms],
+              "h2d": [round(a_.elapsed_time(b_), 3) for a_, b_ in g_copy["h2d"]],
+              "d2h": [round(a_.elapsed_time(b_), 3) for a_, b_ in g_copy["d2h"]]}
+    g_all = [None] * world
+    if world > 1:
+        dist.all_gather_object(g_all, g_mine)
+    else:
+        g_all = [g_mine]
+    tg = torch.tensor([g_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+    g_value = world * B * K / float(tg.item())
+
+    if rank == 0:
+        hbm_peak, peak_src, traffic = load_peaks()
+        step_ms = total_ms_max / K
+        roof = roofline_report(stage_ms, step_ms, P, B, N, T, R_mean, I_mean, hbm_peak, FP32_NOMINAL_TFLOPS, peak_src,
+                               traffic)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": _workload(B), "views_per_rank_per_step": B, "gaussians": P, "image": [H, W],
+                       "instances_per_step": R_mean, "blend_pairs_per_step": I_mean, "R_cap": R_cap,
+                       "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"camera-sharded dp{world}" + (" (views dealt to ranks by blend pairs)" if deals else ""),
+                       "launch": "eager, one stream" if args.no_graph else
+                       f"CUDA graph replay (1 launch/step) + 1 camera copy; the step's views run as {G} "
+                       f"independent forward->backward chains on {G} streams inside the graph (stage_ms: the same "
+                       f"kernels launched eagerly on one stream)",
+                       "collective": "none (N=1)" if world == 1 else
+                       ("libghr NVLink peer-memory all-reduce kernel (two-shot, in place) of the packed grads (56 B x P), "
+                        "inside the graph" if peer else "NCCL all-reduce of packed grads (56 B x P)")},
+            "roofline": roof,
+            "roofline_fp32": {"peak_tflops_nominal": FP32_NOMINAL_TFLOPS, "probe_ffma_tflops": fp32_scalar,
+                              "probe_ffma2_tflops": fp32_packed,
+                              "note": "dependent-FMA chains with register operands, 128 FMA instructions per loop trip"},
+            "stage_ms": stage_ms,
+            "step_ms": step_stats,
+            "e2e": {"value": g_value, "unit": UNIT, "h2d_bytes_per_step": g_h2d, "d2h_bytes_per_step": g_d2h,
+                    "loss": g_loss,
+                    "step_wall_ms": {"median": float(np.median(g_steps)), "p90": float(np.percentile(g_steps, 90)),
+                                     "max": float(g_steps.max()), "note": "rank 0, wall clock between consecutive results",
+                                     "host_call_ms_max": {k_: float(max(v_)) if v_ else None for k_, v_ in g_host.items()},
+                                     "host_call_ms_median": {k_: float(np.median(v_)) if v_ else None for k_, v_ in g_host.items()},
+                                     "steps": [round(float(x), 3) for x in g_steps],
+                                     "replay_device_ms_per_rank": g_all},
+                    "api": "guassianhand_b200.dist.GraphedFitStep.replay() (captured ghr_forward + ghr_backward"
+                           " [+ all-reduce] of the step's views); per step: H2D of the Gaussian attributes + cameras "
+                           "from pinned host memory into the step's static inputs, D2H of the packed gradients + the "
+                           "loss; two graph instances alternate so uploads overlap the previous step, results read "
+                           "one launch later, wall clock"},
+            "gpu_launches": launches_per_step * K,
+            "clocks": clk.summary(),
+        }
+        if ar_check is not None:
+            line["allreduce_check"] = ar_check
+        line.update(line_extra)
+        if world == 1 and not args.quick:
+            line["cull_efficiency"] = cull_stats(B)
+        if world == 1 and not args.no_cpu:
+            vps, done, nthr = cpu_views_per_s(256, threads=os.cpu_count(), budget_s=12.0)
+            line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
+                                    "sample": f"{done} single views of the same C2 scene, fwd+bwd, "
+                                              f"oracle/gs_oracle.c OpenMP on {nthr} pinned threads"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        # Leave without tearing NCCL down: destroy_process_group() with collectives captured in live
+        # CUDA graphs can block forever (seen at N=2), and the line above is already out.
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def single_gpu_extras(args, torch, api, scenes, util, gauss, cams, bg, dL, grads, dev, t, fit_step_grads,
+                      GraphedFitStep):
+    """N=1 only: single-view latency and the reference-as-shipped call pattern through the drop-in API."""
+    out = {}
+    s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # ---- single-view latency (the shape the reference itself runs: 1 view per call) ----
     v1 = util.gpu_views([cams[0]], bg, dev)
     dL1 = dL[:1].contiguous()
@@ -347,7 +730,6 @@ def run_ours(args):
     for _ in range(5):
         fit_step_grads(gauss, v1, dL1, grads, R_cap=cap1, check="none")
     torch.cuda.synchronize()
-    s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n1 = 50
     s1.record()
     for _ in range(n1):
@@ -356,7 +738,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     single_ms = s1.elapsed_time(e1) / n1
     single_graph_ms = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         g1 = GraphedFitStep(gauss, v1, dL1, grads, R_cap=cap1)
         for _ in range(5):
             g1.replay()
@@ -369,6 +751,10 @@ def run_ours(args):
         single_graph_ms = s1.elapsed_time(e1) / n1
         if g1.status()[1]:
             raise RuntimeError("bench: overflow in the single-view graph")
+    out["single_view"] = {"ms_per_view_eager": single_ms, "views_per_s_eager": 1000.0 / single_ms,
+                          "ms_per_view_graph": single_graph_ms,
+                          "views_per_s_graph": (1000.0 / single_graph_ms) if single_graph_ms else None,
+                          "note": "1 view per call (the shape the reference runs), L2 warm"}
 
     # ---- the reference-as-shipped shape: 98,562 Gaussians, 256x256, one view per
     # call through the drop-in GaussianRasterizer, an RGB render and an all-ones mask render of the same
@@ -376,15 +762,14 @@ def run_ours(args):
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     sc_s = scenes.two_hand_scene(98562, seed=0)
     cam_s = scenes.fibonacci_cameras(4, 256, 256, seed=0)
-    ts = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
-    leafs = [ts(x).requires_grad_(True) for x in (sc_s.means3D, sc_s.opacities, sc_s.scales, sc_s.rotations, sc_s.colors)]
+    leafs = [t(x).requires_grad_(True) for x in (sc_s.means3D, sc_s.opacities, sc_s.scales, sc_s.rotations, sc_s.colors)]
     ones_s = torch.ones_like(leafs[0])
-    w_s = ts((np.random.default_rng(5).normal(size=(3, 256, 256)) / 65536).astype(np.float32))
+    w_s = t((np.random.default_rng(5).normal(size=(3, 256, 256)) / 65536).astype(np.float32))
 
     def settings_of(c, bgv):
         return GaussianRasterizationSettings(
             image_height=c.H, image_width=c.W, tanfovx=c.tanfovx, tanfovy=c.tanfovy, bg=bgv, scale_modifier=1.0,
-            viewmatrix=ts(c.viewmatrix), projmatrix=ts(c.projmatrix), sh_degree=0, campos=ts(c.campos),
+            viewmatrix=t(c.viewmatrix), projmatrix=t(c.projmatrix), sh_degree=0, campos=t(c.campos),
             prefiltered=False, debug=False)
     rs_s = [settings_of(c, torch.zeros(3, device=dev)) for c in cam_s]
 
@@ -415,297 +800,201 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         shipped[name + "_pairs_per_s"] = 40 / (s1.elapsed_time(e1) * 1e-3)
+    out["as_shipped"] = {**shipped, "note": "reference-as-shipped shape: 98,562 Gaussians, 256x256, one view per "
+                         "call through the drop-in GaussianRasterizer + autograd (eager), RGB + all-ones mask "
+                         "render pair fwd+bwd; two_calls = the reference's call pattern unchanged, fused_mask = "
+                         "forward_with_mask (coverage from the same pass)"}
+    return out
 
-    # ---- FP32 peak probes (dependent FMA chains, register operands): scalar FFMA and packed FFMA2 ----
-    import ctypes as C
-    sink = torch.zeros(1, device=dev)
-    probe_in = torch.tensor([0.999, 1e-3], device=dev)
-    flops = C.c_double()
 
-    def probe(packed):
-        best = 0.0
-        for _ in range(3):
-            ps, pe = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ps.record()
-            NV.check(NV.lib().ghr_fp32_probe(1 << 11, packed, probe_in.data_ptr(), sink.data_ptr(), C.byref(flops),
-                                             stream.cuda_stream), "probe")
-            pe.record()
-            torch.cuda.synchronize()
-            best = max(best, flops.value / (ps.elapsed_time(pe) * 1e-3) / 1e12)
-        return best
-    fp32_scalar, fp32_packed = probe(0), probe(1)
-    fp32_peak = max(fp32_scalar, fp32_packed)
+# ----------------------------------------------------------------------------- other BASELINE configs
 
-    # ---- e2e through the public autograd API with host buffers ----
-    # Every step copies ITS inputs (Gaussian attributes + cameras) from pinned host memory to the
-    # device and ITS results (attribute gradients + the loss) back to pinned host memory.  The loop is
-    # software-pipelined the way a fitting loop that keeps the GPU busy is written: inputs are
-    # triple-buffered on a copy stream (step i+1 uploads while step i renders), results leave on a
-    # second stream, and the host reads step i's loss after it has launched step i+2.
-    # host side: ONE pinned block for the Gaussian attributes and one per view group for the cameras
-    # (the device blocks are carved into the per-attribute tensors the API takes), so a step's inputs
-    # are two H2D copies
-    names = list(gauss.keys())
-    sizes = {k: gauss[k].numel() for k in names}
-    host_flat = torch.cat([gauss[k].detach().reshape(-1).cpu() for k in names]).pin_memory()
-    cam_names = ["viewmatrix", "projmatrix", "campos", "tanfov"]
-    cam_sizes = {k: getattr(view_groups[0], k).numel() for k in cam_names}
-    host_cams = [torch.cat([getattr(vg, k).reshape(-1).cpu() for k in cam_names]).pin_memory() for vg in view_groups]
-    NBUF = 3
-    dev_flat = [torch.empty_like(host_flat, device=dev) for _ in range(NBUF)]
-    dev_camflat = [torch.empty_like(host_cams[0], device=dev) for _ in range(NBUF)]
-
-    def carve(flat, names_, sizes_, like):
-        out, o = {}, 0
-        for k in names_:
-            out[k] = flat[o:o + sizes_[k]].view(like(k).shape)
-            o += sizes_[k]
-        return out
-
-    dev_in = [carve(f, names, sizes, lambda k: gauss[k]) for f in dev_flat]
-    dev_cam = [carve(f, cam_names, cam_sizes, lambda k: getattr(view_groups[0], k)) for f in dev_camflat]
-    host = {k: gauss[k] for k in names}
-    host_grads = [{k: torch.empty(gauss[k].shape).pin_memory() for k in names} for _ in range(NBUF)]
-    host_loss = [torch.zeros(1).pin_memory() for _ in range(NBUF)]
-    bg_dev = t(bg)
-    h2d = host_flat.numel() * 4 + host_cams[0].numel() * 4
-    d2h = sum(v.numel() * 4 for v in host_grads[0].values()) + 4
-    up, down = torch.cuda.Stream(), torch.cuda.Stream()
-    ev_up = [torch.cuda.Event() for _ in range(NBUF)]
-    ev_used = [torch.cuda.Event() for _ in range(NBUF)]     # inputs of slot consumed by the render
-    ev_down = [torch.cuda.Event() for _ in range(NBUF)]
-    main = torch.cuda.current_stream()
-
-    def e2e_upload(i):
-        sl = i % NBUF
-        with torch.cuda.stream(up):
-            up.wait_event(ev_used[sl])
-            dev_flat[sl].copy_(host_flat, non_blocking=True)
-            dev_camflat[sl].copy_(host_cams[i % n_groups], non_blocking=True)
-            ev_up[sl].record(up)
-
-    def e2e_render(i):
-        sl = i % NBUF
-        main.wait_event(ev_up[sl])
-        leaf = {k: v.detach().requires_grad_(True) for k, v in dev_in[sl].items()}
-        c = dev_cam[sl]
-        views = api.ViewBatch(image_height=H, image_width=W, viewmatrix=c["viewmatrix"], projmatrix=c["projmatrix"],
-                              campos=c["campos"], tanfov=c["tanfov"], bg=bg_dev)
-        imgs, _ = api.rasterize_views(leaf["means3D"], leaf["opacities"], views, colors_precomp=leaf["colors_precomp"],
-                                      scales=leaf["scales"], rotations=leaf["rotations"], check="deferred")
-        loss = (imgs * dL).sum()
-        loss.backward()
-        gr = {k: leaf[k].grad for k in host}
-        if world > 1:
-            flat = torch.cat([gr[k].reshape(-1) for k in host])
-            dist.all_reduce(flat)
-            o = 0
-            for k in host:
-                n = host[k].numel()
-                gr[k] = flat[o:o + n].view_as(host[k])
-                o += n
-        ev_used[sl].record(main)
-        down.wait_stream(main)
-        with torch.cuda.stream(down):
-            for k in host:
-                gr[k].record_stream(down)
-                host_grads[sl][k].copy_(gr[k], non_blocking=True)
-            loss.record_stream(down)
-            host_loss[sl].copy_(loss.detach().reshape(1), non_blocking=True)
-            ev_down[sl].record(down)
-
-    def e2e_collect(i):
-        ev_down[i % NBUF].synchronize()
-        return float(host_loss[i % NBUF][0])
-
-    def e2e_run(n):
-        for sl in range(NBUF):
-            ev_used[sl].record(main)
-        e2e_upload(0)
-        for i in range(n):
-            if i + 1 < n:
-                e2e_upload(i + 1)
-            e2e_render(i)
-            if i >= 2:
-                e2e_collect(i - 2)          # the host reads a step's results two launches later
-        if n >= 2:
-            e2e_collect(n - 2)
-        last = e2e_collect(n - 1)
-        torch.cuda.synchronize()
-        api.check_deferred(dev)
-        return last
-
-    e2e_run(4)
-    sync_all()
-    t0 = time.perf_counter()
-    e2e_loss = e2e_run(K)
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K / float(te.item())
-
-    # ---- e2e through the graphed step API (GraphedFitStep) with host buffers: the headline e2e ----
-    # Same contract: every step uploads ITS Gaussian attributes + cameras from pinned host memory into the
-    # step's static input buffers (two H2D copies), replays the captured forward+backward(+all-reduce), and
-    # downloads the packed gradients + the loss (two D2H copies).  Two graph instances with their own
-    # static buffers alternate, so step i+1 uploads while step i runs; the host reads step i's results
-    # after it has launched step i+1.
-    NG = 2
-    gslots = []
-    for sl in range(NG):
-        flat, camflat = torch.empty_like(host_flat, device=dev), torch.empty_like(host_cams[0], device=dev)
-        flat.copy_(host_flat)
-        camflat.copy_(host_cams[0])
-        gin = carve(flat, names, sizes, lambda k: gauss[k])
-        cin = carve(camflat, cam_names, cam_sizes, lambda k: getattr(view_groups[0], k))
-        sviews = api.ViewBatch(image_height=H, image_width=W, viewmatrix=cin["viewmatrix"],
-                               projmatrix=cin["projmatrix"], campos=cin["campos"], tanfov=cin["tanfov"], bg=bg_dev)
-        ggr = PackedGrads(P, 0, device=dev)
-        gs = GraphedFitStep(gin, sviews, dL, ggr, R_cap=caps, overlap=G)
-        gslots.append(dict(flat=flat, camflat=camflat, step=gs, grads=ggr,
-                           host_grads=torch.empty(ggr.flat.numel()).pin_memory(), host_loss=torch.zeros(1).pin_memory(),
-                           host_status=torch.zeros(G, 4, dtype=torch.int64).pin_memory(),
-                           ev_up=torch.cuda.Event(), ev_used=torch.cuda.Event(), ev_down=torch.cuda.Event()))
-    g_h2d = host_flat.numel() * 4 + host_cams[0].numel() * 4
-    g_d2h = gslots[0]["host_grads"].numel() * 4 + 4
-    dL_flat = dL.reshape(-1)
-
-    def g_upload(i):
-        sl = gslots[i % NG]
-        with torch.cuda.stream(up):
-            up.wait_event(sl["ev_used"])
-            sl["flat"].copy_(host_flat, non_blocking=True)
-            sl["camflat"].copy_(host_cams[i % n_groups], non_blocking=True)
-            sl["ev_up"].record(up)
-
-    def g_render(i):
-        sl = gslots[i % NG]
-        main.wait_event(sl["ev_up"])
-        main.wait_event(sl["ev_down"])              # the slot's previous results have left the device
-        res = sl["step"].replay()
-        loss = torch.vdot(res.color.reshape(-1), dL_flat)
-        for j, st in enumerate(sl["step"].states()):
-            NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
-                                                    main.cuda_stream), "status")
-        sl["ev_used"].record(main)
-        down.wait_stream(main)
-        with torch.cuda.stream(down):
-            sl["host_grads"].copy_(sl["grads"].flat, non_blocking=True)
-            loss.record_stream(down)
-            sl["host_loss"].copy_(loss.reshape(1), non_blocking=True)
-            sl["ev_down"].record(down)
-
-    def g_collect(i):
-        sl = gslots[i % NG]
-        sl["ev_down"].synchronize()
-        if int((sl["host_status"][:, 1] & 0xFFFFFFFF).sum()) != 0:
-            raise RuntimeError("bench: instance capacity overflow in the e2e graph leg")
-        return float(sl["host_loss"][0])
-
-    def g_run(n):
-        for sl in gslots:
-            sl["ev_used"].record(main)
-            sl["ev_down"].record(main)
-        g_upload(0)
-        last = None
-        for i in range(n):
-            if i + 1 < n:
-                g_upload(i + 1)
-            g_render(i)
-            if i >= 1:
-                last = g_collect(i - 1)
-        last = g_collect(n - 1)
-        torch.cuda.synchronize()
-        return last
-
-    g_run(4)
-    sync_all()
-    t0 = time.perf_counter()
-    g_loss = g_run(K)
-    g_s = time.perf_counter() - t0
-    tg = torch.tensor([g_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-    g_value = world * B * K / float(tg.item())
-
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
-        dom = max(stage_ms, key=stage_ms.get)
-        alg = algorithmic_bytes(dom, P, B, N, T, R_mean)
-        ach = alg / (stage_ms[dom] * 1e-3) / 1e9
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
-        except Exception:
-            pass
-        step_bytes = sum(algorithmic_bytes(s, P, B, N, T, R_mean) for s in stage_ms)
-        blend_flops = {"blend_forward": 24.0 * I_mean, "blend_backward": 70.0 * I_mean}
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": _workload(B), "views_per_rank_per_step": B, "gaussians": P, "image": [H, W],
-                       "instances_per_step": R_mean, "blend_pairs_per_step": I_mean, "R_cap": R_cap,
-                       "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"camera-sharded dp{world}" + (" (views dealt to ranks by instance count)" if assign else ""),
-                       "launch": "eager, one stream" if args.no_graph else
-                       f"CUDA graph replay (1 launch/step) + 1 camera copy; the step's views run as {G} "
-                       f"independent forward->backward chains on {G} streams inside the graph (stage_ms: the same "
-                       f"kernels launched eagerly on one stream)",
-                       "collective": "none (N=1)" if world == 1 else "NCCL all-reduce of packed grads (56 B x P)"},
-            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": ach / hbm_peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
-                         "launch_ms": stage_ms[dom], "peak_source": peak_src},
-            "roofline_step": {"algorithmic_bytes_per_step": step_bytes,
-                              "achieved_GBps": step_bytes / (total_ms_max / K * 1e-3) / 1e9,
-                              "frac_of_hbm_peak": step_bytes / (total_ms_max / K * 1e-3) / 1e9 / hbm_peak},
-            "roofline_fp32": {"peak_tflops_measured": fp32_peak, "probe_ffma_tflops": fp32_scalar, "probe_ffma2_tflops": fp32_packed, "peak_tflops_nominal": 74.4,
-                              **{k: {"flops_per_launch": f, "achieved_tflops": f / (stage_ms[k] * 1e-3) / 1e12,
-                                     "frac": f / (stage_ms[k] * 1e-3) / 1e12 / fp32_peak}
-                                 for k, f in blend_flops.items()}},
-            "stage_ms": stage_ms,
-            "single_view": {"ms_per_view_eager": single_ms, "views_per_s_eager": 1000.0 / single_ms,
-                            "ms_per_view_graph": single_graph_ms,
-                            "views_per_s_graph": (1000.0 / single_graph_ms) if single_graph_ms else None,
-                            "note": "1 view per call (the shape the reference runs), L2 warm"},
-            "as_shipped": {**shipped, "note": "reference-as-shipped shape: 98,562 Gaussians, 256x256, one view per "
-                           "call through the drop-in GaussianRasterizer + autograd (eager), RGB + all-ones mask "
-                           "render pair fwd+bwd; two_calls = the reference's call pattern unchanged, fused_mask = "
-                           "forward_with_mask (coverage from the same pass)"},
-            "e2e": {"value": g_value, "unit": UNIT, "h2d_bytes_per_step": g_h2d, "d2h_bytes_per_step": g_d2h,
-                    "loss": g_loss,
-                    "api": "guassianhand_b200.dist.GraphedFitStep.replay() (captured ghr_forward + ghr_backward"
-                           " [+ all-reduce] of the step's views); per step: H2D of the Gaussian attributes + cameras "
-                           "from pinned host memory into the step's static inputs, D2H of the packed gradients + the "
-                           "loss; two graph instances alternate so uploads overlap the previous step, results read "
-                           "one launch later, wall clock",
-                    "autograd_api": {"value": e2e_value, "loss": e2e_loss, "h2d_bytes_per_step": h2d,
-                                     "d2h_bytes_per_step": d2h,
-                                     "api": "guassianhand_b200.rasterize_views(check='deferred') + loss.backward() in an "
-                                            "eager Python loop (host-bound at this size), same copies"}},
-            "gpu_launches": launches_per_step * K,
-            "clocks": clk.summary(),
-        }
-        if world == 1 and not args.no_cpu:
-            vps, done, nthr = cpu_views_per_s(64, threads=os.cpu_count(), budget_s=12.0)
-            line["cpu_baseline"] = {"value": vps, "unit": UNIT, "cores": nthr, "kind": "port",
-                                    "sample": f"{done} single views of the same C2 scene, fwd+bwd, "
-                                              f"oracle/gs_oracle.c OpenMP on {nthr} threads"}
+def run_config(args):
+    """--config c1 | c4 | c5: one line per BASELINE.json configuration other than the headline one."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cfg = args.config
+    base = {"steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "n_gpus": world}
+    if cfg == "c1":
+        # BASELINE config 1: single right hand, 30k Gaussians, SH degree 0, one 256x256 camera, fwd+bwd through the
+        # pure-PyTorch CPU re-expression (oracle/torch_ref.py, autograd), all host threads
+        if rank != 0:
+            return
+        from guassianhand_b200 import scenes
+        from oracle import torch_ref
+        nthr = os.cpu_count()
+        torch.set_num_threads(nthr)
+        sc = scenes.two_hand_scene(30000, seed=0, hands=1, sh_degree=0)
+        cam = scenes.fibonacci_cameras(4, 256, 256, seed=0)[0]
+        dL = (np.random.default_rng(1).normal(size=(3, 256, 256)) / 65536).astype(np.float32)
+        bg = np.zeros(3, np.float32)
+        for _ in range(max(1, min(args.warmup, 2))):
+            torch_ref.forward_backward(sc, cam, bg, dL, threads=nthr)
+        n = max(1, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n):
+            torch_ref.forward_backward(sc, cam, bg, dL, threads=nthr)
+        dt = time.perf_counter() - t0
+        vps = n / dt
+        cvps, cdone, cthr = cpu_views_per_s(64, threads=nthr, budget_s=5.0, P=30000, H=256, W=256, hands=1, sh_degree=0)
+        line = {**base, "impl": "reference", "metric": "fwd+bwd views/s @256x256 one-hand 30k Gaussians SH0 (CPU)",
+                "value": vps, "unit": UNIT, "steps": n, "ms_per_step": 1000 * dt / n,
+                "config": {"workload": "BASELINE config 1: one hand, 30000 Gaussians, SH degree 0, 256x256, 1 view fwd+bwd, "
+                                       "oracle/torch_ref.py (pure PyTorch, autograd) on the host CPU"},
+                "cpu_baseline": {"value": vps, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": f"{n} views, torch {torch.__version__} CPU, {torch.get_num_threads()} threads"},
+                "cpu_c_oracle": {"value": cvps, "unit": UNIT, "cores": cthr, "views": cdone,
+                                 "note": "same config through oracle/gs_oracle.c (OpenMP)"},
+                "e2e": {"value": vps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
         print(json.dumps(line), flush=True)
+        return
+    # GPU configs
+    import torch.distributed as dist
+    from guassianhand_b200 import _native as NV, api, scenes
+    from guassianhand_b200.dist import PackedGrads, fit_step_grads
+    import util
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        # Leave without tearing NCCL down: destroy_process_group() with NCCL calls captured in live
-        # CUDA graphs can block forever (seen at N=2), and the line above is already out.
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    bg = np.zeros(3, np.float32)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    K, Wm = args.steps, max(args.warmup, 3)
+    hbm_peak, peak_src, _ = load_peaks()
+    if cfg == "c4":
+        # BASELINE config 4: 1M Gaussians (hand geometry tiled 4x4), SH degree 3, 1024x1024, 16 views fwd+bwd;
+        # views are sharded over the ranks, a step = V views per rank in calls of Bc views
+        P, H, W, M, V = 1000000, 1024, 1024, 16, max(1, 16 // world)
+        Bc = min(4, V)
+        sc = scenes.two_hand_scene(P, seed=0, sh_degree=3, tile=4)
+        cams = scenes.fibonacci_cameras(16, H, W, seed=0)
+        mine = cams[rank * V:(rank + 1) * V]
+        gauss = dict(means3D=t(sc.means3D), opacities=t(sc.opacities), scales=t(sc.scales), rotations=t(sc.rotations),
+                     shs=t(sc.shs))
+        N, T = H * W, ((W + 15) // 16) * ((H + 15) // 16)
+        groups = [util.gpu_views(mine[i:i + Bc], bg, dev, sh_degree=3) for i in range(0, V, Bc)]
+        dL = t((np.random.default_rng(1 + rank).normal(size=(Bc, 3, H, W)) / N).astype(np.float32))
+        grads = PackedGrads(P, M, device=dev, peer=world > 1)
+        caps, Rs, pairs = [], [], []
+        for vg in groups:
+            nv = vg.viewmatrix.shape[0]
+            r = fit_step_grads(gauss, vg, dL[:nv], grads, sh_degree=3, group=False)
+            caps.append(int(r.R * 1.1) + (1 << 16))
+            Rs.append(r.R)
+            lay = NV.layout(P, nv, H, W, M, 3, r.R_cap)
+            pairs.append(int(r.state[lay.off_ncontrib: lay.off_ncontrib + nv * N * 4].view(torch.int32)
+                             .sum(dtype=torch.int64).item()))
+            del r
+
+        def one_step(fe=None, be=None):
+            # (gradients of the calls of a step would be accumulated by the caller; the timing does not depend on it)
+            for gi, (vg, cap) in enumerate(zip(groups, caps)):
+                nv = vg.viewmatrix.shape[0]
+                fit_step_grads(gauss, vg, dL[:nv], grads, sh_degree=3, R_cap=cap, check="none", group=False,
+                               fwd_events=fe[gi] if fe else None, bwd_events=be[gi] if be else None)
+            grads.all_reduce_()
+        for _ in range(Wm):
+            one_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.zero_()
+            evs[i][0].record()
+            one_step()
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        ms = np.array([a.elapsed_time(b) for a, b in evs])
+        tm = torch.tensor([ms.sum()], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total = float(tm.item())
+        value = world * V * K / (total / 1000)
+        fe = [NV.StageEvents(NV.GHR_NSTAGES_FWD) for _ in groups]
+        be = [NV.StageEvents(NV.GHR_NSTAGES_BWD) for _ in groups]
+        flush.zero_()
+        one_step(fe, be)
+        torch.cuda.synchronize()
+        stage_ms = {}
+        for si, name in enumerate(NV.FWD_STAGES):
+            stage_ms[name] = float(sum(e.elapsed_ms(si) for e in fe))
+        for si, name in enumerate(NV.BWD_STAGES):
+            stage_ms[name] = float(sum(e.elapsed_ms(si) for e in be))
+        if rank == 0:
+            roof = roofline_report(stage_ms, total / K, P, V, N, T, float(sum(Rs)), float(sum(pairs)), hbm_peak,
+                                   FP32_NOMINAL_TFLOPS, peak_src, None, M=M)
+            line = {**base, "metric": "fwd+bwd views/s @1024x1024 1M Gaussians SH3", "value": value, "unit": UNIT,
+                    "steps": K, "warmup": Wm, "ms_per_step": total / K,
+                    "config": {"workload": f"BASELINE config 4: 1M Gaussians (two-hand geometry tiled 4x4), SH degree 3, "
+                                           f"1024x1024, {V} views per rank per step in calls of {Bc}, fwd+bwd, eager launches",
+                               "instances_per_step": float(sum(Rs)), "blend_pairs_per_step": float(sum(pairs)),
+                               "l2": "flushed between timed steps"},
+                    "roofline": roof, "stage_ms": stage_ms,
+                    "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                            "note": "not measured for this configuration (see the headline config)"},
+                    "gpu_launches": (13 * len(groups) + (1 if world > 1 else 0)) * K}
+            print(json.dumps(line), flush=True)
+    elif cfg == "c5":
+        # BASELINE config 5: novel-pose drive render, forward only, 1920x1080, 256 poses sharded over 8 ranks
+        # (32 poses per rank; per-pose rigid + noise perturbation of the means), calls of 4 views
+        P, H, W, n_pose, Bc = 60000, 1080, 1920, 32, 4
+        sc = scenes.two_hand_scene(P, seed=0)
+        cams = scenes.fibonacci_cameras(64, H, W, seed=2)
+        rng = np.random.default_rng(10 + rank)
+        base_means = t(sc.means3D)
+        gauss = dict(opacities=t(sc.opacities), scales=t(sc.scales), rotations=t(sc.rotations), colors=t(sc.colors))
+        poses = [base_means + t((rng.normal(size=(1, 3)) * 0.01).astype(np.float32)) +
+                 t((rng.normal(size=sc.means3D.shape) * 2e-4).astype(np.float32)) for _ in range(8)]
+        vgs = [util.gpu_views([cams[(rank * n_pose + i + j) % 64] for j in range(Bc)], bg, dev)
+               for i in range(0, n_pose, Bc)]
+        r0 = api.forward_raw(vgs[0].cams(), poses[0], gauss["opacities"], gauss["scales"], gauss["rotations"], None, None,
+                             gauss["colors"], 0, 1.0)
+        cap = int(r0.R * 1.5) + (1 << 16)
+        del r0
+
+        def one_step():
+            for i, vg in enumerate(vgs):
+                api.forward_raw(vg.cams(), poses[i % len(poses)], gauss["opacities"], gauss["scales"], gauss["rotations"],
+                                None, None, gauss["colors"], 0, 1.0, check="none", R_cap=cap)
+        for _ in range(Wm):
+            one_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.zero_()
+            evs[i][0].record()
+            one_step()
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        ms = np.array([a.elapsed_time(b) for a, b in evs])
+        tm = torch.tensor([ms.sum()], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total = float(tm.item())
+        value = world * n_pose * K / (total / 1000)
+        if rank == 0:
+            line = {**base, "metric": "forward poses/s @1920x1080 two-hand Gaussians", "value": value, "unit": "poses/s",
+                    "steps": K, "warmup": Wm, "ms_per_step": total / K,
+                    "config": {"workload": f"BASELINE config 5: forward only, 1920x1080, 60000 Gaussians, {n_pose} poses per "
+                                           f"rank per step in calls of {Bc} views, pose-sharded (no collective), eager launches",
+                               "l2": "flushed between timed steps"},
+                    "e2e": {"value": None, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                            "note": "not measured for this configuration"},
+                    "gpu_launches": 9 * len(vgs) * K}
+            print(json.dumps(line), flush=True)
+    if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
         os._exit(0)
 
 
@@ -716,12 +1005,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--views", type=int, default=8, help="views per rank per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c1", "c4", "c5"],
+                    help="c2/c3 = the headline workload (c3 = the same under torchrun); c1, c4, c5 = the other BASELINE configs")
+    ap.add_argument("--allreduce", default="peer", choices=["peer", "nccl"],
+                    help="N>1: libghr's NVLink peer-memory all-reduce kernel (default) or NCCL")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="skip the single-view / as-shipped / cull-efficiency extras")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--overlap", type=int, default=2,
                     help="view groups of a step run as concurrent chains on this many streams (graph mode)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.config in ("c1", "c4", "c5"):
+        run_config(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

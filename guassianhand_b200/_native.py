@@ -19,7 +19,7 @@ BWD_STAGES = ["blend_backward", "preprocess_backward"]
 EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",
            "ghr_mark_visible", "ghr_read_status_async", "ghr_event_create", "ghr_event_destroy", "ghr_event_record",
            "ghr_event_elapsed_ms", "ghr_fp32_probe", "ghr_attributes_forward", "ghr_attributes_backward",
-           "ghr_comm_create", "ghr_comm_handle", "ghr_comm_connect", "ghr_comm_buffer", "ghr_comm_allreduce",
+           "ghr_cameras_from_w2c", "ghr_comm_create", "ghr_comm_handle", "ghr_comm_connect", "ghr_comm_buffer", "ghr_comm_allreduce",
            "ghr_comm_status", "ghr_comm_destroy"]
 GHR_COMM_MAX_RANKS, GHR_COMM_HANDLE_BYTES = 8, 128
 GHR_ATTR_XYZ_OFFSET, GHR_ATTR_RESTRICT_OFFSET, GHR_ATTR_CLIP_SCALING = 1, 2, 4
@@ -128,6 +128,9 @@ def lib():
     L.ghr_attributes_forward.argtypes = [C.POINTER(GhrAttributeArgs), _vp]
     L.ghr_attributes_backward.restype = C.c_int
     L.ghr_attributes_backward.argtypes = [C.POINTER(GhrAttributeArgs), C.POINTER(GhrAttributeGrads), _vp]
+    L.ghr_cameras_from_w2c.restype = C.c_int
+    L.ghr_cameras_from_w2c.argtypes = [C.c_int32, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp,
+                                       _vp, _vp]
     L.ghr_comm_create.restype = C.c_int
     L.ghr_comm_create.argtypes = [C.c_int32, C.c_int32, C.c_size_t, C.POINTER(_vp)]
     L.ghr_comm_handle.restype = C.c_int

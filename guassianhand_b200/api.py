@@ -497,6 +497,31 @@ class ViewBatch(NamedTuple):
     sh_degree: int = 0
     scale_modifier: float = 1.0
 
+    @staticmethod
+    def from_w2c(w2c: torch.Tensor, intrinsics: torch.Tensor, image_height: int, image_width: int, bg: torch.Tensor,
+                 sh_degree: int = 0, scale_modifier: float = 1.0, znear: float = 0.01, zfar: float = 1000.0) -> "ViewBatch":
+        """V cameras from world-to-camera matrices [V,4,4] and intrinsics [V,3,3] (CUDA), built by ONE kernel
+        of libghr with no host synchronisation: the device-side replacement of the reference's per-view
+        Camera.from_w2c + getProjectionMatrix_refine + intrinsic_to_fov and of the two math.tan(cuda scalar)
+        syncs (/root/reference/tgs/models/renderer_one_shot.py:61-112, :278-279; its view loop :494-503).
+        The reference ignores the znear / zfar it is given and uses 0.01 / 1000 (:99-100): the defaults."""
+        _require_cuda(w2c, intrinsics)
+        w, k = _f32c(w2c).view(-1, 16), _f32c(intrinsics).view(-1, 9)
+        V = w.shape[0]
+        if k.shape[0] != V:
+            raise RuntimeError("ViewBatch.from_w2c: w2c and intrinsics must hold the same number of views")
+        dev = w.device
+        view = torch.empty(V, 4, 4, dtype=torch.float32, device=dev)
+        proj = torch.empty(V, 4, 4, dtype=torch.float32, device=dev)
+        campos = torch.empty(V, 3, dtype=torch.float32, device=dev)
+        tanfov = torch.empty(V, 2, dtype=torch.float32, device=dev)
+        N.check(N.lib().ghr_cameras_from_w2c(V, w.data_ptr(), k.data_ptr(), int(image_height), int(image_width),
+                                             float(znear), float(zfar), view.data_ptr(), proj.data_ptr(),
+                                             campos.data_ptr(), tanfov.data_ptr(), _raw_stream(dev)),
+                "ghr_cameras_from_w2c")
+        return ViewBatch(image_height=int(image_height), image_width=int(image_width), viewmatrix=view, projmatrix=proj,
+                         campos=campos, tanfov=tanfov, bg=bg, sh_degree=sh_degree, scale_modifier=scale_modifier)
+
     def cams(self) -> _Cams:
         V = self.viewmatrix.shape[0]
         bg = _f32c(self.bg)

@@ -43,6 +43,7 @@ def _stale(out=None):
 # before the first _native.lib() call.
 VARIANTS = {
     "exact": ["-DGHR_EXACT_EXP"],        # libdevice expf + IEEE divide in the blend kernels (parity counting test)
+    "count": ["-DGHR_COUNT"],            # evaluated / contributing pair counters of the blend kernels (tools/cull_stats.py)
     "timeline": ["-DGHR_TIMELINE"],      # per-CTA start/stop clocks of the blend kernels (tools/blend_timeline.py)
     "bwd2": ["-DGHR_BWD_WARPS=2"],       # A/B: two half-tile CTAs per backward unit
     "bwdilp3": ["-DGHR_BWD_ILP=3"],      # A/B: instances per backward iteration

@@ -299,6 +299,20 @@ int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, c
   return GHR_OK;
 }
 
+int ghr_cameras_from_w2c(int32_t V, const float *w2c, const float *K, int32_t H, int32_t W, float znear, float zfar,
+                         float *viewmatrix, float *projmatrix, float *campos, float *tanfov, void *cuda_stream) {
+  if (V < 0 || H < 1 || W < 1 || !(zfar > znear) ||
+      (V > 0 && (!w2c || !K || !viewmatrix || !projmatrix || !campos || !tanfov))) {
+    set_error("ghr_cameras_from_w2c: bad arguments");
+    return GHR_EINVAL;
+  }
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const bool debug = false;
+  GHR_TRY(launch_cameras_from_w2c(V, w2c, K, H, W, znear, zfar, viewmatrix, projmatrix, campos, tanfov, s),
+          "ghr_cameras_from_w2c");
+  return GHR_OK;
+}
+
 int ghr_event_create(void **event_out) {
   if (!event_out) { set_error("ghr_event_create: NULL"); return GHR_EINVAL; }
   cudaEvent_t e;

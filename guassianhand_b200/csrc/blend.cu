@@ -47,6 +47,17 @@ constexpr int kQPad = 8;         // padding entries on both sides of a survivor 
 #endif
 static_assert(kStageN == kSeg, "a forward stage is one backward segment");
 
+#ifdef GHR_COUNT
+// counting variant only (libghr_count.so, bench.py cull_efficiency): (pixel, instance) pairs the blend kernels
+// evaluate after culling and pairs that actually contribute -- [0] fwd evaluated, [1] fwd contributing,
+// [2] bwd evaluated, [3] bwd contributing
+__device__ unsigned long long g_counts[4];
+__device__ __forceinline__ void count_add(int i, uint32_t v) {
+  v = __reduce_add_sync(0xFFFFFFFFu, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&g_counts[i], (unsigned long long)v);
+}
+#endif
+
 #ifdef GHR_TIMELINE
 // profiling variant only (libghr_timeline.so): {start ns, stop ns, smid, work} per CTA of the blend kernels
 constexpr uint32_t kTimelineCap = 1u << 17;
@@ -414,6 +425,9 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       tl_c0 = clock64();
 #endif
       uint32_t lastq = 0;                                     // 1 + queue index of the last blended survivor
+#ifdef GHR_COUNT
+      uint32_t n_contributing = 0;
+#endif
       for (uint32_t b = 0; b < total; b += kIlpF) {
         const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
         const uint32_t packed[4] = {p4.x, p4.y, p4.z, p4.w};
@@ -437,6 +451,9 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
           float r0, g0;
           upk2(mul2(pk2(c.x, c.y), bc2(al[k])), r0, g0);               // upstream's order: (c * alpha) * T
           fwd_blend_step(tc, Tr, Cr, Cg, Cb, lastq, fsub(1.0f, al[k]), al[k], r0, g0, fmul(c.z, al[k]), b + k + 1);
+#ifdef GHR_COUNT
+          n_contributing += lastq == b + k + 1;
+#endif
         }
         if (__all_sync(0xFFFFFFFFu, tc < 0.0001f)) {
           wdone = true;
@@ -445,6 +462,10 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
         }
       }
       if (lastq) last = r * kStageN + ((uint32_t)q[kQPad + lastq - 1] - rec_base) / kRecBytes + 1;
+#ifdef GHR_COUNT
+      count_add(0, total);          // x 32 pixels, applied on the host
+      count_add(1, n_contributing);
+#endif
 #ifdef GHR_TIMELINE
       tl_blend += clock64() - tl_c0;
 #endif
@@ -670,6 +691,10 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
 
   // survivors of this warp's block among the instances that precede the warp's last contributor
   const uint32_t total = build_queue_idx(&s_msk[(uint32_t)g0 & 15u], cnt, wlast - first, hitmask_of_warp(warp), lane, q);
+#ifdef GHR_COUNT
+  count_add(2, total);              // x 64 pixels, applied on the host
+  uint32_t n_contributing = 0;
+#endif
   for (uint32_t b = 0; b < total; b += kIlpB) {
     // phase 1 (independent per instance): alpha, G, 1/(1-alpha), offsets, colour . dL/dpix
     f32x2 al[kIlpB], Gk[kIlpB], omk[kIlpB], rck[kIlpB], dyk[kIlpB], cdk[kIlpB];
@@ -702,6 +727,9 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
       float a0, a1;
       upk2(al[k], a0, a1);
       contrib[k] = a0 != 0.f || a1 != 0.f;
+#ifdef GHR_COUNT
+      n_contributing += (a0 != 0.f) + (a1 != 0.f);
+#endif
       const f32x2 wgt = mul2(al[k], Tr);
       Dn = fma2(cdk[k], wgt, Dn);
       const f32x2 dL_dalpha = fma2(Tr, cdk[k], mul2(add2(Dn, TbN), rck[k]));
@@ -754,6 +782,9 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
     __syncwarp();
     ring_flush(ring, ids, pend, accb, lane);
   }
+#ifdef GHR_COUNT
+  count_add(3, n_contributing);
+#endif
 }
 
 // shared-memory carveout preference, set once per device and kernel
@@ -768,6 +799,18 @@ void prefer_shared(K kern) {
 }
 
 }  // namespace
+
+#ifdef GHR_COUNT
+extern "C" int ghr_debug_counts(unsigned long long *out4, int reset) {
+  cudaDeviceSynchronize();
+  if (out4) cudaMemcpyFromSymbol(out4, g_counts, sizeof(unsigned long long) * 4);
+  if (reset) {
+    const unsigned long long z[4] = {0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_counts, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 #ifdef GHR_TIMELINE
 extern "C" int ghr_debug_timeline(unsigned long long *host_out, unsigned int cap, unsigned int *count) {

@@ -56,12 +56,14 @@ __device__ __forceinline__ void st_peer(float4 *p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-// wait until every rank's flag word of `phase` in MY flag array carries `epoch` (threads 0..world-1 poll)
+// wait until every rank's flag word of `phase` in MY flag array carries `epoch` (threads 0..world-1 poll, with
+// a short sleep between polls: a spinning kernel must not hammer the system-scope path)
 __device__ __forceinline__ void wait_flags(const CommDev &c, int phase, uint32_t epoch, uint32_t *err) {
   if ((int)threadIdx.x < c.world) {
     const uint32_t *f = c.flags[c.rank] + phase * kMaxRanks + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(f) != epoch) {
+      __nanosleep(100);
       if (clock64() - t0 > kSpinLimit) {
         atomicExch(err, 1u + (uint32_t)phase);
         break;
@@ -70,18 +72,39 @@ __device__ __forceinline__ void wait_flags(const CommDev &c, int phase, uint32_t
   }
   __syncthreads();
 }
+__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
-// state words (local): [0] epoch of the last completed all-reduce, [1] CTAs finished, [2] error
+// state words (local): [0] epoch of the last completed all-reduce, [1] CTAs finished, [2] error,
+// [3] "every rank has arrived" of the running all-reduce (set by CTA 0, which alone polls the peers' flags)
 __global__ void __launch_bounds__(kCommThreads)
 peer_allreduce_kernel(CommDev c, size_t n4, uint32_t *__restrict__ st) {
   __shared__ uint32_t s_last;
   const uint32_t epoch = *(volatile uint32_t *)&st[0] + 1u;   // (st[0] is advanced by the grid's last CTA only)
   // barrier A: my gradients are complete (stream order) -- tell every rank, wait for every rank
-  if (blockIdx.x == 0 && (int)threadIdx.x < c.world) {
-    __threadfence_system();
-    st_release_sys(c.flags[threadIdx.x] + 0 * kMaxRanks + c.rank, epoch);
+  if (blockIdx.x == 0) {
+    if ((int)threadIdx.x < c.world) {
+      __threadfence_system();
+      st_release_sys(c.flags[threadIdx.x] + 0 * kMaxRanks + c.rank, epoch);
+    }
+    wait_flags(c, 0, epoch, &st[2]);
+    if (threadIdx.x == 0) st_release_gpu(&st[3], epoch);
+  } else {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(&st[3]) != epoch) {
+        __nanosleep(100);
+        if (clock64() - t0 > kSpinLimit + (kSpinLimit >> 2)) break;     // (CTA 0 has recorded the error)
+      }
+    }
+    __syncthreads();
   }
-  wait_flags(c, 0, epoch, &st[2]);
   // reduce-scatter + all-gather of my slice: sum in rank order, push to every rank
   const size_t slice = (n4 + c.world - 1) / c.world;
   const size_t lo = (size_t)c.rank * slice, hi = lo + slice < n4 ? lo + slice : n4;

@@ -209,6 +209,8 @@ struct GradOut {
 cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const Cameras &cam,
                                        const Gaussians &g, float scale_modifier, const char *state,
                                        const float *acc, const GradOut &go, cudaStream_t s);
+cudaError_t launch_cameras_from_w2c(int V, const float *w2c, const float *K, int H, int W, float znear, float zfar,
+                                    float *view, float *proj, float *campos, float *tanfov, cudaStream_t s);
 cudaError_t launch_mark_visible(int P, const float *means3D, const float *view, uint8_t *present,
                                 cudaStream_t s);
 

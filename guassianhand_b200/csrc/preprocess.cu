@@ -298,7 +298,66 @@ __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, co
   present[i] = pvz > 0.2f;
 }
 
+// Cameras of V views from (w2c, K) on the device: what the reference builds per view on the host with two
+// implicit device->host syncs (/root/reference/tgs/models/renderer_one_shot.py:61-112 Camera.from_w2c +
+// getProjectionMatrix_refine + intrinsic_to_fov, :278-279 math.tan of a CUDA scalar).  One thread per view.
+//   viewmatrix = w2c^T;  projmatrix = viewmatrix @ P^T with P from the intrinsics (off-centre cx, cy, skew);
+//   campos = inverse(viewmatrix)[3, :3];  tanfov = tan(0.5 * 2 atan2(size, 2 f)) evaluated like the reference
+//   (fp32 atan2, fp32 halving, double tan, rounded to fp32).
+__global__ void cameras_from_w2c_kernel(int V, const float *__restrict__ w2c, const float *__restrict__ K, int H, int W,
+                                        float znear, float zfar, float *__restrict__ view, float *__restrict__ proj,
+                                        float *__restrict__ campos, float *__restrict__ tanfov) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const float *m = w2c + 16 * v, *k = K + 9 * v;
+  float vw[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) vw[i][j] = m[4 * j + i];            // transpose
+  const float fx = k[0], sk = k[1], cx = k[2], fy = k[4], cy = k[5];
+  float P[4][4] = {};
+  P[0][0] = fdiv(fmul(2.f, fx), (float)W);
+  P[0][1] = fdiv(fmul(2.f, sk), (float)W);
+  P[0][2] = fadd(-1.f, fmul(2.f, fdiv(cx, (float)W)));
+  P[1][1] = fdiv(fmul(2.f, fy), (float)H);
+  P[1][2] = fadd(-1.f, fmul(2.f, fdiv(cy, (float)H)));
+  P[2][2] = fdiv(fadd(zfar, znear), fsub(zfar, znear));
+  P[2][3] = fdiv(fmul(fmul(-2.f, zfar), znear), fsub(zfar, znear));
+  P[3][2] = 1.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float acc = fmul(vw[i][0], P[j][0]);                            // (view @ P^T)[i][j] = sum_k view[i][k] P[j][k]
+#pragma unroll
+      for (int q = 1; q < 4; q++) acc = ffma(vw[i][q], P[j][q], acc);
+      proj[16 * v + 4 * i + j] = acc;
+      view[16 * v + 4 * i + j] = vw[i][j];
+    }
+  // camera centre: inverse(view)[3, :3] = -(A^-1 t) for w2c = [A t; 0 0 0 1], in double (adjugate / determinant)
+  const double a00 = m[0], a01 = m[1], a02 = m[2], a10 = m[4], a11 = m[5], a12 = m[6], a20 = m[8], a21 = m[9], a22 = m[10];
+  const double t0 = m[3], t1 = m[7], t2 = m[11];
+  const double c00 = a11 * a22 - a12 * a21, c01 = a02 * a21 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+  const double c10 = a12 * a20 - a10 * a22, c11 = a00 * a22 - a02 * a20, c12 = a02 * a10 - a00 * a12;
+  const double c20 = a10 * a21 - a11 * a20, c21 = a01 * a20 - a00 * a21, c22 = a00 * a11 - a01 * a10;
+  const double det = a00 * c00 + a01 * c10 + a02 * c20, id = 1.0 / det;
+  campos[3 * v + 0] = (float)(-(c00 * t0 + c01 * t1 + c02 * t2) * id);
+  campos[3 * v + 1] = (float)(-(c10 * t0 + c11 * t1 + c12 * t2) * id);
+  campos[3 * v + 2] = (float)(-(c20 * t0 + c21 * t1 + c22 * t2) * id);
+  const float fovx = fmul(2.f, atan2f((float)W, fmul(2.f, fx))), fovy = fmul(2.f, atan2f((float)H, fmul(2.f, fy)));
+  tanfov[2 * v + 0] = (float)tan((double)fmul(fovx, 0.5f));
+  tanfov[2 * v + 1] = (float)tan((double)fmul(fovy, 0.5f));
+}
+
 }  // namespace
+
+cudaError_t launch_cameras_from_w2c(int V, const float *w2c, const float *K, int H, int W, float znear, float zfar,
+                                    float *view, float *proj, float *campos, float *tanfov, cudaStream_t s) {
+  if (V <= 0) return cudaSuccess;
+  cameras_from_w2c_kernel<<<(V + 63) / 64, 64, 0, s>>>(V, w2c, K, H, W, znear, zfar, view, proj, campos, tanfov);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &cam, const Gaussians &g,
                               float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,

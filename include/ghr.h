@@ -182,6 +182,15 @@ int ghr_backward(const GhrBackwardArgs *args, void *cuda_stream);
 int ghr_mark_visible(int32_t P, const float *means3D, const float *viewmatrix, const float *projmatrix,
                      uint8_t *present, void *cuda_stream);
 
+/* Cameras of V views on the device, from world-to-camera matrices and intrinsics.
+ * Replaces the per-view host work of /root/reference/tgs/models/renderer_one_shot.py:61-112 (Camera.from_w2c,
+ * getProjectionMatrix_refine, intrinsic_to_fov) and the two math.tan(cuda scalar) host syncs of :278-279:
+ * one launch, no synchronisation.  w2c [V,4,4] and K [V,3,3] row-major device fp32; outputs are exactly the
+ * per-view arrays GhrForwardArgs takes: viewmatrix [V,16] (= w2c^T), projmatrix [V,16] (= viewmatrix @ P^T),
+ * campos [V,3] (= inverse(viewmatrix)[3,:3]), tanfov [V,2].  The reference forces znear = 0.01, zfar = 1000. */
+int ghr_cameras_from_w2c(int32_t V, const float *w2c, const float *K, int32_t H, int32_t W, float znear, float zfar,
+                         float *viewmatrix, float *projmatrix, float *campos, float *tanfov, void *cuda_stream);
+
 /* Thin event helpers so a host without a CUDA binding can time stages (cudaEvent_t as void*). */
 int ghr_event_create(void **event_out);
 int ghr_event_destroy(void *event);

@@ -298,3 +298,50 @@ def test_misaligned_rotations_through_drop_in(cuda_device):
     f, g = util.run_oracle(sc, cam, bg, wgt.cpu().numpy())
     assert np.abs(img.detach().cpu().numpy() - f["out_color"]).max() <= 1e-5
     assert util.rel_err(packed.grad[1:].view(P, 4).cpu().numpy(), g["dL_drots"]) <= 1e-4
+
+
+def test_device_side_cameras_from_w2c(cuda_device):
+    """ViewBatch.from_w2c (ghr_cameras_from_w2c, one launch, no host sync) against the host restatement of the
+    reference's Camera.from_w2c / getProjectionMatrix_refine / intrinsic_to_fov + math.tan
+    (scenes.camera_from_w2c <- renderer_one_shot.py:61-112, :278-279): matrices to 1 ulp, and the same scene
+    rendered through both camera sets gives identical radii and images."""
+    from guassianhand_b200 import api
+    dev = cuda_device
+    H, W, V = 96, 112, 6
+    rng = np.random.default_rng(12)
+    fx = 1300.0 * W / 334.0
+    w2cs, Ks, host = [], [], []
+    for v in range(V):
+        eye = rng.normal(size=3)
+        eye = eye / np.linalg.norm(eye) * rng.uniform(0.8, 1.3)
+        eye[2] = -abs(eye[2]) - 0.3
+        w2c = scenes.look_at_w2c(eye, rng.normal(size=3) * 0.02)
+        K = np.array([[fx * rng.uniform(0.9, 1.1), rng.uniform(-0.5, 0.5), W / 2 + rng.uniform(-5, 5)],
+                      [0, fx * rng.uniform(0.9, 1.1), H / 2 + rng.uniform(-5, 5)], [0, 0, 1]])
+        w2cs.append(w2c.astype(np.float32))
+        Ks.append(K.astype(np.float32))
+        host.append(scenes.camera_from_w2c(w2c, K, H, W))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    vb = api.ViewBatch.from_w2c(t(np.stack(w2cs)), t(np.stack(Ks)), H, W, t(bg))
+    torch.cuda.synchronize()
+    ulp = lambda a, b: np.abs(a.astype(np.float64) - b.astype(np.float64)) / np.maximum(np.spacing(np.abs(b).astype(np.float32)), 1e-45)
+    for v in range(V):
+        assert np.array_equal(vb.viewmatrix[v].cpu().numpy(), host[v].viewmatrix)
+        pm, hm = vb.projmatrix[v].cpu().numpy(), host[v].projmatrix
+        assert np.abs(pm - hm).max() <= 4e-7 * np.abs(hm).max()           # fp32 4-term dot products
+        assert ulp(vb.campos[v].cpu().numpy(), host[v].campos).max() <= 1.0
+        tf = vb.tanfov[v].cpu().numpy()
+        assert ulp(tf, np.array([host[v].tanfovx, host[v].tanfovy], np.float32)).max() <= 2.0
+    # end to end: identical integers, images to 1e-5
+    sc = scenes.two_hand_scene(3000, seed=5)
+    tt = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    args = (tt(sc.means3D), tt(sc.opacities), tt(sc.scales), tt(sc.rotations), None, None, tt(sc.colors), 0, 1.0)
+    r_dev = api.forward_raw(vb.cams(), *args)
+    r_host = api.forward_raw(util.gpu_views(host, bg, dev).cams(), *args)
+    torch.cuda.synchronize()
+    assert (r_dev.radii != r_host.radii).float().mean().item() <= 1e-3     # a 1-ulp tanfov may move a ceil()
+    assert (r_dev.color - r_host.color).abs().max().item() <= 2e-3
+    same = (r_dev.radii == r_host.radii).all().item()
+    if same:
+        assert (r_dev.color - r_host.color).abs().max().item() <= 1e-5

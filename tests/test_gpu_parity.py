@@ -43,10 +43,15 @@ def _check_forward(f, g, img_tol=IMG_TOL):
     assert d_img.max() <= 1e-2 and d_T.max() <= 1e-2
 
 
+GRAD_FLOOR = 1e-5   # per-element bar: |a - b| <= 1e-4 |b| + GRAD_FLOOR max|b| (see util.grad_violation)
+
+
 def _check_grads(oracle_sum, ggrad):
     for ok, gk in GRAD_KEYS.items():
         if gk in ggrad and ok in oracle_sum and oracle_sum[ok].size:
-            assert util.rel_err(ggrad[gk].reshape(oracle_sum[ok].shape), oracle_sum[ok]) <= GRAD_TOL, ok
+            got = ggrad[gk].reshape(oracle_sum[ok].shape)
+            assert util.rel_err(got, oracle_sum[ok]) <= GRAD_TOL, ok
+            assert util.grad_violation(got, oracle_sum[ok], GRAD_TOL, GRAD_FLOOR) <= 1.0, ok
 
 
 def _full_compare(scene, cams, bg, seed=0, **kw):
@@ -83,27 +88,55 @@ def test_ragged_image_sizes(cuda_device, hw):
 
 
 def test_property_random_shapes(cuda_device):
-    """SURVEY.md §8(c) property test: random P, ragged H x W (not multiples of 16), SH degree 0-3 or
-    precomputed colours, scale_modifier != 1, non-black backgrounds, 1-3 views, with Gaussians behind the
-    camera, huge ones and exact depth ties (scenes.random_scene) -- every case to the full parity bar."""
+    """SURVEY.md §8(c) property test: random P (including 0), ragged H x W (not multiples of 16), SH degree 0-3
+    or precomputed colours, scale_modifier != 1, non-black backgrounds, 1-3 views, all-culled scenes,
+    cov3D_precomp, with Gaussians behind the camera, huge ones and exact depth ties (scenes.random_scene) --
+    every case to the full parity bar."""
     from hypothesis import given, settings, strategies as st, HealthCheck
 
-    @settings(max_examples=12, deadline=None, derandomize=True, database=None,
+    @settings(max_examples=100, deadline=None, derandomize=True, database=None,
               suppress_health_check=list(HealthCheck))
-    @given(P=st.integers(1, 3000), H=st.integers(1, 150), W=st.integers(1, 150),
+    @given(P=st.one_of(st.just(0), st.integers(1, 3000)), H=st.integers(1, 150), W=st.integers(1, 150),
            deg=st.sampled_from([None, 0, 1, 2, 3]), mod=st.sampled_from([1.0, 0.6, 1.9]),
-           V=st.integers(1, 3), seed=st.integers(0, 10_000), huge=st.sampled_from([0.0, 0.01, 0.05]))
-    def run(P, H, W, deg, mod, V, seed, huge):
-        sc = scenes.random_scene(P, seed=seed, sh_degree=deg, behind_frac=0.1, huge_frac=huge)
+           V=st.integers(1, 3), seed=st.integers(0, 10_000), huge=st.sampled_from([0.0, 0.01, 0.05]),
+           mode=st.sampled_from(["plain", "plain", "plain", "culled", "cov3d"]))
+    def run(P, H, W, deg, mod, V, seed, huge, mode):
         rng = np.random.default_rng(seed)
         bg = rng.uniform(0, 1, size=3).astype(np.float32)
         if V == 1:
             cams = [scenes.simple_camera(H, W, fx=float(rng.uniform(40, 300)))]
         else:
             cams = scenes.fibonacci_cameras(V, H, W, seed=seed)
-        _full_compare(sc, cams, bg, seed=seed, scale_modifier=mod)
+        if P == 0:
+            _check_empty_scene(cams, bg, deg)
+            return
+        sc = scenes.random_scene(P, seed=seed, sh_degree=deg, behind_frac=0.1, huge_frac=huge)
+        if mode == "culled":
+            sc.means3D[:, :] = sc.means3D - 50.0 * np.stack([c.viewmatrix[:3, 2] for c in cams]).mean(0)   # far behind every camera
+        if mode == "cov3d" and V == 1:
+            f, _ = util.run_oracle(sc, cams[0], bg, scale_modifier=mod)
+            _full_compare(sc, cams, bg, seed=seed, cov3D=f["cov3D"])
+            return
+        info = _full_compare(sc, cams, bg, seed=seed, scale_modifier=mod)
+        if mode == "culled" and V == 1:
+            assert info["R"] == 0
 
     run()
+
+
+def _check_empty_scene(cams, bg, deg):
+    """P = 0 through the raw entry: background image, no instances, empty gradients."""
+    import torch
+    from guassianhand_b200 import api
+    views = util.gpu_views(cams, bg, "cuda:0", sh_degree=deg or 0)
+    z = lambda *s: torch.zeros(*s, device="cuda:0")
+    M = 0 if deg is None else (deg + 1) ** 2
+    res = api.forward_raw(views.cams(), z(0, 3), z(0, 1), z(0, 3), z(0, 4), None, z(0, M, 3) if M else None,
+                          None if M else z(0, 3), deg or 0, 1.0)
+    torch.cuda.synchronize()
+    assert res.R == 0
+    for v in range(len(cams)):
+        assert np.allclose(res.color[v].cpu().numpy(), bg[:, None, None])
 
 
 def test_multi_view_batch_matches_per_view_oracle(cuda_device):

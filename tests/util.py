@@ -99,3 +99,37 @@ def rel_err(a, b):
     if den == 0:
         return float(np.abs(a).max())
     return float(np.abs(a - b).max() / den)
+
+
+def grad_violation(a, b, rtol=1e-4, floor=1e-6):
+    """Per-element gradient bar: max over elements of |a - b| / (rtol |b| + floor max|b|); <= 1 passes.
+    Unlike rel_err (max error over max magnitude) a small-magnitude element cannot hide a large relative error
+    beyond the absolute floor `floor * max|b|` (fp32 accumulation noise of sums whose terms cancel)."""
+    a = np.asarray(a, np.float64).reshape(-1)
+    b = np.asarray(b, np.float64).reshape(-1)
+    if b.size == 0:
+        return 0.0
+    den = rtol * np.abs(b) + floor * np.abs(b).max()
+    if not np.any(den > 0):
+        return float(np.abs(a).max() > 0) * np.inf if np.abs(a).max() > 0 else 0.0
+    return float((np.abs(a - b) / np.maximum(den, 1e-300)).max())
+
+
+class use_library_variant:
+    """Route guassianhand_b200 through a build variant (libghr_<name>.so) inside the `with` block."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        from guassianhand_b200 import _native, build
+        self._native, self._saved = _native, (_native._lib, _native.LIB_PATH)
+        path = build.variant_path(self.name)
+        if not os.path.exists(path) or build._stale(path):
+            build.build(variant=self.name)
+        _native._lib, _native.LIB_PATH = None, path
+        _native.lib()
+        return self
+
+    def __exit__(self, *a):
+        self._native._lib, self._native.LIB_PATH = self._saved

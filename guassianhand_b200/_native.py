@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
-GHR_ABI_VERSION = 9
+GHR_ABI_VERSION = 10
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
 FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
@@ -56,6 +56,7 @@ class GhrForwardArgs(C.Structure):
         ("state", _vp), ("state_bytes", C.c_size_t), ("temp", _vp), ("temp_bytes", C.c_size_t),
         ("dbg_keys_sorted", _vp), ("dbg_point_list", _vp),
         ("host_status", _vp), ("seq", C.c_uint64), ("stage_events", _vp),
+        ("reuse_state", _vp), ("reuse_M", C.c_int32),
     ]
 
 

@@ -17,6 +17,7 @@ import ctypes as C
 import itertools
 import threading
 import time
+import weakref
 from typing import NamedTuple, Optional
 
 import torch
@@ -56,6 +57,7 @@ class _Workspace:
         self.device = device
         self.temp = torch.empty(0, dtype=torch.uint8, device=device)
         self.cap = {}          # (P, V, H, W) -> entries
+        self.hist = {}         # (P, V, H, W) -> [exact instance counts seen, their maximum]
         self.pinned = torch.zeros(64, 4, dtype=torch.int64).pin_memory()   # 64 slots of GhrStatus
         self.pinned_np = self.pinned.numpy()      # same memory: reading a status word costs no tensor op
         self.pinned_ptr = self.pinned.data_ptr()
@@ -73,6 +75,17 @@ class _Workspace:
             c = max(8 * P * V, 1 << 16)
             self.cap[key] = c
         return c
+
+    def note(self, key, R):
+        h = self.hist.setdefault(key, [0, 0])
+        h[0] += 1
+        h[1] = max(h[1], int(R))
+
+    def stable(self, key, cap) -> bool:
+        """check="auto": the capacity has covered several exact counts with room to spare, so the host need not
+        wait for this call's count (it is verified later; an overflow then raises)."""
+        h = self.hist.get(key)
+        return h is not None and h[0] >= 3 and cap >= int(h[1] * 1.3) + 4096
 
     def next_slot(self):
         """Returns (numpy row view [4] int64, host address) of the next pinned GhrStatus slot."""
@@ -96,6 +109,7 @@ class _Workspace:
                 if int(row[2]) != seq:
                     raise RuntimeError("ghr_forward: status report never arrived")
             R, overflow = int(row[0]), int(row[1]) & 0xFFFFFFFF
+            self.note(key, R)
             if not fixed and key in self.cap:
                 self.cap[key] = max(self.cap[key], int(R * 1.5) + (1 << 14))
             if overflow:
@@ -208,13 +222,16 @@ class ForwardResult(NamedTuple):
 def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, colors, sh_degree,
                 scale_modifier, flags=0, check: str = "poll", want_debug: bool = False,
                 R_cap: Optional[int] = None, stage_events=None, want_mask: bool = False, out=None,
-                temp: Optional[torch.Tensor] = None) -> ForwardResult:
+                temp: Optional[torch.Tensor] = None, reuse=None) -> ForwardResult:
     """Enqueue one libghr forward (V views).  check: "poll" (exact: the host waits for the instance
     count, which arrives while the GPU is still sorting/blending, and re-runs on overflow),
     "deferred" (no host wait: the report is verified at the next call on this stream or by
     check_deferred(); an overflow raises there), "none" (caller checks GhrStatus itself; needed
     under CUDA-graph capture).  temp: caller-owned scratch (uint8, >= layout temp_bytes) instead of the
-    per-(device, stream) workspace -- required for anything whose pointers outlive the call (CUDA graphs)."""
+    per-(device, stream) workspace -- required for anything whose pointers outlive the call (CUDA graphs).
+    check="auto": "deferred" once the capacity has proven itself on this shape (_Workspace.stable), else "poll".
+    reuse=(state, M, R): geometry reuse (GhrForwardArgs.reuse_state) -- the state blob of an earlier forward
+    with identical geometry inputs, camera and R_cap (V == 1); only colours are recomputed and the blend runs."""
     L = N.lib()
     dev = means3D.device
     stream = _raw_stream(dev)
@@ -225,6 +242,10 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
     if ws.pending:
         ws.verify_pending()
     cap = int(R_cap) if R_cap is not None else ws.capacity(key, P, cams.V)
+    if reuse is not None:
+        check = "none"                 # the instance count and the capacity are those of the earlier call
+    elif check == "auto":
+        check = "deferred" if ws.stable(key, cap) else "poll"
     while True:
         lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, cap)
         state = torch.empty(lay.state_bytes, dtype=torch.uint8, device=dev)
@@ -255,13 +276,15 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
             a.dbg_keys_sorted, a.dbg_point_list = dbg["keys"].data_ptr(), dbg["point_list"].data_ptr()
         if stage_events is not None:
             a.stage_events = stage_events.ptr()
+        if reuse is not None:
+            a.reuse_state, a.reuse_M = reuse[0].data_ptr(), int(reuse[1])
         row = None
         seq = next(_seq)
         a.seq = seq
         if check in ("poll", "deferred"):
             row, a.host_status = ws.next_slot()
         N.check(L.ghr_forward(C.byref(a), stream), "ghr_forward")
-        R = None
+        R = None if reuse is None else reuse[2]
         if check == "deferred":
             ws.pending.append((row, seq, key, cap, R_cap is not None, ws.slot))
         if check == "poll":
@@ -273,6 +296,7 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
                         raise RuntimeError("ghr_forward: status report never arrived")
             R = int(row[0])
             overflow = int(row[1]) & 0xFFFFFFFF
+            ws.note(key, R)
             if R_cap is None:
                 ws.cap[key] = max(ws.cap[key], int(R * 1.5) + (1 << 14))
             if overflow:
@@ -304,6 +328,8 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     P = means3D.shape[0]
     M = 0 if shs is None or shs.numel() == 0 else shs.shape[1]
     lay = _layout(P, cams.V, cams.H, cams.W, M, sh_degree, R_cap)
+    if ws.pending:
+        ws.verify_pending()            # a deferred capacity report that has arrived (raises on overflow)
     if temp is None:
         temp = ws.get_temp(max(lay.temp_bytes, lay.temp_bwd_bytes))
     elif temp.numel() < lay.temp_bwd_bytes:
@@ -361,6 +387,48 @@ def _opt(t):
     return None if t is None or t.numel() == 0 else _f32a(t)
 
 
+class _GeomCache:
+    """The last single-view forward per device, for the reference's call pattern: every view is rendered twice
+    with IDENTICAL geometry (RGB, then an all-ones mask render; renderer_one_shot.py:338-346, :372-379).  The
+    second call is recognised by the IDENTITY and the autograd version counters of the geometry and camera
+    tensors (the entry keeps them alive, so an address cannot be recycled into a false hit) and reuses the
+    first call's projected geometry, tile ranges, depth order and cull masks (GhrForwardArgs.reuse_state)."""
+    entries = {}
+    hits = 0
+
+    @staticmethod
+    def _ident(t):
+        # (storage address, shape, strides, autograd version); inference tensors have no version: never cached
+        return None if t is None else (t.data_ptr(), tuple(t.shape), t.stride(), t._version)
+
+    @classmethod
+    def lookup(cls, dev_index, tensors, scalars):
+        e = cls.entries.get(dev_index)
+        if e is None:
+            return None
+        _, idents, es, state_ref, M, R_cap, R = e
+        try:
+            if es != scalars or idents != tuple(cls._ident(t) for t in tensors):
+                return None
+        except RuntimeError:
+            return None
+        state = state_ref()
+        if state is None:
+            return None
+        cls.hits += 1
+        return state, M, R_cap, R
+
+    @classmethod
+    def store(cls, dev_index, tensors, scalars, state, M, R_cap, R):
+        try:
+            idents = tuple(cls._ident(t) for t in tensors)
+        except RuntimeError:
+            cls.entries.pop(dev_index, None)
+            return
+        # the entry holds the tensors: while it lives their addresses cannot be handed to other tensors
+        cls.entries[dev_index] = (tensors, idents, scalars, weakref.ref(state), M, R_cap, R)
+
+
 class _RasterizeGaussians(torch.autograd.Function):
     """Same argument order and gradient order as upstream's autograd node."""
 
@@ -375,7 +443,15 @@ class _RasterizeGaussians(torch.autograd.Function):
         means3D_c, opac_c = _f32c(means3D), _f32c(opacities)
         sh_c, col_c, sc_c, rot_c, cov_c = _opt(sh), _opt(colors_precomp), _opt(scales), _opt(rotations), _opt(cov3Ds_precomp)
         args = (cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(rs.sh_degree), float(rs.scale_modifier))
-        if rs.debug:
+        M = 0 if sh_c is None else sh_c.shape[1]
+        dev_index = means3D_c.device.index
+        nz = lambda t_: None if (t_ is None or t_.numel() == 0) else t_
+        gtensors = (means3D, opacities, nz(scales), nz(rotations), nz(cov3Ds_precomp), rs.viewmatrix, rs.projmatrix, rs.campos)
+        gscalars = (means3D.shape[0], cams.H, cams.W, cams.tanfovx, cams.tanfovy, float(rs.scale_modifier), _flags(rs))
+        hit = None if rs.debug else _GeomCache.lookup(dev_index, gtensors, gscalars)
+        if hit is not None:
+            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask, R_cap=hit[2], reuse=(hit[0], hit[1], hit[3]))
+        elif rs.debug:
             cpu_args = [None if t is None or not torch.is_tensor(t) else t.detach().cpu().clone()
                         for t in (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)]
             try:
@@ -385,7 +461,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
         else:
-            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask)
+            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask, check="auto")
+            _GeomCache.store(dev_index, gtensors, gscalars, res.state, M, res.R_cap, res.R)
         ctx.raster_settings = rs
         ctx.want_mask = want_mask
         ctx.cams = cams

@@ -215,6 +215,33 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   Gaussians g{a->means3D, a->opacities, a->scales, a->rotations, a->cov3D_precomp, a->shs, a->colors_precomp};
 
   StageTimer tm{a->stage_events, s};
+  if (a->reuse_state) {
+    // geometry reuse: copy what depends on geometry only, recompute the colours, blend
+    if (d.V != 1) { set_error("ghr_forward: reuse_state needs V == 1"); return GHR_EINVAL; }
+    GhrDims dold = d;
+    dold.M = a->reuse_M;
+    Layout Lold;
+    rc = compute_layout(dold, &Lold);
+    if (rc != GHR_OK) return rc;
+    const char *old_state = (const char *)a->reuse_state;
+    tm.start(0);
+    GHR_TRY(launch_recolor_geom(d, L, Lold, cam, g, old_state, state, a->radii, s), "ghr_forward: recolour geometry");
+    tm.stop(0);
+    tm.start(1);
+    tm.stop(1);
+    tm.start(2);
+    tm.stop(2);
+    tm.start(3);
+    GHR_TRY(launch_reuse_binning(d, L, Lold, old_state, state, a->seq, s), "ghr_forward: reuse binning");
+    tm.stop(3);
+    if (a->host_status)
+      GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),
+              "ghr_forward: status copy");
+    tm.start(4);
+    GHR_TRY(launch_blend_forward(d, L, cam, state, a->out_color, a->out_mask, s), "ghr_forward: blend");
+    tm.stop(4);
+    return GHR_OK;
+  }
   tm.start(0);
   GHR_TRY(cudaMemsetAsync(temp, 0, L.t_zero_bytes, s), "ghr_forward: memset(temp)");
   {

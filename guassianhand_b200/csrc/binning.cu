@@ -809,6 +809,35 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ it
 
 __global__ void init_status_kernel(GhrStatus *st, GhrStatus v) { *st = v; }
 
+// Geometry reuse: the earlier call's status with this call's sequence number and an empty backward unit list
+__global__ void reuse_status_kernel(const GhrStatus *old, GhrStatus *st, uint64_t seq) {
+  GhrStatus v = *old;
+  v.reserved[0] = seq;
+  v.reserved[1] = 0;
+  *st = v;
+}
+
+// Geometry reuse: sorted records and cull masks are copied (they depend on geometry only); the colour of
+// every record comes from this call's geometry block.  One thread per sorted instance, R from the status.
+__global__ void __launch_bounds__(256)
+recolor_records_kernel(uint64_t R_cap, const GhrStatus *__restrict__ old_status, const float4 *__restrict__ old_rec,
+                       const uint8_t *__restrict__ old_masks, const float4 *__restrict__ geom,
+                       float4 *__restrict__ rec, uint8_t *__restrict__ masks) {
+  const uint64_t R = old_status->R < R_cap ? old_status->R : R_cap;
+  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (uint64_t)gridDim.x * blockDim.x) {
+    const float4 q0 = old_rec[3 * r], q1 = old_rec[3 * r + 1];
+    float4 q2 = old_rec[3 * r + 2];
+    const float4 c = geom[4 * (size_t)__float_as_uint(q2.w) + 2];
+    q2.x = c.x;
+    q2.y = c.y;
+    q2.z = c.z;
+    rec[3 * r] = q0;
+    rec[3 * r + 1] = q1;
+    rec[3 * r + 2] = q2;
+    masks[r] = old_masks[r];
+  }
+}
+
 }  // namespace
 
 // Lists longer than kPartMin are depth-partitioned instead of rank-merged.  The partition passes are
@@ -828,6 +857,27 @@ static bool use_partition(const GhrDims &d, const Layout &L) {
 
 cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s) {
   init_status_kernel<<<1, 1, 0, s>>>((GhrStatus *)status, st0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reuse_binning(const GhrDims &d, const Layout &L, const Layout &Lold, const char *old_state,
+                                 char *state, uint64_t seq, cudaStream_t s) {
+  const size_t VT = (size_t)d.V * L.T;
+  reuse_status_kernel<<<1, 1, 0, s>>>((const GhrStatus *)(old_state + Lold.pub.off_status),
+                                      (GhrStatus *)(state + L.pub.off_status), seq);
+  cudaError_t e = cudaMemcpyAsync(state + L.pub.off_ranges, old_state + Lold.pub.off_ranges, VT * 8, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(state + L.pub.off_order, old_state + Lold.pub.off_order, VT * 4, cudaMemcpyDeviceToDevice, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(state + L.pub.off_tilemax, 0, VT * 8, s);
+  if (e != cudaSuccess) return e;
+  if (d.R_cap > 0) {
+    int grid = (int)((d.R_cap + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    recolor_records_kernel<<<grid, 256, 0, s>>>((uint64_t)d.R_cap, (const GhrStatus *)(old_state + Lold.pub.off_status),
+                                                (const float4 *)(old_state + Lold.pub.off_records),
+                                                (const uint8_t *)(old_state + Lold.pub.off_masks),
+                                                (const float4 *)(state + L.pub.off_geom),
+                                                (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks));
+  }
   return cudaGetLastError();
 }
 

@@ -194,6 +194,10 @@ cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &
                               float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,
                               cudaStream_t s);
 cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s);
+cudaError_t launch_recolor_geom(const GhrDims &d, const Layout &L, const Layout &Lold, const Cameras &cam,
+                                const Gaussians &g, const char *old_state, char *state, int32_t *radii, cudaStream_t s);
+cudaError_t launch_reuse_binning(const GhrDims &d, const Layout &L, const Layout &Lold, const char *old_state,
+                                 char *state, uint64_t seq, cudaStream_t s);
 cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
 cudaError_t launch_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
 cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t *dbg_keys,

@@ -290,6 +290,41 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
   }
 }
 
+// Geometry reuse (GhrForwardArgs.reuse_state): the projected record of every Gaussian is copied from the
+// earlier call's state and only its colour is recomputed (colors_precomp, or the SH evaluation in the very
+// order of preprocess_kernel); radii are re-exported.  One thread per Gaussian, one view.
+template <bool kVecSH>
+__global__ void __launch_bounds__(256)
+recolor_geom_kernel(int P, int M, int D, Cameras cam, Gaussians g, const float4 *__restrict__ old_geom,
+                    float4 *__restrict__ geom, uint8_t *__restrict__ clamped, int32_t *__restrict__ radii) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 q0 = old_geom[4 * (size_t)i], q1 = old_geom[4 * (size_t)i + 1], q3 = old_geom[4 * (size_t)i + 3];
+  float4 q2 = old_geom[4 * (size_t)i + 2];
+  uint32_t cbits = 0;
+  if (__float_as_uint(q3.y)) {               // visible: tiles_touched > 0
+    float rgb[3];
+    if (g.colors_precomp) {
+      rgb[0] = g.colors_precomp[3 * i];
+      rgb[1] = g.colors_precomp[3 * i + 1];
+      rgb[2] = g.colors_precomp[3 * i + 2];
+    } else {
+      const float px = g.means3D[3 * i], py = g.means3D[3 * i + 1], pz = g.means3D[3 * i + 2];
+      if (kVecSH) sh_to_rgb_vec(D, reinterpret_cast<const float4 *>(g.shs + (size_t)i * M * 3), px, py, pz, cam.campos, rgb, &cbits);
+      else sh_to_rgb(D, g.shs + (size_t)i * M * 3, px, py, pz, cam.campos, rgb, &cbits);
+    }
+    q2.x = rgb[0];
+    q2.y = rgb[1];
+    q2.z = rgb[2];
+  }
+  geom[4 * (size_t)i] = q0;
+  geom[4 * (size_t)i + 1] = q1;
+  geom[4 * (size_t)i + 2] = q2;
+  geom[4 * (size_t)i + 3] = q3;
+  if (clamped) clamped[i] = (uint8_t)cbits;
+  radii[i] = __float_as_int(q3.x);
+}
+
 __global__ void mark_visible_kernel(int P, const float *__restrict__ means3D, const float *__restrict__ Vm,
                                     uint8_t *__restrict__ present) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +418,18 @@ cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &
   };
   cudaError_t e = vec_sh ? launch(preprocess_kernel<true>) : launch(preprocess_kernel<false>);
   if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_recolor_geom(const GhrDims &d, const Layout &L, const Layout &Lold, const Cameras &cam,
+                                const Gaussians &g, const char *old_state, char *state, int32_t *radii, cudaStream_t s) {
+  if (d.P == 0) return cudaSuccess;
+  const int nb = (d.P + 255) / 256;
+  const bool vec_sh = g.shs && !g.colors_precomp && (d.M * 3) % 4 == 0 && ((uintptr_t)g.shs & 15) == 0;
+  uint8_t *cl = d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr;
+  const float4 *og = (const float4 *)(old_state + Lold.pub.off_geom);
+  if (vec_sh) recolor_geom_kernel<true><<<nb, 256, 0, s>>>(d.P, d.M, d.sh_degree, cam, g, og, (float4 *)(state + L.pub.off_geom), cl, radii);
+  else recolor_geom_kernel<false><<<nb, 256, 0, s>>>(d.P, d.M, d.sh_degree, cam, g, og, (float4 *)(state + L.pub.off_geom), cl, radii);
   return cudaGetLastError();
 }
 

@@ -41,7 +41,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 9
+#define GHR_ABI_VERSION 10
 #define GHR_SEGMENT 128 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
@@ -134,6 +134,14 @@ typedef struct GhrForwardArgs {
   /* optional per-stage timing: HOST array of 2*GHR_NSTAGES_FWD cudaEvent_t (start,stop per stage,
    * created with ghr_event_create), recorded on the stream around each stage; NULL = off. */
   void **stage_events;
+  /* optional geometry reuse (V == 1): the state of an earlier ghr_forward with IDENTICAL geometry inputs
+   * (means3D, opacities, scales/rotations or cov3D_precomp, camera, image size, scale_modifier, R_cap) whose
+   * colours / background / SH inputs may differ -- the reference renders every view twice this way (RGB, then
+   * an all-ones "mask" render, /root/reference/tgs/models/renderer_one_shot.py:338-346, :372-379).  The
+   * projected geometry, tile ranges, depth order and cull masks are copied, only the colours are recomputed
+   * and the blend runs: preprocess, scan, duplication and sort are skipped.  reuse_M = the M of that call. */
+  const void *reuse_state;
+  int32_t reuse_M;
 } GhrForwardArgs;
 
 typedef struct GhrBackwardArgs {

@@ -345,3 +345,70 @@ def test_device_side_cameras_from_w2c(cuda_device):
     same = (r_dev.radii == r_host.radii).all().item()
     if same:
         assert (r_dev.color - r_host.color).abs().max().item() <= 1e-5
+
+
+def test_geometry_cache_second_call_reuses_binning(cuda_device):
+    """The reference renders every view twice with identical geometry (RGB, then colours = 1 / bg = 0 / sh_degree 0,
+    renderer_one_shot.py:338-346, :372-379), passing the SAME tensor objects for geometry and camera.  The second
+    call must take the geometry-reuse path, give bit-identical outputs and gradients to a call that does not,
+    and an in-place change of a geometry tensor must invalidate the cache."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    from guassianhand_b200 import api
+    dev = cuda_device
+    sc = scenes.two_hand_scene(5000, seed=33)
+    cam = scenes.fibonacci_cameras(2, 128, 112, seed=33)[1]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    view, proj, campos = t(cam.viewmatrix.T).transpose(0, 1), t(cam.projmatrix), t(cam.campos)   # shared by both calls
+
+    def settings(bg):
+        return GaussianRasterizationSettings(
+            image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+            viewmatrix=view, projmatrix=proj, sh_degree=0, campos=campos, prefiltered=False, debug=False)
+    w_img = t((np.random.default_rng(0).normal(size=(3, cam.H, cam.W)) / (cam.H * cam.W)).astype(np.float32))
+    w_msk = t((np.random.default_rng(1).normal(size=(3, cam.H, cam.W)) / (cam.H * cam.W)).astype(np.float32))
+
+    def pair(clear_between):
+        leaf = lambda a: torch.from_numpy(a).to(dev).requires_grad_(True)
+        xyz, opacity, scaling, rotation, colors = map(leaf, (sc.means3D, sc.opacities, sc.scales, sc.rotations, sc.colors))
+        m2d = torch.zeros_like(xyz, requires_grad=True)
+        api._GeomCache.entries.clear()
+        img, radii = GaussianRasterizer(raster_settings=settings(t(np.array([0.2, 0.3, 0.4], np.float32))))(
+            means3D=xyz, means2D=m2d, shs=None, colors_precomp=colors, opacities=opacity, scales=scaling,
+            rotations=rotation, cov3D_precomp=None)
+        if clear_between:
+            api._GeomCache.entries.clear()
+        msk, radii2 = GaussianRasterizer(raster_settings=settings(torch.zeros(3, device=dev)))(
+            means3D=xyz, means2D=m2d, colors_precomp=torch.ones_like(xyz), opacities=opacity, scales=scaling,
+            rotations=rotation, cov3D_precomp=None)
+        ((img * w_img).sum() + (msk * w_msk).sum()).backward()
+        torch.cuda.synchronize()
+        return img.detach(), msk.detach(), radii, radii2, [x.grad.clone() for x in (xyz, opacity, scaling, rotation, colors, m2d)]
+
+    h0 = api._GeomCache.hits
+    a = pair(clear_between=False)
+    assert api._GeomCache.hits == h0 + 1                                 # the mask call reused the RGB call's binning
+    b = pair(clear_between=True)
+    assert api._GeomCache.hits == h0 + 1
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    for ga, gb in zip(a[4], b[4]):
+        assert util.rel_err(ga.cpu().numpy(), gb.cpu().numpy().astype(np.float64)) <= 1e-5    # atomics order only
+    # oracle: the mask render is what a stand-alone render of colours = 1 gives
+    ones = scenes.GaussianScene(**{**sc.__dict__})
+    ones.colors = np.ones_like(sc.colors)
+    f2, _ = util.run_oracle(ones, cam, np.zeros(3, np.float32))
+    assert np.abs(a[1].cpu().numpy() - f2["out_color"]).max() <= 1e-5
+    # in-place modification of a geometry tensor between the calls: version bump -> no reuse
+    xyz = t(sc.means3D)
+    opacity, scaling, rotation, colors = t(sc.opacities), t(sc.scales), t(sc.rotations), t(sc.colors)
+    m2d = torch.zeros_like(xyz)
+    api._GeomCache.entries.clear()
+    r = GaussianRasterizer(raster_settings=settings(torch.zeros(3, device=dev)))
+    r(means3D=xyz, means2D=m2d, colors_precomp=colors, opacities=opacity, scales=scaling, rotations=rotation)
+    xyz.add_(0.01)
+    h1 = api._GeomCache.hits
+    img2, _ = r(means3D=xyz, means2D=m2d, colors_precomp=colors, opacities=opacity, scales=scaling, rotations=rotation)
+    assert api._GeomCache.hits == h1
+    moved = scenes.GaussianScene(**{**sc.__dict__})
+    moved.means3D = (sc.means3D + np.float32(0.01)).astype(np.float32)
+    f3, _ = util.run_oracle(moved, cam, np.zeros(3, np.float32))
+    assert np.abs(img2.cpu().numpy() - f3["out_color"]).max() <= 1e-5

@@ -33,9 +33,18 @@ import sys
 import threading
 import time
 
-# the CPU arm's OpenMP threads stay where they start (set before any OpenMP runtime is loaded)
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+# The CPU arm's OpenMP threads stay where they start (set before any OpenMP runtime is loaded) -- in a
+# single-process run only.  Under torchrun every rank would bind its main thread to the FIRST core: two ranks
+# whose hosts spin on an event then share one core and take turns in ~3 ms scheduler slices (seen on 2 x B200:
+# e2e 7.7k views/s with alternating 3.2 ms stalls; the late host makes the other rank wait in the all-reduce).
+if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
+elif hasattr(os, "sched_setaffinity"):
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))      # undo a binding inherited from the launcher
+    except OSError:
+        pass
 
 import numpy as np  # noqa: E402
 
@@ -265,7 +274,10 @@ def cull_stats(views):
             return None
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cull_stats.py"), "--views", str(views)],
                            capture_output=True, text=True, timeout=120)
-        return json.loads(r.stdout.strip().splitlines()[-1])
+        lines = r.stdout.strip().splitlines()
+        if r.returncode != 0 or not lines:
+            return {"error": f"tools/cull_stats.py rc {r.returncode}: {r.stderr.strip()[-300:]}"}
+        return json.loads(lines[-1])
     except Exception as e:  # noqa: BLE001
         return {"error": str(e)[:200]}
 
@@ -425,9 +437,12 @@ def run_ours(args):
     sampler = ClockSampler(local, period=0.005 if world == 1 else 0.02) if rank == 0 else contextlib.nullcontext()
     n_states = 1
     with sampler as clk:
-        for i in range(2):
-            run_step(i)
         sync_all()
+        # two untimed steps after the host-side barrier: ranks leave a device synchronisation up to milliseconds
+        # apart (host wake-up latency), and the all-reduce of a step is what re-aligns the GPUs
+        for i in range(2):
+            flush.zero_()
+            run_step(i)
         for i in range(K):
             flush.zero_()                                   # L2 flush, outside the timed events
             ev_s[i].record()

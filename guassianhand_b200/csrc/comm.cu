@@ -39,11 +39,14 @@ struct CommDev {
 __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+// Flag polls are RELAXED system-scope loads; the acquire is ONE fence after the flag has been seen (a spinning
+// kernel should not issue a system-scope acquire per poll).
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t *p) {
   uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ float4 ld_peer(const float4 *p) {
   float4 v;
   asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
@@ -62,22 +65,23 @@ __device__ __forceinline__ void wait_flags(const CommDev &c, int phase, uint32_t
   if ((int)threadIdx.x < c.world) {
     const uint32_t *f = c.flags[c.rank] + phase * kMaxRanks + threadIdx.x;
     const long long t0 = clock64();
-    while (ld_acquire_sys(f) != epoch) {
-      __nanosleep(100);
+    while (ld_relaxed_sys(f) != epoch) {
+      __nanosleep(200);
       if (clock64() - t0 > kSpinLimit) {
         atomicExch(err, 1u + (uint32_t)phase);
         break;
       }
     }
+    fence_acq_rel_sys();
   }
   __syncthreads();
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
   uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -98,10 +102,11 @@ peer_allreduce_kernel(CommDev c, size_t n4, uint32_t *__restrict__ st) {
   } else {
     if (threadIdx.x == 0) {
       const long long t0 = clock64();
-      while (ld_acquire_gpu(&st[3]) != epoch) {
-        __nanosleep(100);
+      while (ld_relaxed_gpu(&st[3]) != epoch) {
+        __nanosleep(200);
         if (clock64() - t0 > kSpinLimit + (kSpinLimit >> 2)) break;     // (CTA 0 has recorded the error)
       }
+      fence_acq_rel_sys();      // (cumulative: CTA 0 acquired the peers' releases before it released st[3])
     }
     __syncthreads();
   }

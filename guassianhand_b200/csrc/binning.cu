@@ -72,29 +72,35 @@ constexpr int kSlabs = 256;            // depth slabs of a heavy tile (fine hist
 // totals, then walks its run again.
 __global__ void __launch_bounds__(kScanThreads1)
 tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hchunk_cap, uint32_t heavy_cap,
-                          uint32_t part_min, const uint32_t *__restrict__ tile_count, uint2 *__restrict__ ranges,
+                          uint32_t part_min, uint32_t big_max, const uint32_t *__restrict__ tile_count,
+                          uint2 *__restrict__ ranges,
                           uint32_t *__restrict__ order, uint4 *__restrict__ items, uint2 *__restrict__ hchunks,
                           uint32_t *__restrict__ heavy, uint32_t *__restrict__ heavy_id,
                           uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
   __shared__ uint64_t s_warp[kScanThreads1 / 32];
   __shared__ uint32_t s_wl[kScanThreads1 / 32], s_wh[kScanThreads1 / 32], s_whc[kScanThreads1 / 32];
   __shared__ uint32_t s_cls[kClasses + 1], s_cur[kClasses + 1];
+  __shared__ uint32_t s_nbig;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid < kClasses) s_cls[tid] = 0;
+  if (tid == 0) s_nbig = 0;
   const int per = (VT + kScanThreads1 - 1) / kScanThreads1;
   const int t0 = min(VT, tid * per), t1 = min(VT, t0 + per);
   uint64_t sum = 0;
   uint32_t lsum = 0, hsum = 0, hcsum = 0;      // light tiles, heavy tiles, heavy chunks of this run
+  uint32_t nbig = 0;                           // lists longer than a chunk (= the head of order[])
   for (int t = t0; t < t1; t++) {
     const uint32_t c = tile_count[t];
     sum += c;
+    nbig += c > (uint32_t)kChunk;
     if (c > part_min) {
       hsum++;
       hcsum += (c + kChunk - 1) / kChunk;
-    } else {
+    } else if (!(c > (uint32_t)kChunk && c <= big_max)) {   // (a big list is ONE item of sort_big_kernel)
       lsum += (c + kChunk - 1) / kChunk;       // one final item, or plain chunks finished by the rank merge
     }
   }
+  nbig = __reduce_add_sync(0xFFFFFFFFu, nbig);
   uint64_t incl = sum;
   uint32_t lincl = lsum, hincl = hsum, hcincl = hcsum;
 #pragma unroll
@@ -110,11 +116,13 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
       hcincl += hcup;
     }
   }
+  __syncthreads();                             // (s_nbig = 0 above)
   if (lane == 31) {
     s_warp[warp] = incl;
     s_wl[warp] = lincl;
     s_wh[warp] = hincl;
     s_whc[warp] = hcincl;
+    if (nbig) atomicAdd(&s_nbig, nbig);
   }
   __syncthreads();
   uint64_t start = incl - sum, total = 0;
@@ -153,7 +161,7 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
         }
         hoff++;
         hcoff += m;
-      } else {
+      } else if (!(c > (uint32_t)kChunk && c <= big_max)) {
         for (uint32_t q = 0; q < m && loff + q < item_cap; q++)
           items[loff + q] = make_uint4((uint32_t)t, q * kChunk, min((uint32_t)kChunk, c - q * kChunk),
                                        m == 1 ? kItemFinal : 0u);
@@ -169,6 +177,7 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
     misc[0] = ltotal < item_cap ? ltotal : item_cap;
     misc[1] = hctotal < hchunk_cap ? hctotal : hchunk_cap;
     misc[2] = htotal < heavy_cap ? htotal : heavy_cap;
+    misc[3] = s_nbig;
     uint32_t acc = 0;
     for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
       s_cur[c] = acc;
@@ -203,10 +212,12 @@ duplicate_kernel(int P, int gx, int gy, int T, int smem_tiles, uint64_t R_cap, c
   uint32_t depth_bits = 0, gid = 0;
   if (i < P) {
     gid = (uint32_t)v * (uint32_t)P + (uint32_t)i;
+    // (three independent loads: issued together, not one after the visibility test)
     const float4 q3 = geom[4 * (size_t)gid + 3];
+    const float4 q0 = geom[4 * (size_t)gid];
+    const float q2w = geom[4 * (size_t)gid + 2].w;
     if (__float_as_uint(q3.y)) {
-      const float4 q0 = geom[4 * (size_t)gid];
-      depth_bits = __float_as_uint(geom[4 * (size_t)gid + 2].w);
+      depth_bits = __float_as_uint(q2w);
       rect_of(q0.x, q0.y, __float_as_int(q3.x), gx, gy, minx, miny, maxx, maxy);
     }
   }
@@ -530,30 +541,45 @@ __device__ __forceinline__ void emit_instance(size_t r, uint32_t depth_bits, uin
 // distribution) is re-sorted by stable LSD radix passes over every key byte that varies.  Either way
 // the result is the total order on (depth bits, index).
 constexpr uint32_t kMaxRun = 32;
+
+// shared memory of one sort CTA (dynamic): keys | bin counts / offsets (aliased by the fallback passes'
+// counters) | per-warp record staging of the final gather
 template <int kSortThreads>
-__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
-sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ items, const uint32_t *__restrict__ misc,
-                   const uint2 *__restrict__ ranges, uint2 *inst, uint2 *inst_b, const float4 *__restrict__ geom,
-                   float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
-                   uint32_t *__restrict__ dbg_plist) {
+struct SortSmem {
+  static constexpr int kWarps = kSortThreads / 32;
+  static constexpr int kItemMax = kSortThreads * kSortItems;
+  static constexpr size_t kHistBytes =
+      ((sizeof(ChunkSort<kSortThreads>) > (size_t)kItemMax * 4 ? sizeof(ChunkSort<kSortThreads>) : (size_t)kItemMax * 4) + 15) / 16 * 16;
+  static constexpr size_t kOffHist = (size_t)kItemMax * 8;
+  static constexpr size_t kOffStage = kOffHist + kHistBytes;
+  static constexpr size_t kBytes = kOffStage + (size_t)kWarps * 96 * 16;
+};
+
+template <int kSortThreads>
+__device__ __forceinline__ void sort_item(const uint4 item, const uint2 range, int P, FastDiv dT, FastDiv dgx, uint2 *inst,
+                                          uint2 *inst_b, const float4 *__restrict__ geom, float4 *__restrict__ records,
+                                          uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
+                                          uint32_t *__restrict__ dbg_plist) {
   constexpr int kSortWarps = kSortThreads / 32;
   constexpr int kChunk = kSortThreads * kSortItems;
   constexpr int kBins = kChunk;                       // 8 bins per thread in the bin scan
-  constexpr int kBinBits = kSortThreads == 256 ? 11 : 12;
+  constexpr int kBinBits = kSortThreads == 256 ? 11 : (kSortThreads == 512 ? 12 : 13);
   static_assert(kBins == 1 << kBinBits, "chunk size");
-  extern __shared__ __align__(16) uint64_t s_buf[];   // [kChunk] keys
-  __shared__ union {
-    ChunkSort<kSortThreads> cs;   // fallback passes only
-    uint32_t hist[kBins];         // bin counts, then bin offsets
-  } U;
+  using SM = SortSmem<kSortThreads>;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  uint64_t *s_buf = reinterpret_cast<uint64_t *>(s_dyn);                       // [kChunk] keys
+  struct HistU {
+    union {
+      ChunkSort<kSortThreads> cs;   // fallback passes only
+      uint32_t hist[kBins];         // bin counts, then bin offsets
+    };
+  };
+  HistU &U = *reinterpret_cast<HistU *>(s_dyn + SM::kOffHist);
+  float4 (*s_stage)[96] = reinterpret_cast<float4 (*)[96]>(s_dyn + SM::kOffStage);   // record staging of the final gather
   __shared__ uint32_t s_scan[kSortWarps];
   __shared__ uint32_t s_dmin, s_dmax;
   __shared__ unsigned long long s_and, s_or;
-  __shared__ __align__(16) float4 s_stage[kSortWarps][96];   // record staging of the final gather
-  if (blockIdx.x >= misc[0]) return;
-  const uint4 item = items[blockIdx.x];
   const uint32_t vt = item.x;
-  const uint2 range = ranges[vt];
   const uint32_t cstart = range.x + item.y;
   if (cstart >= range.y) return;                       // item of a list clamped by an instance-capacity overflow
   const uint32_t n = min(min((uint32_t)kChunk, item.z), range.y - cstart);
@@ -562,6 +588,9 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
   const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
   if (item.w & kItemSrcB) inst = inst_b;
   uint2 *src = inst + cstart;
+  // keys per thread this item needs: every per-key loop below stops there (a 300-instance list must not pay
+  // for eight rounds; uniform over the CTA)
+  const int it = (int)((n + kSortThreads - 1) / kSortThreads);
   if (tid == 0) {
     s_dmin = 0xFFFFFFFFu;
     s_dmax = 0u;
@@ -577,8 +606,9 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
 #pragma unroll
     for (int i = 0; i < kSortItems; i++) {
       const uint32_t k = i * kSortThreads + tid;
-      e[i] = k < n ? src[k] : make_uint2(0u, 0u);
-      if (k < n) {
+      e[i] = make_uint2(0u, 0u);
+      if (i < it && k < n) {
+        e[i] = src[k];
         dmin = min(dmin, e[i].x);
         dmax = max(dmax, e[i].x);
       }
@@ -602,7 +632,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
     for (int i = 0; i < kSortItems; i++) {
       const uint32_t k = i * kSortThreads + tid;
       slot[i] = 0;
-      if (k < n) {
+      if (i < it && k < n) {
         const uint32_t rel = e[i].x - dmin;
         slot[i] = atomicAdd(&U.hist[rel >> shift0], 1u);
         const uint64_t key = ((uint64_t)rel << 32) | (e[i].y - gbase);
@@ -653,7 +683,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
 #pragma unroll
   for (int i = 0; i < kSortItems; i++) {
     const uint32_t k = i * kSortThreads + tid;
-    if (k < n) {
+    if (i < it && k < n) {
       const uint32_t rel = e[i].x - dmin;
       a[U.hist[rel >> shift0] + slot[i]] = ((uint64_t)rel << 32) | (e[i].y - gbase);
     }
@@ -671,7 +701,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
       const uint32_t k = i * kSortThreads + tid;
       x[i] = 0;
       pos[i] = 0;
-      if (k < n) {
+      if (i < it && k < n) {
         x[i] = a[k];
         const uint32_t bin = (uint32_t)(x[i] >> ps);
         const uint32_t start = U.hist[bin], end = bin + 1 < (uint32_t)kBins ? U.hist[bin + 1] : n;
@@ -683,7 +713,7 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kSortItems; i++)
-      if (i * kSortThreads + tid < n) a[pos[i]] = x[i];
+      if (i < it && i * kSortThreads + tid < n) a[pos[i]] = x[i];
   } else {
     const uint64_t vary = s_and ^ s_or;
     for (int shift = 0; shift < 64; shift += 8) {
@@ -700,30 +730,53 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
     // A warp's 32 records are one contiguous 1536-byte block of the slab: they are staged in shared memory
     // (48-byte stride: conflict-free 128-bit stores) and leave as three fully coalesced warp stores instead
     // of three stores that each touch all 48 sectors of the block.
+    // Gather of a warp's 32 records.  A thread loading "its" record's three float4 touches 32 different cache
+    // lines per load instruction (96 L1 wavefronts per 32 records: the LSU data pipe was the kernel's busiest
+    // unit).  Instead 4 lanes share a record -- lane piece p < 3 loads float4 p, so one load instruction covers 8
+    // records with 8 wavefronts -- and the raw pieces meet in the warp's staging block, where the record's owner
+    // lane computes the cull mask and rewrites the first two float4 in the blend kernels' order.
     float4 *stg = &s_stage[warp][0];
+    const uint32_t piece = lane & 3u, sub = lane >> 2;
+    float4 raw[4];
+    auto load_raw = [&](uint32_t kb_) {
+      const uint32_t cnt_ = min(32u, n - kb_);
+#pragma unroll
+      for (int rd = 0; rd < 4; rd++) {
+        const uint32_t rec = rd * 8 + sub;
+        raw[rd] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rec < cnt_ && piece < 3u) raw[rd] = geom[4 * ((size_t)gbase + (uint32_t)a[kb_ + rec]) + piece];
+      }
+    };
+    if (warp * 32u < n) load_raw(warp * 32u);
     for (uint32_t kb = warp * 32; kb < n; kb += kSortThreads) {
-      const uint32_t k = kb + lane;
-      if (k < n) {
+      const uint32_t cnt = min(32u, n - kb);
+#pragma unroll
+      for (int rd = 0; rd < 4; rd++) {
+        const uint32_t rec = rd * 8 + sub;
+        if (rec < cnt && piece < 3u) stg[3 * rec + piece] = raw[rd];
+      }
+      // the loads of the warp's next 32 records fly while these are finished
+      if (kb + kSortThreads < n) load_raw(kb + kSortThreads);
+      __syncwarp();
+      if (lane < cnt) {
+        const uint32_t k = kb + lane;
         const uint64_t key = a[k];
         const uint32_t id = (uint32_t)key;
-        const size_t g = (size_t)gbase + id, r = (size_t)cstart + k;
-        const float4 q0 = geom[4 * g], q1 = geom[4 * g + 1];
-        float4 q2 = geom[4 * g + 2];
+        const size_t r = (size_t)cstart + k;
+        const float4 q0 = stg[3 * lane], q1 = stg[3 * lane + 1];
         masks[r] = (uint8_t)subblock_mask(q0, q1, tile_x0, tile_y0);
         if (dbg_keys) dbg_keys[r] = ((uint64_t)tile << 32) | ((uint32_t)(key >> 32) + dmin);
         if (dbg_plist) dbg_plist[r] = id;
-        q2.w = __uint_as_float(id);
         stg[3 * lane] = make_float4(q0.x, q0.y, q0.z, q1.x);       // {x, y, A, C}
         stg[3 * lane + 1] = make_float4(q0.w, q1.y, q1.z, 0.f);   // {B, opacity, thr, 0}
-        stg[3 * lane + 2] = q2;
+        reinterpret_cast<uint32_t *>(&stg[3 * lane + 2])[3] = id; // {r, g, b, id}
       }
       __syncwarp();
-      const uint32_t cnt3 = 3u * min(32u, n - kb);
       float4 *out = records + 3 * ((size_t)cstart + kb);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         const uint32_t idx = i * 32 + lane;
-        if (idx < cnt3) out[idx] = stg[idx];
+        if (idx < 3u * cnt) out[idx] = stg[idx];
       }
       __syncwarp();
     }
@@ -733,6 +786,36 @@ sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ ite
     uint64_t *dst = reinterpret_cast<uint64_t *>(src);
     for (uint32_t k = tid; k < n; k += kSortThreads) dst[k] = a[k] + ((uint64_t)dmin << 32);
   }
+}
+
+template <int kSortThreads>
+__global__ void __launch_bounds__(kSortThreads, 1024 / kSortThreads)
+sort_chunks_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ items, const uint32_t *__restrict__ misc,
+                   const uint2 *__restrict__ ranges, uint2 *inst, uint2 *inst_b, const float4 *__restrict__ geom,
+                   float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
+                   uint32_t *__restrict__ dbg_plist) {
+  // (one item per CTA: taking items from a work counter in a loop was slower -- 91 vs 86 us per 8 views; the
+  // hardware starts the next CTA faster than a CTA can fetch its next item)
+  if (blockIdx.x >= misc[0]) return;
+  const uint4 item = items[blockIdx.x];
+  sort_item<kSortThreads>(item, ranges[item.x], P, dT, dgx, inst, inst_b, geom, records, masks, dbg_keys, dbg_plist);
+}
+
+// Lists of kChunk < n <= kBigChunk instances (two to four chunks: 2/3 of the instances of the two-hand scene)
+// are ONE item of a 1024-thread CTA and final after it -- no key write-back, no rank merge, coalesced record
+// stores.  The tiles come from the head of order[] (descending size class: every list longer than a chunk
+// is there, misc[3] of them, longest first).
+__global__ void __launch_bounds__(1024, 1)
+sort_big_kernel(int P, FastDiv dT, FastDiv dgx, uint32_t big_max, const uint32_t *__restrict__ order,
+                const uint32_t *__restrict__ tile_count, const uint32_t *__restrict__ misc,
+                const uint2 *__restrict__ ranges, uint2 *inst, const float4 *__restrict__ geom,
+                float4 *__restrict__ records, uint8_t *__restrict__ masks, uint64_t *__restrict__ dbg_keys,
+                uint32_t *__restrict__ dbg_plist) {
+  if (blockIdx.x >= misc[3]) return;
+  const uint32_t vt = order[blockIdx.x], c = tile_count[vt];
+  if (c <= (uint32_t)kChunk || c > big_max) return;    // (longer lists: depth partition or chunks + merge)
+  sort_item<1024>(make_uint4(vt, 0u, c, kItemFinal), ranges[vt], P, dT, dgx, inst, inst, geom, records, masks, dbg_keys,
+                  dbg_plist);
 }
 
 // Multi-chunk tiles: one CTA per chunk.  Final position of a key = its index in its own (sorted) chunk
@@ -845,10 +928,12 @@ recolor_records_kernel(uint64_t R_cap, const GhrStatus *__restrict__ old_status,
 // Python layer sizes R_cap from the instance counts it has seen): at the two-hand sizes no list reaches
 // kPartMin and four empty launches per forward would be pure overhead.  Either way every list is
 // handled exactly -- the merge has no length limit.  GHR_PARTITION=0/1 forces the choice (A/B).
-static int part_min() {
-  static const int v = [] { const char *e = getenv("GHR_PART_MIN_CHUNKS"); return (e ? atoi(e) : 1) * kChunk; }();
-  return v;
-}
+constexpr int kBigChunk = 8192;       // longest list one 1024-thread CTA sorts (sort_big_kernel)
+// A big item occupies a whole SM for ~20 us; with few of them (a single view: ~45) most SMs idle and the launch
+// lasts as long as its longest list, where 2048-instance chunks + the rank merge spread the same lists over five
+// times as many CTAs (single view: 37 vs 46 us).  The big items pay off once they fill the machine twice.
+static uint32_t big_max(const GhrDims &d) { return (uint64_t)d.R_cap / kChunk >= 2u * 148u ? (uint32_t)kBigChunk : 0u; }
+static uint32_t part_min(const GhrDims &d) { return big_max(d) ? big_max(d) : (uint32_t)kChunk; }
 static bool use_partition(const GhrDims &d, const Layout &L) {
   static const int forced = [] { const char *e = getenv("GHR_PARTITION"); return e ? atoi(e) : -1; }();
   if (forced >= 0) return forced != 0;
@@ -886,7 +971,8 @@ cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *s
   if (VT == 0) return cudaSuccess;
   tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
       VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (uint32_t)L.n_hchunks, (uint32_t)L.n_heavy,
-      use_partition(d, L) ? (uint32_t)part_min() : 0xFFFFFFFFu, (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
+      use_partition(d, L) ? part_min(d) : 0xFFFFFFFFu, big_max(d),
+      (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
       (uint32_t *)(state + L.pub.off_order), (uint4 *)(temp + L.t_chunks), (uint2 *)(temp + L.t_hchunks),
       (uint32_t *)(temp + L.t_heavy), (uint32_t *)(temp + L.t_heavy_id), (uint32_t *)(temp + L.t_misc),
       (GhrStatus *)(state + L.pub.off_status));
@@ -940,10 +1026,20 @@ cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, c
   // chunk sort of every item (light tiles and depth buckets are final), rank merge for the fallback tiles
   const int grid = partition ? (int)L.n_chunks : (int)((size_t)d.R_cap / kChunk + VT + 1);
   constexpr int kThreads = 256;
-  const size_t sort_smem = (size_t)kThreads * kSortItems * 8;
+  const size_t sort_smem = SortSmem<kThreads>::kBytes, big_smem = SortSmem<1024>::kBytes;
   cudaError_t e = cudaFuncSetAttribute(sort_chunks_kernel<kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sort_smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(sort_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_smem);
   if (e != cudaSuccess) return e;
+  // lists of two to four chunks first (the longest work items), one CTA each
+  size_t big_grid = (size_t)d.R_cap / kChunk + 1;
+  if (big_grid > (size_t)VT) big_grid = (size_t)VT;
+  if (big_max(d))
+    sort_big_kernel<<<(int)big_grid, 1024, big_smem, s>>>(
+      d.P, dT, dgx, big_max(d), (const uint32_t *)(state + L.pub.off_order),
+      (const uint32_t *)(temp + L.t_tile_count), misc, ranges, inst, (const float4 *)(state + L.pub.off_geom),
+      (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
   sort_chunks_kernel<kThreads><<<grid, kThreads, sort_smem, s>>>(
       d.P, dT, dgx, items, misc, ranges, inst, inst_b, (const float4 *)(state + L.pub.off_geom),
       (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);

@@ -59,57 +59,43 @@ __device__ __forceinline__ void st_peer(float4 *p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
-// wait until every rank's flag word of `phase` in MY flag array carries `epoch` (threads 0..world-1 poll, with
-// a short sleep between polls: a spinning kernel must not hammer the system-scope path)
-__device__ __forceinline__ void wait_flags(const CommDev &c, int phase, uint32_t epoch, uint32_t *err) {
+__device__ __forceinline__ void red_add_release_sys(uint32_t *p, uint32_t v) {
+  asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until every rank's word of `phase` in MY flag array equals `want` (threads 0..world-1 poll local memory)
+__device__ __forceinline__ void wait_flags(const CommDev &c, int phase, uint32_t want, uint32_t *err, bool acquire) {
   if ((int)threadIdx.x < c.world) {
     const uint32_t *f = c.flags[c.rank] + phase * kMaxRanks + threadIdx.x;
     const long long t0 = clock64();
-    while (ld_relaxed_sys(f) != epoch) {
-      __nanosleep(200);
+    while (ld_relaxed_sys(f) != want) {
+      __nanosleep(40);
       if (clock64() - t0 > kSpinLimit) {
         atomicExch(err, 1u + (uint32_t)phase);
         break;
       }
     }
-    fence_acq_rel_sys();
+    if (acquire) fence_acq_rel_sys();
   }
   __syncthreads();
 }
-__device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t *p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
-// state words (local): [0] epoch of the last completed all-reduce, [1] CTAs finished, [2] error,
-// [3] "every rank has arrived" of the running all-reduce (set by CTA 0, which alone polls the peers' flags)
+// The kernel's critical path is a chain of system-scope fences and NVLink flag trips (a 256-byte all-reduce takes
+// as long as 60 % of the 3.4 MB one), so it has as few of them as the protocol allows:
+//   A  "my gradients are written": CTA 0 releases the epoch into every rank's phase-0 word (the gradients come
+//      from earlier kernels of the stream); EVERY CTA polls its own rank's words and acquires once;
+//   B  "my pushes have landed": every CTA, after its stores and one CTA barrier, adds 1 with release semantics to
+//      its phase-1 word on every rank; the words count CTA arrivals since the communicator was created, and every
+//      CTA waits until each rank's count has reached the running target -- no hand-over through a last CTA.  No
+//      acquire after B: the kernel ends there and the next kernel of the stream reads the buffer.
+// state words (local): [0] all-reduces completed (= epoch), [1] CTAs finished, [2] error, [3] CTA arrivals expected
+// from every rank so far; [0] and [3] are advanced by the grid's last CTA after every CTA has read them.
 __global__ void __launch_bounds__(kCommThreads)
 peer_allreduce_kernel(CommDev c, size_t n4, uint32_t *__restrict__ st) {
-  __shared__ uint32_t s_last;
-  const uint32_t epoch = *(volatile uint32_t *)&st[0] + 1u;   // (st[0] is advanced by the grid's last CTA only)
-  // barrier A: my gradients are complete (stream order) -- tell every rank, wait for every rank
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < c.world) {
-      __threadfence_system();
-      st_release_sys(c.flags[threadIdx.x] + 0 * kMaxRanks + c.rank, epoch);
-    }
-    wait_flags(c, 0, epoch, &st[2]);
-    if (threadIdx.x == 0) st_release_gpu(&st[3], epoch);
-  } else {
-    if (threadIdx.x == 0) {
-      const long long t0 = clock64();
-      while (ld_relaxed_gpu(&st[3]) != epoch) {
-        __nanosleep(200);
-        if (clock64() - t0 > kSpinLimit + (kSpinLimit >> 2)) break;     // (CTA 0 has recorded the error)
-      }
-      fence_acq_rel_sys();      // (cumulative: CTA 0 acquired the peers' releases before it released st[3])
-    }
-    __syncthreads();
-  }
+  const uint32_t epoch = *(volatile uint32_t *)&st[0] + 1u;
+  const uint32_t target = *(volatile uint32_t *)&st[3] + gridDim.x;
+  if (blockIdx.x == 0 && (int)threadIdx.x < c.world)
+    st_release_sys(c.flags[threadIdx.x] + 0 * kMaxRanks + c.rank, epoch);
+  wait_flags(c, 0, epoch, &st[2], true);
   // reduce-scatter + all-gather of my slice: sum in rank order, push to every rank
   const size_t slice = (n4 + c.world - 1) / c.world;
   const size_t lo = (size_t)c.rank * slice, hi = lo + slice < n4 ? lo + slice : n4;
@@ -128,19 +114,12 @@ peer_allreduce_kernel(CommDev c, size_t n4, uint32_t *__restrict__ st) {
     for (int p = 0; p < kMaxRanks; p++)
       if (p < c.world) st_peer(reinterpret_cast<float4 *>(c.data[p]) + i, acc);
   }
-  // barrier B: the grid's last CTA tells every rank that my pushes have landed and waits for theirs
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&st[1], 1u) == gridDim.x - 1u;
-  __syncthreads();
-  if (!s_last) return;
-  if ((int)threadIdx.x < c.world) {
-    __threadfence_system();
-    st_release_sys(c.flags[threadIdx.x] + 1 * kMaxRanks + c.rank, epoch);
-  }
-  wait_flags(c, 1, epoch, &st[2]);
-  if (threadIdx.x == 0) {
+  __syncthreads();                   // the CTA's stores are ordered before the releases below (cumulativity)
+  if ((int)threadIdx.x < c.world) red_add_release_sys(c.flags[threadIdx.x] + 1 * kMaxRanks + c.rank, 1u);
+  wait_flags(c, 1, target, &st[2], false);
+  if (threadIdx.x == 0 && atomicAdd(&st[1], 1u) == gridDim.x - 1u) {
     st[1] = 0u;
+    *(volatile uint32_t *)&st[3] = target;
     *(volatile uint32_t *)&st[0] = epoch;
   }
 }
@@ -250,7 +229,7 @@ int ghr_comm_allreduce(GhrComm *c, size_t nfloats, void *cuda_stream) {
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const size_t n4 = nfloats / 4, slice = (n4 + c->world - 1) / c->world;
   int grid = (int)((slice + kCommThreads - 1) / kCommThreads);
-  if (grid > 96) grid = 96;
+  if (grid > 148) grid = 148;
   if (grid < 1) grid = 1;
   peer_allreduce_kernel<<<grid, kCommThreads, 0, s>>>(c->dev, n4, (uint32_t *)(c->base + c->off_state));
   cudaError_t e = cudaGetLastError();

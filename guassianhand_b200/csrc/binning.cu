@@ -828,16 +828,20 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ it
                     uint32_t *__restrict__ dbg_plist) {
   constexpr int kChunk = kSortThreads * kSortItems;
   __shared__ __align__(16) uint64_t s_other[kChunk];
-  if (blockIdx.x >= misc[0]) return;
-  const uint4 item = items[blockIdx.x];
-  if (item.w & kItemFinal) return;                     // light tile or depth bucket: finished by sort_chunks
+  // grid-stride over the item list: with the grid at its upper bound every CTA has one item; when merge items
+  // are the exception (lists up to kBigChunk go to sort_big_kernel) a small grid skims the list instead of
+  // thousands of CTAs being launched to find out that their item is final
+  const uint32_t n_items = misc[0];
+  for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+  const uint4 item = items[it];
+  if (item.w & kItemFinal) continue;                   // light tile or depth bucket: finished by sort_chunks
   const uint32_t vt = item.x;
   const uint2 range = ranges[vt];
   const uint32_t nt = range.y - range.x;
   const uint32_t m = (nt + kChunk - 1) / kChunk;       // the tile's plain chunks (plan_kernel's fallback)
   const uint32_t own = item.y / kChunk;
   const uint32_t cstart = range.x + item.y;
-  if (cstart >= range.y) return;
+  if (cstart >= range.y) continue;
   const uint32_t n = min((uint32_t)kChunk, range.y - cstart);
   const int tid = threadIdx.x;
   const uint32_t v = dT.div(vt), tile = vt - v * dT.d, gbase = v * (uint32_t)P;
@@ -887,6 +891,7 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ it
     if (k < n)
       emit_instance((size_t)range.x + pos[i], (uint32_t)(key[i] >> 32), (uint32_t)key[i], gbase, tile, tile_x0, tile_y0,
                     geom, records, masks, dbg_keys, dbg_plist);
+  }
   }
 }
 
@@ -1043,7 +1048,8 @@ cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, c
   sort_chunks_kernel<kThreads><<<grid, kThreads, sort_smem, s>>>(
       d.P, dT, dgx, items, misc, ranges, inst, inst_b, (const float4 *)(state + L.pub.off_geom),
       (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
-  merge_gather_kernel<kThreads><<<grid, kThreads, 0, s>>>(
+  const int merge_grid = big_max(d) && grid > 148 * 4 ? 148 * 4 : grid;
+  merge_gather_kernel<kThreads><<<merge_grid, kThreads, 0, s>>>(
       d.P, dT, dgx, items, misc, ranges, inst, (const float4 *)(state + L.pub.off_geom),
       (float4 *)(state + L.pub.off_records), (uint8_t *)(state + L.pub.off_masks), dbg_keys, dbg_plist);
   return cudaGetLastError();

@@ -1,10 +1,13 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list per kernel.
+    python tools/launch_summary.py launches.csv [--step-only]
+--step-only keeps libghr's step kernels (no FP32 probes, no torch fill / copy kernels of the harness): the shares
+are then shares of the fwd+bwd step, comparable with bench.py's stage_ms."""
 import collections
 import csv
 import sys
 
 
-def main(path):
+def main(path, step_only=False):
     rows = list(csv.reader(open(path)))
     hdr = None
     agg = collections.OrderedDict()
@@ -16,6 +19,8 @@ def main(path):
             d = dict(zip(hdr, r))
             if d.get("Metric Name") == "gpu__time_duration.sum":
                 name = d["Kernel Name"].split("(")[0][:70]
+                if step_only and ("ghr::" not in name or "probe" in name):
+                    continue
                 v = float(d["Metric Value"].replace(",", ""))
                 unit = d["Metric Unit"]
                 v = v / 1000.0 if unit in ("ns", "nsecond") else (v * 1000.0 if unit in ("ms", "msecond") else v)
@@ -28,4 +33,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], "--step-only" in sys.argv)

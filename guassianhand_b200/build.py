@@ -49,6 +49,10 @@ VARIANTS = {
     "bwdilp3": ["-DGHR_BWD_ILP=3"],      # A/B: instances per backward iteration
     "bwdilp4": ["-DGHR_BWD_ILP=4"],
     "bwdocc8": ["-DGHR_BWD_MINCTAS=8"],  # A/B: 64 registers, 8 CTAs per SM
+    "bwdocc6": ["-DGHR_BWD_MINCTAS=6"],
+    # A/B: forward blend occupancy (registers via min CTAs, shared memory via ring depth) against per-warp ILP
+    "fwdilp8occ5": ["-DGHR_FWD_ILP=8", "-DGHR_FWD_MINCTAS=4", "-DGHR_FWD_STAGES=6"],   # the round-2 start point
+    "fwdilp8occ8": ["-DGHR_FWD_ILP=8", "-DGHR_FWD_MINCTAS=8", "-DGHR_FWD_STAGES=4"],
     "nored": ["-DGHR_NO_RED"],           # experiment: backward blend without its global reductions (wrong results)
 }
 

@@ -29,7 +29,10 @@ namespace ghr {
 namespace {
 
 constexpr int kStageN = 128;  // instances per stage (6 KB)
-constexpr int kStages = 6;      // forward stage ring
+#ifndef GHR_FWD_STAGES
+#define GHR_FWD_STAGES 4
+#endif
+constexpr int kStages = GHR_FWD_STAGES;      // forward stage ring (build-time A/B)
 constexpr int kBlendWarps = 4;               // backward: 8x8-pixel blocks of a tile
 constexpr float kAlphaMin = 1.0f / 255.0f;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -37,7 +40,7 @@ constexpr float kLog2e = 1.4426950408889634f;
 #define GHR_BWD_ILP 2
 #endif
 #ifndef GHR_BWD_MINCTAS
-#define GHR_BWD_MINCTAS 6
+#define GHR_BWD_MINCTAS 7       // 72 registers (A/B: 6 CTAs at 76 registers 191 us, 7 at 72: 188.5, 8 at 64: 197.6)
 #endif
 constexpr int kIlpB = GHR_BWD_ILP;   // instances per backward iteration (build-time A/B)
 constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
@@ -233,7 +236,16 @@ __device__ __forceinline__ uint32_t build_queue_idx(const uint8_t *msk, uint32_t
 constexpr int kFwdWarps = 4;                  // warps per CTA: one per scheduler
 constexpr int kFwdParts = 2;                  // CTAs per tile (upper / lower half), each staging the slab
 constexpr int kFwdThreads = kFwdWarps * 32;
-constexpr int kIlpF = 8;                      // instances per iteration
+// A/B on B200 (tools/stage_times.py, 8 views, graphed step with two chains): {8 instances per iteration, 94
+// registers, 6 stages: 5 CTAs per SM} 0.4165 ms; {8, 64 registers, 4 stages: 8 CTAs} 0.4109; {4, 64, 4: 8 CTAs}
+// 0.4065.  The kernel's own duration barely moves (93-96 us): the smaller CTAs let the other chain's kernels in.
+#ifndef GHR_FWD_ILP
+#define GHR_FWD_ILP 4
+#endif
+#ifndef GHR_FWD_MINCTAS
+#define GHR_FWD_MINCTAS 8
+#endif
+constexpr int kIlpF = GHR_FWD_ILP;            // instances per iteration (build-time A/B)
 struct __align__(128) FwdSmem {
   StageBuf sb;
   uint16_t q[kFwdWarps][kStageN + 2 * kQPad];
@@ -327,7 +339,7 @@ __device__ __forceinline__ void pixel_of_thread(int warp, int lane, int &lx, int
   ly = ((warp >> 1) << 2) + (lane >> 3);
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 4)
+__global__ void __launch_bounds__(kFwdThreads, GHR_FWD_MINCTAS)
 blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *__restrict__ order,
                      const uint2 *__restrict__ ranges, const float4 *__restrict__ records,
                      const uint8_t *__restrict__ masks, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
@@ -429,8 +441,14 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       uint32_t n_contributing = 0;
 #endif
       for (uint32_t b = 0; b < total; b += kIlpF) {
-        const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
-        const uint32_t packed[4] = {p4.x, p4.y, p4.z, p4.w};
+        uint32_t packed[4];
+        if (kIlpF == 8) {
+          const uint4 p4 = *reinterpret_cast<const uint4 *>(q + kQPad + b);
+          packed[0] = p4.x; packed[1] = p4.y; packed[2] = p4.z; packed[3] = p4.w;
+        } else {
+          const uint2 p2 = *reinterpret_cast<const uint2 *>(q + kQPad + b);
+          packed[0] = p2.x; packed[1] = p2.y; packed[2] = 0u; packed[3] = 0u;
+        }
         uint32_t addr[kIlpF];
         float4 ga[kIlpF];
         float2 gb[kIlpF];

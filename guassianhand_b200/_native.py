@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
+GHR_STATUS_OVERFLOW, GHR_STATUS_PREFILTER = 1, 2
 GHR_ABI_VERSION = 10
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
 FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]

@@ -109,6 +109,9 @@ class _Workspace:
                 if int(row[2]) != seq:
                     raise RuntimeError("ghr_forward: status report never arrived")
             R, overflow = int(row[0]), int(row[1]) & 0xFFFFFFFF
+            if overflow & N.GHR_STATUS_PREFILTER:
+                self.pending = []
+                raise RuntimeError(_PREFILTER_MSG)
             self.note(key, R)
             if not fixed and key in self.cap:
                 self.cap[key] = max(self.cap[key], int(R * 1.5) + (1 << 14))
@@ -119,6 +122,10 @@ class _Workspace:
                                    f"has been raised) or use check='poll'.")
         self.pending = keep
 
+
+# upstream's in_frustum() prints this and __trap()s (the CUDA context is lost); here the forward raises and the
+# context survives
+_PREFILTER_MSG = "Point is filtered although prefiltered is set. This shouldn't happen!"
 
 _ws_lock = threading.Lock()
 _workspaces = {}
@@ -296,6 +303,8 @@ def forward_raw(cams: _Cams, means3D, opacities, scales, rotations, cov3D, shs, 
                         raise RuntimeError("ghr_forward: status report never arrived")
             R = int(row[0])
             overflow = int(row[1]) & 0xFFFFFFFF
+            if overflow & N.GHR_STATUS_PREFILTER:
+                raise RuntimeError(_PREFILTER_MSG)
             ws.note(key, R)
             if R_cap is None:
                 ws.cap[key] = max(ws.cap[key], int(R * 1.5) + (1 << 14))
@@ -461,7 +470,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
                 raise
         else:
-            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask, check="auto")
+            res = forward_raw(*args, flags=_flags(rs), want_mask=want_mask, check="poll" if rs.prefiltered else "auto")
             _GeomCache.store(dev_index, gtensors, gscalars, res.state, M, res.R_cap, res.R)
         ctx.raster_settings = rs
         ctx.want_mask = want_mask

@@ -244,18 +244,11 @@ int ghr_forward(const GhrForwardArgs *a, void *cuda_stream) {
   }
   tm.start(0);
   GHR_TRY(cudaMemsetAsync(temp, 0, L.t_zero_bytes, s), "ghr_forward: memset(temp)");
-  {
-    // status starts as {R=0, overflow=0, n_visible=0, seq}: 32 bytes passed by value
-    GhrStatus st0;
-    memset(&st0, 0, sizeof(st0));
-    st0.reserved[0] = a->seq;
-    GHR_TRY(launch_init_status(state + L.pub.off_status, st0, s), "ghr_forward: init status");
-  }
   GHR_TRY(launch_preprocess(d, L, cam, g, a->scale_modifier, a->flags, state, temp, a->radii, s),
           "ghr_forward: preprocess");
   tm.stop(0);
   tm.start(1);
-  GHR_TRY(launch_tile_scan_schedule(d, L, state, temp, s), "ghr_forward: tile scan+schedule");
+  GHR_TRY(launch_tile_scan_schedule(d, L, state, temp, a->seq, s), "ghr_forward: tile scan+schedule");
   tm.stop(1);
   if (a->host_status)
     GHR_TRY(cudaMemcpyAsync(a->host_status, state + L.pub.off_status, sizeof(GhrStatus), cudaMemcpyDeviceToHost, s),

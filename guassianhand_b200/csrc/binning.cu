@@ -29,6 +29,8 @@
 // bit for bit the upstream order (checked against the oracle's sorted keys / point list / ranges).
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "ghr_internal.cuh"
 
 namespace ghr {
@@ -68,39 +70,114 @@ constexpr int kSlabs = 256;            // depth slabs of a heavy tile (fine hist
 // items[] = one sort item per light tile (misc[0] = their number; the plan kernel appends the heavy
 // tiles' buckets), hchunks[] = (tile, chunk index) pieces of the heavy tiles for the partition passes
 // (misc[1]), heavy[] = the heavy tiles (misc[2]) with heavy_id[tile] their index, status = {R, overflow}.
-// One CTA: every thread owns a run of consecutive tiles, sums it, one block scan of the 1024 run
-// totals, then walks its run again.
+// gridDim.x CTAs, each owning a span of consecutive tiles, with NO communication between them: every CTA
+// first reads ALL V*T counts (a few coalesced, independent loads per thread) and reduces them twice -- over
+// everything (R, the class histogram that lays out order[], the list totals) and over the tiles in front of
+// its span (its base offsets) -- then scans its own span (a thread owns a run of consecutive tiles, one block
+// scan of the run totals, a second walk over the run).  One CTA per ~1024 tiles: 8 views of 672 tiles are
+// one tile per thread on 6 SMs instead of 6 tiles per thread on one (round 2: 17 -> ~7 us).
+struct ScanTotals {
+  unsigned long long sum;   // instances
+  uint32_t l, h, hc, nbig;  // light items, heavy tiles, heavy chunks, lists longer than a chunk
+  uint32_t merge;           // light items that are one of several chunks of their list (finished by merge_gather)
+};
+
 __global__ void __launch_bounds__(kScanThreads1)
 tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hchunk_cap, uint32_t heavy_cap,
                           uint32_t part_min, uint32_t big_max, const uint32_t *__restrict__ tile_count,
                           uint2 *__restrict__ ranges,
                           uint32_t *__restrict__ order, uint4 *__restrict__ items, uint2 *__restrict__ hchunks,
                           uint32_t *__restrict__ heavy, uint32_t *__restrict__ heavy_id,
-                          uint32_t *__restrict__ misc, GhrStatus *__restrict__ status) {
+                          uint32_t *__restrict__ misc, GhrStatus *__restrict__ status, uint64_t seq) {
   __shared__ uint64_t s_warp[kScanThreads1 / 32];
   __shared__ uint32_t s_wl[kScanThreads1 / 32], s_wh[kScanThreads1 / 32], s_whc[kScanThreads1 / 32];
-  __shared__ uint32_t s_cls[kClasses + 1], s_cur[kClasses + 1];
-  __shared__ uint32_t s_nbig;
+  __shared__ uint32_t s_cls[kClasses + 1], s_before[kClasses + 1], s_cur[kClasses + 1];
+  __shared__ ScanTotals s_all, s_pre;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < kClasses) s_cls[tid] = 0;
-  if (tid == 0) s_nbig = 0;
-  const int per = (VT + kScanThreads1 - 1) / kScanThreads1;
-  const int t0 = min(VT, tid * per), t1 = min(VT, t0 + per);
+  if (tid <= kClasses) {
+    s_cls[tid] = 0;
+    s_before[tid] = 0;
+  }
+  if (tid == 0) {
+    s_all = ScanTotals{0ull, 0u, 0u, 0u, 0u, 0u};
+    s_pre = ScanTotals{0ull, 0u, 0u, 0u, 0u, 0u};
+  }
+  __syncthreads();
+  const int span = (VT + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int lo = min(VT, (int)blockIdx.x * span), hi = min(VT, lo + span);
+
+  // ---- pass 1: every count, reduced over all tiles and over the tiles in front of the span ----
+  {
+    unsigned long long a_sum = 0, b_sum = 0;
+    uint32_t a_l = 0, a_h = 0, a_hc = 0, a_nbig = 0, a_merge = 0, b_l = 0, b_h = 0, b_hc = 0;
+    for (int t0 = 0; t0 < VT; t0 += kScanThreads1) {
+      const int t = t0 + tid;
+      const bool valid = t < VT;
+      const uint32_t c = valid ? tile_count[t] : 0u;
+      const bool pre = valid && t < lo;
+      uint32_t l = 0, h = 0, hc = 0;
+      if (c > part_min) {
+        h = 1;
+        hc = (c + kChunk - 1) / kChunk;
+      } else if (!(c > (uint32_t)kChunk && c <= big_max)) {   // (a big list is ONE item of sort_big_kernel)
+        l = (c + kChunk - 1) / kChunk;           // one final item, or plain chunks finished by the rank merge
+      }
+      a_sum += c; a_l += l; a_h += h; a_hc += hc;
+      a_nbig += c > (uint32_t)kChunk;
+      a_merge += l > 1u ? l : 0u;
+      if (pre) { b_sum += c; b_l += l; b_h += h; b_hc += hc; }
+      // class counters are warp-aggregated (match.any): most tiles are empty, and thousands of shared-memory
+      // atomics on one address would serialise
+      const int cls = valid ? size_class(c) : kClasses;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+      if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
+      if (lo > 0) {                                 // (block-uniform)
+        const uint32_t bpeers = __match_any_sync(0xFFFFFFFFu, pre ? cls : kClasses);
+        if (pre && lane == __ffs(bpeers) - 1) atomicAdd(&s_before[cls], (uint32_t)__popc(bpeers));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a_sum += __shfl_xor_sync(0xFFFFFFFFu, a_sum, o);
+      b_sum += __shfl_xor_sync(0xFFFFFFFFu, b_sum, o);
+    }
+    a_l = __reduce_add_sync(0xFFFFFFFFu, a_l);
+    a_h = __reduce_add_sync(0xFFFFFFFFu, a_h);
+    a_hc = __reduce_add_sync(0xFFFFFFFFu, a_hc);
+    a_nbig = __reduce_add_sync(0xFFFFFFFFu, a_nbig);
+    a_merge = __reduce_add_sync(0xFFFFFFFFu, a_merge);
+    b_l = __reduce_add_sync(0xFFFFFFFFu, b_l);
+    b_h = __reduce_add_sync(0xFFFFFFFFu, b_h);
+    b_hc = __reduce_add_sync(0xFFFFFFFFu, b_hc);
+    if (lane == 0) {
+      if (a_sum) atomicAdd(&s_all.sum, a_sum);
+      if (a_l) atomicAdd(&s_all.l, a_l);
+      if (a_h) atomicAdd(&s_all.h, a_h);
+      if (a_hc) atomicAdd(&s_all.hc, a_hc);
+      if (a_nbig) atomicAdd(&s_all.nbig, a_nbig);
+      if (a_merge) atomicAdd(&s_all.merge, a_merge);
+      if (b_sum) atomicAdd(&s_pre.sum, b_sum);
+      if (b_l) atomicAdd(&s_pre.l, b_l);
+      if (b_h) atomicAdd(&s_pre.h, b_h);
+      if (b_hc) atomicAdd(&s_pre.hc, b_hc);
+    }
+  }
+
+  // ---- pass 2: the span ----
+  const int per = (hi - lo + kScanThreads1 - 1) / kScanThreads1;
+  const int t0 = min(hi, lo + tid * per), t1 = min(hi, t0 + per);
   uint64_t sum = 0;
   uint32_t lsum = 0, hsum = 0, hcsum = 0;      // light tiles, heavy tiles, heavy chunks of this run
-  uint32_t nbig = 0;                           // lists longer than a chunk (= the head of order[])
   for (int t = t0; t < t1; t++) {
     const uint32_t c = tile_count[t];
     sum += c;
-    nbig += c > (uint32_t)kChunk;
     if (c > part_min) {
       hsum++;
       hcsum += (c + kChunk - 1) / kChunk;
-    } else if (!(c > (uint32_t)kChunk && c <= big_max)) {   // (a big list is ONE item of sort_big_kernel)
-      lsum += (c + kChunk - 1) / kChunk;       // one final item, or plain chunks finished by the rank merge
+    } else if (!(c > (uint32_t)kChunk && c <= big_max)) {
+      lsum += (c + kChunk - 1) / kChunk;
     }
   }
-  nbig = __reduce_add_sync(0xFFFFFFFFu, nbig);
   uint64_t incl = sum;
   uint32_t lincl = lsum, hincl = hsum, hcincl = hcsum;
 #pragma unroll
@@ -116,42 +193,62 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
       hcincl += hcup;
     }
   }
-  __syncthreads();                             // (s_nbig = 0 above)
   if (lane == 31) {
     s_warp[warp] = incl;
     s_wl[warp] = lincl;
     s_wh[warp] = hincl;
     s_whc[warp] = hcincl;
-    if (nbig) atomicAdd(&s_nbig, nbig);
+  }
+  __syncthreads();                             // (and the pass-1 totals are complete)
+  uint64_t start = s_pre.sum + (incl - sum);
+  uint32_t loff = s_pre.l + (lincl - lsum), hoff = s_pre.h + (hincl - hsum), hcoff = s_pre.hc + (hcincl - hcsum);
+  for (int w = 0; w < warp; w++) {
+    start += s_warp[w];
+    loff += s_wl[w];
+    hoff += s_wh[w];
+    hcoff += s_whc[w];
+  }
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
+      s_cur[c] = acc + s_before[c];
+      acc += s_cls[c];
+    }
+    if (blockIdx.x == 0) {
+      const uint64_t total = s_all.sum;
+      // the whole status: preprocess left its two words in misc (zeroed with the rest of the temp prefix), the
+      // forward blend appends its backward units to reserved[1]
+      GhrStatus st;
+      st.R = total;
+      st.overflow = (misc[kMiscPrefilter] ? GHR_STATUS_PREFILTER : 0u) | (total > R_cap ? GHR_STATUS_OVERFLOW : 0u);
+      st.n_visible = misc[kMiscVisible];
+      st.reserved[0] = seq;
+      st.reserved[1] = 0;
+      *status = st;
+      misc[0] = s_all.l < item_cap ? s_all.l : item_cap;
+      misc[1] = s_all.hc < hchunk_cap ? s_all.hc : hchunk_cap;
+      misc[2] = s_all.h < heavy_cap ? s_all.h : heavy_cap;
+      misc[3] = s_all.nbig;
+      misc[4] = s_all.merge;       // (the plan kernel adds the fallback tiles' chunks)
+    }
   }
   __syncthreads();
-  uint64_t start = incl - sum, total = 0;
-  uint32_t loff = lincl - lsum, hoff = hincl - hsum, hcoff = hcincl - hcsum, ltotal = 0, htotal = 0, hctotal = 0;
-  for (int w = 0; w < kScanThreads1 / 32; w++) {
-    if (w < warp) {
-      start += s_warp[w];
-      loff += s_wl[w];
-      hoff += s_wh[w];
-      hcoff += s_whc[w];
-    }
-    total += s_warp[w];
-    ltotal += s_wl[w];
-    htotal += s_wh[w];
-    hctotal += s_whc[w];
-  }
-  // class counters are warp-aggregated (match.any): most tiles are empty, and 5000 shared-memory atomics
-  // on one address would serialise
+  const uint32_t lt_mask = (1u << lane) - 1u;
   for (int j = 0; j < per; j++) {
     const int t = t0 + j;
     const bool valid = t < t1;
     const uint32_t c = valid ? tile_count[t] : 0u;
     const int cls = valid ? size_class(c) : kClasses;
     const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(&s_cur[cls], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
     if (valid) {
+      order[base + __popc(peers & lt_mask)] = (uint32_t)t;
       const uint64_t end = start + c;
       ranges[t] = c ? make_uint2((uint32_t)(start < R_cap ? start : R_cap), (uint32_t)(end < R_cap ? end : R_cap))
                     : make_uint2(0u, 0u);
-      if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
       const uint32_t m = (c + kChunk - 1) / kChunk;
       if (c > part_min) {
         if (hoff < heavy_cap) {
@@ -169,33 +266,6 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
       }
       start = end;
     }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    status->R = total;
-    status->overflow = total > R_cap ? 1u : 0u;
-    misc[0] = ltotal < item_cap ? ltotal : item_cap;
-    misc[1] = hctotal < hchunk_cap ? hctotal : hchunk_cap;
-    misc[2] = htotal < heavy_cap ? htotal : heavy_cap;
-    misc[3] = s_nbig;
-    uint32_t acc = 0;
-    for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
-      s_cur[c] = acc;
-      acc += s_cls[c];
-    }
-  }
-  __syncthreads();
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int j = 0; j < per; j++) {
-    const int t = t0 + j;
-    const bool valid = t < t1;
-    const int cls = valid ? size_class(tile_count[t]) : kClasses;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (valid && lane == leader) base = atomicAdd(&s_cur[cls], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (valid) order[base + __popc(peers & lt_mask)] = (uint32_t)t;
   }
 }
 
@@ -421,6 +491,7 @@ heavy_plan_kernel(const uint32_t *__restrict__ heavy, const uint2 *__restrict__ 
     heavy_flag[hid] = fallback ? 1u : 0u;
     s_nb = nb;
     s_at = atomicAdd(&misc[0], nb);
+    if (fallback) atomicAdd(&misc[4], nb);
   }
   __syncthreads();
   const uint32_t nb = s_nb, at = s_at;
@@ -831,6 +902,7 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ it
   // grid-stride over the item list: with the grid at its upper bound every CTA has one item; when merge items
   // are the exception (lists up to kBigChunk go to sort_big_kernel) a small grid skims the list instead of
   // thousands of CTAs being launched to find out that their item is final
+  if (misc[4] == 0u) return;                           // no list needs the rank merge (the usual case)
   const uint32_t n_items = misc[0];
   for (uint32_t it = blockIdx.x; it < n_items; it += gridDim.x) {
   const uint4 item = items[it];
@@ -895,8 +967,6 @@ merge_gather_kernel(int P, FastDiv dT, FastDiv dgx, const uint4 *__restrict__ it
   }
 }
 
-__global__ void init_status_kernel(GhrStatus *st, GhrStatus v) { *st = v; }
-
 // Geometry reuse: the earlier call's status with this call's sequence number and an empty backward unit list
 __global__ void reuse_status_kernel(const GhrStatus *old, GhrStatus *st, uint64_t seq) {
   GhrStatus v = *old;
@@ -945,11 +1015,6 @@ static bool use_partition(const GhrDims &d, const Layout &L) {
   return (uint64_t)d.R_cap >= (uint64_t)d.V * L.T * kChunk;
 }
 
-cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s) {
-  init_status_kernel<<<1, 1, 0, s>>>((GhrStatus *)status, st0);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_reuse_binning(const GhrDims &d, const Layout &L, const Layout &Lold, const char *old_state,
                                  char *state, uint64_t seq, cudaStream_t s) {
   const size_t VT = (size_t)d.V * L.T;
@@ -971,16 +1036,19 @@ cudaError_t launch_reuse_binning(const GhrDims &d, const Layout &L, const Layout
   return cudaGetLastError();
 }
 
-cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s) {
+cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t seq,
+                                      cudaStream_t s) {
   const int VT = d.V * L.T;
   if (VT == 0) return cudaSuccess;
-  tile_scan_schedule_kernel<<<1, kScanThreads1, 0, s>>>(
+  // one CTA per ~1024 tiles (every CTA reads all counts first: bounded so that pass stays short)
+  const int scan_ctas = std::min(32, std::max(1, (VT + kScanThreads1 - 1) / kScanThreads1));
+  tile_scan_schedule_kernel<<<scan_ctas, kScanThreads1, 0, s>>>(
       VT, (uint64_t)d.R_cap, (uint32_t)L.n_chunks, (uint32_t)L.n_hchunks, (uint32_t)L.n_heavy,
       use_partition(d, L) ? part_min(d) : 0xFFFFFFFFu, big_max(d),
       (const uint32_t *)(temp + L.t_tile_count), (uint2 *)(state + L.pub.off_ranges),
       (uint32_t *)(state + L.pub.off_order), (uint4 *)(temp + L.t_chunks), (uint2 *)(temp + L.t_hchunks),
       (uint32_t *)(temp + L.t_heavy), (uint32_t *)(temp + L.t_heavy_id), (uint32_t *)(temp + L.t_misc),
-      (GhrStatus *)(state + L.pub.off_status));
+      (GhrStatus *)(state + L.pub.off_status), seq);
   return cudaGetLastError();
 }
 

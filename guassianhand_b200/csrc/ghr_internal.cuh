@@ -10,6 +10,9 @@ namespace ghr {
 constexpr int kTile = 16;            // 16x16 pixel tiles
 constexpr int kRecBytes = 48;        // sorted instance record: 3 x float4
 constexpr int kChunk = 2048;         // instances per work item of the per-tile sort
+// words of the zero-initialised temp block `misc` (16 words): [0..4] binning work counts (binning.cu), then
+constexpr int kMiscVisible = 5;     // Gaussians with radius > 0, summed over views (preprocess)
+constexpr int kMiscPrefilter = 6;   // GHR_FLAG_PREFILTERED violated (preprocess)
 constexpr int kMaxSmemTiles = 16384; // tiles per view whose per-block counters fit in shared memory
 constexpr int kSeg = GHR_SEGMENT;     // instances per backward work unit
 constexpr int kAccStride = 12;       // floats per (view,Gaussian) backward accumulator
@@ -193,12 +196,12 @@ void set_error(const char *fmt, ...);
 cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &cam, const Gaussians &g,
                               float scale_modifier, uint32_t flags, char *state, char *temp, int32_t *radii,
                               cudaStream_t s);
-cudaError_t launch_init_status(char *status, GhrStatus st0, cudaStream_t s);
 cudaError_t launch_recolor_geom(const GhrDims &d, const Layout &L, const Layout &Lold, const Cameras &cam,
                                 const Gaussians &g, const char *old_state, char *state, int32_t *radii, cudaStream_t s);
 cudaError_t launch_reuse_binning(const GhrDims &d, const Layout &L, const Layout &Lold, const char *old_state,
                                  char *state, uint64_t seq, cudaStream_t s);
-cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
+cudaError_t launch_tile_scan_schedule(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t seq,
+                                      cudaStream_t s);
 cudaError_t launch_duplicate(const GhrDims &d, const Layout &L, char *state, char *temp, cudaStream_t s);
 cudaError_t launch_sort_gather(const GhrDims &d, const Layout &L, char *state, char *temp, uint64_t *dbg_keys,
                                uint32_t *dbg_plist, cudaStream_t s);

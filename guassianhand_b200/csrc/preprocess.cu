@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256)
 preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, float scale_modifier, uint32_t flags,
                   Cameras cam, Gaussians g, float4 *__restrict__ geom, uint8_t *__restrict__ clamped,
                   int32_t *__restrict__ radii, uint32_t *__restrict__ tile_count, uint32_t *__restrict__ tilemax,
-                  GhrStatus *__restrict__ status, int T, int smem_tiles) {
+                  uint32_t *__restrict__ misc, int T, int smem_tiles) {
   // s_cnt[t]: instances this block's Gaussians put on tile t of its view (smem_tiles == T), flushed
   // as one RED per touched tile; with more tiles than fit (smem_tiles == 0) every instance is a RED
   extern __shared__ uint32_t s_cnt[];
@@ -269,7 +269,10 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
         }
       }
     } else if (flags & GHR_FLAG_PREFILTERED) {
-      // upstream traps here ("Point is filtered although prefiltered is set"); we only cull.
+      // upstream prints "Point is filtered although prefiltered is set" and __trap()s here, which takes the CUDA
+      // context down; the point is culled and the violation reported in GhrStatus.overflow (GHR_STATUS_PREFILTER;
+      // the tile scan assembles the status from the zero-initialised misc words)
+      atomicOr(&misc[kMiscPrefilter], 1u);
     }
     size_t e = (size_t)v * P + i;
     geom[4 * e + 0] = q0;
@@ -280,7 +283,7 @@ preprocess_kernel(int P, int V, int H, int W, int M, int D, int gx, int gy, floa
     radii[e] = radius;
   }
   const uint32_t nvis = __popc(__ballot_sync(0xFFFFFFFFu, visible));
-  if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&status->n_visible, nvis);
+  if ((threadIdx.x & 31) == 0 && nvis) atomicAdd(&misc[kMiscVisible], nvis);
   if (smem_tiles) {
     __syncthreads();
     for (int k = threadIdx.x; k < smem_tiles; k += blockDim.x) {
@@ -413,7 +416,7 @@ cudaError_t launch_preprocess(const GhrDims &d, const Layout &L, const Cameras &
         d.P, d.V, d.H, d.W, d.M, d.sh_degree, L.gx, L.gy, scale_modifier, flags, cam, g,
         (float4 *)(state + L.pub.off_geom), d.M > 0 ? (uint8_t *)(state + L.pub.off_clamped) : nullptr, radii,
         (uint32_t *)(temp + L.t_tile_count), (uint32_t *)(state + L.pub.off_tilemax),
-        (GhrStatus *)(state + L.pub.off_status), L.T, smem_tiles);
+        (uint32_t *)(temp + L.t_misc), L.T, smem_tiles);
     return cudaSuccess;
   };
   cudaError_t e = vec_sh ? launch(preprocess_kernel<true>) : launch(preprocess_kernel<false>);

@@ -38,6 +38,8 @@ extern "C" {
 #define GHR_ECUDA (-3)      /* a CUDA call failed; text in ghr_last_error() */
 #define GHR_EOVERFLOW (-4)  /* ghr_read_status: R exceeded R_cap in the last forward */
 
+#define GHR_STATUS_OVERFLOW 1u
+#define GHR_STATUS_PREFILTER 2u
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
@@ -87,7 +89,9 @@ typedef struct GhrLayout {
 
 typedef struct GhrStatus {
   uint64_t R;          /* number of (tile, Gaussian) instances the forward produced (all views) */
-  uint32_t overflow;   /* 1 if R > R_cap: the forward output is invalid, retry with larger R_cap */
+  uint32_t overflow;   /* bit 0 (GHR_STATUS_OVERFLOW): R > R_cap, the forward output is invalid, retry with a larger
+                          R_cap; bit 1 (GHR_STATUS_PREFILTER): GHR_FLAG_PREFILTERED was set and a Gaussian failed the
+                          near-plane test (upstream's in_frustum traps there); the point was culled */
   uint32_t n_visible;  /* Gaussians (summed over views) with radius > 0 */
   uint64_t reserved[2]; /* [0] = GhrForwardArgs.seq of the forward that wrote this status;
                            [1] = number of backward work units (tile, segment) the forward blend emitted */

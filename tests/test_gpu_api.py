@@ -104,6 +104,30 @@ def test_argument_errors_match_upstream(cuda_device):
           rotations=torch.zeros(4, 4))
 
 
+def test_prefiltered_violation_raises_and_context_survives(cuda_device):
+    """upstream's in_frustum prints "Point is filtered although prefiltered is set" and traps when
+    settings.prefiltered is set and a point fails the near-plane test; here the forward raises that text (no lost
+    CUDA context).  With every point in front of the camera prefiltered=True renders exactly like False."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    dev = cuda_device
+    sc = scenes.two_hand_scene(2000, seed=3)
+    cam = scenes.fibonacci_cameras(2, 64, 64, seed=3)[0]
+    rs = _settings(cam, np.zeros(3, np.float32), dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().to(dev)
+    kw = dict(means2D=torch.zeros(sc.P, 3, device=dev), opacities=t(sc.opacities), colors_precomp=t(sc.colors),
+              scales=t(sc.scales), rotations=t(sc.rotations))
+    xyz = t(sc.means3D)
+    img0, rad0 = GaussianRasterizer(raster_settings=rs)(means3D=xyz, **kw)
+    img1, rad1 = GaussianRasterizer(raster_settings=rs._replace(prefiltered=True))(means3D=xyz, **kw)
+    assert torch.equal(img0, img1) and torch.equal(rad0, rad1)
+    behind = xyz.clone()
+    behind[7] = t(cam.campos) - 5.0 * (xyz.mean(0) - t(cam.campos))         # one point behind the camera
+    with pytest.raises(RuntimeError, match="Point is filtered although prefiltered is set"):
+        GaussianRasterizer(raster_settings=rs._replace(prefiltered=True))(means3D=behind, **kw)
+    img2, _ = GaussianRasterizer(raster_settings=rs)(means3D=behind, **kw)   # the context is alive, the point culled
+    assert torch.isfinite(img2).all()
+
+
 def test_batched_views_autograd_equals_view_loop(cuda_device):
     from guassianhand_b200 import rasterize_views
     dev = cuda_device

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libghr.so")
 GHR_OK, GHR_EINVAL, GHR_ENOSPC, GHR_ECUDA, GHR_EOVERFLOW = 0, -1, -2, -3, -4
 GHR_FLAG_PREFILTERED, GHR_FLAG_DEBUG = 1, 2
 GHR_STATUS_OVERFLOW, GHR_STATUS_PREFILTER = 1, 2
-GHR_ABI_VERSION = 10
+GHR_ABI_VERSION = 11
 GHR_NSTAGES_FWD, GHR_NSTAGES_BWD = 5, 2
 FWD_STAGES = ["preprocess", "tile_scan", "duplicate", "sort_gather", "blend_forward"]
 BWD_STAGES = ["blend_backward", "preprocess_backward"]
@@ -20,6 +20,7 @@ BWD_STAGES = ["blend_backward", "preprocess_backward"]
 EXPORTS = ["ghr_abi_version", "ghr_last_error", "ghr_struct_size", "ghr_layout", "ghr_forward", "ghr_backward",
            "ghr_mark_visible", "ghr_read_status_async", "ghr_event_create", "ghr_event_destroy", "ghr_event_record",
            "ghr_event_elapsed_ms", "ghr_fp32_probe", "ghr_attributes_forward", "ghr_attributes_backward",
+           "ghr_sh_blend_forward", "ghr_sh_blend_backward",
            "ghr_cameras_from_w2c", "ghr_comm_create", "ghr_comm_handle", "ghr_comm_connect", "ghr_comm_buffer", "ghr_comm_allreduce",
            "ghr_comm_status", "ghr_comm_destroy"]
 GHR_COMM_MAX_RANKS, GHR_COMM_HANDLE_BYTES = 8, 128
@@ -130,6 +131,10 @@ def lib():
     L.ghr_attributes_forward.argtypes = [C.POINTER(GhrAttributeArgs), _vp]
     L.ghr_attributes_backward.restype = C.c_int
     L.ghr_attributes_backward.argtypes = [C.POINTER(GhrAttributeArgs), C.POINTER(GhrAttributeGrads), _vp]
+    L.ghr_sh_blend_forward.restype = C.c_int
+    L.ghr_sh_blend_forward.argtypes = [C.c_int64, _vp, _vp, _vp, _vp, _vp]
+    L.ghr_sh_blend_backward.restype = C.c_int
+    L.ghr_sh_blend_backward.argtypes = [C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ghr_cameras_from_w2c.restype = C.c_int
     L.ghr_cameras_from_w2c.argtypes = [C.c_int32, _vp, _vp, C.c_int32, C.c_int32, C.c_float, C.c_float, _vp, _vp, _vp,
                                        _vp, _vp]

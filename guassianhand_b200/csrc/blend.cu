@@ -95,6 +95,14 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Release counter of a ring stage: every warp's add RELEASES its generic-proxy reads of the stage, the add that
+// completes the count ACQUIRES them, and the refilling lane then orders the async-proxy write behind them with
+// fence.proxy.async -- the WAR edge between a warp's LDS of a stage and the next bulk copy into it.
+__device__ __forceinline__ uint32_t atom_add_acq_rel_cta(uint32_t *p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -488,11 +496,11 @@ blend_forward_kernel(int H, int W, int gx, int T, Cameras cam, const uint32_t *_
       tl_blend += clock64() - tl_c0;
 #endif
     }
-    // release the stage; the last warp to do so refills it with round r + kStages.  (A relaxed counter:
-    // the warp's loads of the stage have completed -- their values were consumed above.)
+    // release the stage; the last warp to do so refills it with round r + kStages (acq_rel counter: see
+    // atom_add_acq_rel_cta)
     __syncwarp();
     if (lane == 0) {
-      if (atomicAdd(&sb.released[s], 1u) == (uint32_t)kFwdWarps - 1u) {
+      if (atom_add_acq_rel_cta(&sb.released[s], 1u) == (uint32_t)kFwdWarps - 1u) {
         *(volatile uint32_t *)&sb.released[s] = 0u;
         const uint32_t nr = r + kStages;
         if (nr < rounds) {

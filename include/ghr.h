@@ -43,7 +43,7 @@ extern "C" {
 #define GHR_FLAG_PREFILTERED 1u /* settings.prefiltered (renderer_one_shot.py:292) */
 #define GHR_FLAG_DEBUG 2u       /* settings.debug (:293): sync + check after every launch */
 
-#define GHR_ABI_VERSION 10
+#define GHR_ABI_VERSION 11
 #define GHR_SEGMENT 128 /* instances per backward work unit / forward checkpoint interval */
 
 /* stage ids for the optional stage_events arrays */
@@ -259,6 +259,16 @@ typedef struct GhrAttributeGrads {
 
 int ghr_attributes_forward(const GhrAttributeArgs *args, void *cuda_stream);
 int ghr_attributes_backward(const GhrAttributeArgs *args, const GhrAttributeGrads *grads, void *cuda_stream);
+
+/* SH path of the attribute blending (use_rgb = false; /root/reference/tgs/models/renderer_one_shot.py:329-334), n =
+ * P * 16 * 3 coefficients, elementwise:   w == NULL: out = x;   w only: out = x * w;   w and b: out = (x * w) * w + b
+ * (the reference multiplies by color_w a second time when color_b is given, :333-334 -- kept).  b without w is
+ * an error, as in the reference (it dereferences color_w).  The geometry attributes of that path go through
+ * ghr_attributes_forward with rgb_raw == colors == NULL. */
+int ghr_sh_blend_forward(int64_t n, const float *x, const float *w, const float *b, float *out, void *cuda_stream);
+/* d_x / d_w / d_b: NULL = not wanted */
+int ghr_sh_blend_backward(int64_t n, const float *x, const float *w, const float *b, const float *dL_dout, float *d_x,
+                          float *d_w, float *d_b, void *cuda_stream);
 
 /* ---- gradient all-reduce over NVLink peer memory (SURVEY.md §8(e) stage 2) ----
  * Replaces the NCCL all-reduce Lightning DDP performs for the reference (/root/reference/infer_one_shot.py:631,638)

@@ -64,6 +64,57 @@ def test_cuda_attribute_head_matches_oracle(cuda_device, cfg):
         assert float((gg - gr).abs().max()) / den <= 1e-5, k
 
 
+def test_oracle_sh_path_matches_reference_expression():
+    """use_rgb = False (:201-204, :329-334): no sigmoid on the SH logits; color_w applied twice with color_b."""
+    d = _inputs(32, 1)
+    d.pop("rgb_raw")
+    g = torch.Generator().manual_seed(4)
+    shs_raw = torch.randn(32, 48, generator=g)
+    cw, cb = d["color_w"].view(-1, 16, 3), d["color_b"].view(-1, 16, 3)
+    *_, shs = activate_and_blend_ref(**d, shs_raw=shs_raw)
+    assert shs.shape == (32, 16, 3)
+    assert torch.allclose(shs, shs_raw.view(-1, 16, 3) * cw * cw + cb)
+    d.pop("color_b")
+    *_, shs = activate_and_blend_ref(**d, shs_raw=shs_raw)
+    assert torch.allclose(shs, shs_raw.view(-1, 16, 3) * cw)
+    d.pop("color_w")
+    *_, shs = activate_and_blend_ref(**d, shs_raw=shs_raw)
+    assert torch.equal(shs, shs_raw.view(-1, 16, 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("terms", ["w+b", "w", "none"])
+def test_cuda_sh_path_matches_oracle(cuda_device, terms):
+    from guassianhand_b200.attributes import activate_and_blend
+    P = 3001
+    base = _inputs(P, 7)
+    base.pop("rgb_raw")
+    if terms != "w+b":
+        base.pop("color_b")
+    if terms == "none":
+        base.pop("color_w")
+    shs_raw = torch.randn(P, 48, generator=torch.Generator().manual_seed(8))
+    ref_in = {k: v.double().requires_grad_(True) for k, v in {**base, "shs_raw": shs_raw}.items()}
+    gpu_in = {k: v.to(cuda_device).requires_grad_(True) for k, v in {**base, "shs_raw": shs_raw}.items()}
+    ref = activate_and_blend_ref(**ref_in)
+    out = activate_and_blend(**gpu_in)
+    assert out[4].shape == (P, 16, 3)
+    for a, b in zip(out, ref):
+        assert torch.allclose(a.detach().cpu().double(), b.detach(), rtol=2e-6, atol=1e-7)
+    gen = torch.Generator().manual_seed(9)
+    cot = [torch.randn(b.shape, generator=gen) for b in ref]
+    sum((b * w.double()).sum() for b, w in zip(ref, cot)).backward()
+    sum((a * w.to(cuda_device)).sum() for a, w in zip(out, cot)).backward()
+    for k in ref_in:
+        gr, gg = ref_in[k].grad, gpu_in[k].grad
+        assert gr is not None and gg is not None, k
+        den = float(gr.abs().max()) or 1.0
+        assert float((gg.detach().cpu().double() - gr).abs().max()) / den <= 1e-5, k
+    with pytest.raises(AttributeError):                       # color_b without color_w, as the reference
+        activate_and_blend(**{k: v for k, v in gpu_in.items() if k not in ("color_w", "color_b")},
+                           color_b=torch.zeros(P, 48, device=cuda_device))
+
+
 @pytest.mark.gpu
 def test_attribute_head_feeds_the_rasterizer(cuda_device):
     """Head -> rasterize_views -> loss: gradients reach the raw head outputs and blending terms."""

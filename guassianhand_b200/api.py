@@ -138,6 +138,7 @@ def _raw_stream(dev) -> int:
 
 
 _layouts = {}
+_grad_plans = {}     # (P, M, scales/rotations present) -> carving of backward_raw's gradient allocation
 
 
 def _layout(P, V, H, W, M, sh_degree, cap):
@@ -356,24 +357,42 @@ def backward_raw(cams: _Cams, fwd_state, R_cap, dL_dout, means3D, opacities, sca
     g = None if accumulate_into is None else dict(accumulate_into)
     a.accumulate = 1 if (g is not None and accumulate) else 0
     if g is None:
-        # one allocation, carved into the per-attribute gradients (each block 16-byte aligned)
-        shapes = [("dL_dmeans3D", (P, 3)), ("dL_dopacity", (P, 1)), ("dL_dcov3D", (P, 6))]
-        shapes.append(("dL_dsh", (P, M, 3)) if M > 0 else ("dL_dcolors", (P, 3)))
-        if scales is not None and scales.numel():
-            shapes += [("dL_dscales", (P, 3)), ("dL_drotations", (P, 4))]
-        sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for _, sh in shapes]
-        flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-        g, o = {"_flat": flat}, 0
-        for (name, sh), n in zip(shapes, sizes):
-            g[name] = flat[o:o + int(torch.Size(sh).numel())].view(sh)
-            o += n
+        # one allocation, carved into the per-attribute gradients (each block 16-byte aligned); the carving plan
+        # is cached per shape
+        has_sr = scales is not None and scales.numel() > 0
+        plan = _grad_plans.get((P, M, has_sr))
+        if plan is None:
+            shapes = [("dL_dmeans3D", (P, 3)), ("dL_dopacity", (P, 1)), ("dL_dcov3D", (P, 6))]
+            shapes.append(("dL_dsh", (P, M, 3)) if M > 0 else ("dL_dcolors", (P, 3)))
+            if has_sr:
+                shapes += [("dL_dscales", (P, 3)), ("dL_drotations", (P, 4))]
+            items, o = [], 0
+            for name, sh in shapes:
+                n = int(torch.Size(sh).numel())
+                items.append((name, sh, o, n))
+                o += (n + 3) // 4 * 4
+            if len(_grad_plans) > 64:
+                _grad_plans.clear()
+            plan = _grad_plans[(P, M, has_sr)] = (items, o)
+        flat = torch.empty(plan[1], dtype=torch.float32, device=dev)
+        g = {"_flat": flat}
+        base = flat.data_ptr()
+        for name, sh, o, n in plan[0]:
+            g[name] = flat[o:o + n].view(sh)
+            setattr(a, name, base + 4 * o if n else None)
+    else:
+        for k in ("dL_dmeans3D", "dL_dcolors", "dL_dopacity", "dL_dcov3D", "dL_dsh", "dL_dscales", "dL_drotations"):
+            setattr(a, k, _ptr(g.get(k)))
     if want_means2D:
         g["dL_dmeans2D"] = torch.empty(cams.V, P, 3, dtype=torch.float32, device=dev)
+        a.dL_dmeans2D = _ptr(g["dL_dmeans2D"])
+    elif g.get("dL_dmeans2D") is not None:
+        a.dL_dmeans2D = _ptr(g["dL_dmeans2D"])
     if want_conic:
         g["dL_dconic"] = torch.empty(cams.V, P, 4, dtype=torch.float32, device=dev)
-    for k in ("dL_dmeans3D", "dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dcov3D", "dL_dsh", "dL_dscales",
-              "dL_drotations", "dL_dconic"):
-        setattr(a, k, _ptr(g.get(k)))
+        a.dL_dconic = _ptr(g["dL_dconic"])
+    elif g.get("dL_dconic") is not None:
+        a.dL_dconic = _ptr(g["dL_dconic"])
     if stage_events is not None:
         a.stage_events = stage_events.ptr()
     N.check(L.ghr_backward(C.byref(a), stream), "ghr_backward")
@@ -454,8 +473,9 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (cams, means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, int(rs.sh_degree), float(rs.scale_modifier))
         M = 0 if sh_c is None else sh_c.shape[1]
         dev_index = means3D_c.device.index
-        nz = lambda t_: None if (t_ is None or t_.numel() == 0) else t_
-        gtensors = (means3D, opacities, nz(scales), nz(rotations), nz(cov3Ds_precomp), rs.viewmatrix, rs.projmatrix, rs.campos)
+        # (sc_c / rot_c / cov_c are None exactly when the argument is absent or empty)
+        gtensors = (means3D, opacities, scales if sc_c is not None else None, rotations if rot_c is not None else None,
+                    cov3Ds_precomp if cov_c is not None else None, rs.viewmatrix, rs.projmatrix, rs.campos)
         gscalars = (means3D.shape[0], cams.H, cams.W, cams.tanfovx, cams.tanfovy, float(rs.scale_modifier), _flags(rs))
         hit = None if rs.debug else _GeomCache.lookup(dev_index, gtensors, gscalars)
         if hit is not None:
@@ -477,11 +497,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.cams = cams
         ctx.R_cap = res.R_cap
         ctx.num_rendered = res.R
-        ctx.save_for_backward(means3D_c, opac_c, sc_c if sc_c is not None else torch.empty(0),
-                              rot_c if rot_c is not None else torch.empty(0),
-                              cov_c if cov_c is not None else torch.empty(0),
-                              sh_c if sh_c is not None else torch.empty(0),
-                              col_c if col_c is not None else torch.empty(0), res.state)
+        ctx.save_for_backward(means3D_c, opac_c, sc_c, rot_c, cov_c, sh_c, col_c, res.state)
         radii = res.radii[0]
         ctx.mark_non_differentiable(radii)
         if want_mask:
@@ -492,8 +508,6 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_out_color, _grad_radii, grad_mask=None):
         rs = ctx.raster_settings
         means3D, opac, sc, rot, cov, sh, col, state = ctx.saved_tensors
-        none_if_empty = lambda t: None if t.numel() == 0 else t
-        sc, rot, cov, sh, col = map(none_if_empty, (sc, rot, cov, sh, col))
         call = lambda: backward_raw(ctx.cams, state, ctx.R_cap, grad_out_color.unsqueeze(0), means3D, opac, sc, rot,
                                     cov, sh, col, int(rs.sh_degree), float(rs.scale_modifier), flags=_flags(rs),
                                     dL_dmask=grad_mask.unsqueeze(0) if (ctx.want_mask and grad_mask is not None) else None)
@@ -501,7 +515,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             try:
                 g = call()
             except Exception:
-                torch.save([t.detach().cpu() for t in ctx.saved_tensors[:-1]] + [grad_out_color.detach().cpu()],
+                torch.save([None if t is None else t.detach().cpu() for t in ctx.saved_tensors[:-1]] + [grad_out_color.detach().cpu()],
                            "snapshot_bw.dump")
                 print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
                 raise
@@ -563,9 +577,10 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        e = lambda t: torch.Tensor([]) if t is None else t
-        return rasterize_gaussians(means3D, means2D, e(shs), e(colors_precomp), opacities, e(scales), e(rotations),
-                                   e(cov3D_precomp), rs, _want_mask)
+        # (upstream substitutes torch.Tensor([]) for the absent arguments here; the node takes None directly --
+        # three tensor constructions per call less on a host-bound path)
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, rs, _want_mask)
 
 
 # ------------------------------------------------------------------ multi-view batched entry

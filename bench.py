@@ -584,17 +584,18 @@ def run_ours(args):
         res = sl["step"].replay()
         ge1.record(main)
         g_gpu.append((ge0, ge1))
-        loss = torch.vdot(res.color.reshape(-1), dL_flat)
-        for j, st in enumerate(sl["step"].states()):
-            NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
-                                                    main.cuda_stream), "status")
-        sl["ev_used"].record(main)
+        sl["ev_used"].record(main)                  # the slot's inputs have been consumed
+        # everything that follows the replay -- the loss, the status reads and the downloads -- runs on the
+        # download stream, so the main stream goes straight on to the next step's replay (the other slot)
         down.wait_stream(main)
         with torch.cuda.stream(down):
+            loss = torch.vdot(res.color.reshape(-1), dL_flat)
+            for j, st in enumerate(sl["step"].states()):
+                NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
+                                                        down.cuda_stream), "status")
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             c0.record(down)
             sl["host_grads"].copy_(sl["grads"].flat, non_blocking=True)
-            loss.record_stream(down)
             sl["host_loss"].copy_(loss.reshape(1), non_blocking=True)
             c1.record(down)
             g_copy["d2h"].append((c0, c1))

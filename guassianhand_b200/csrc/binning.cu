@@ -110,30 +110,42 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
   {
     unsigned long long a_sum = 0, b_sum = 0;
     uint32_t a_l = 0, a_h = 0, a_hc = 0, a_nbig = 0, a_merge = 0, b_l = 0, b_h = 0, b_hc = 0;
-    for (int t0 = 0; t0 < VT; t0 += kScanThreads1) {
-      const int t = t0 + tid;
-      const bool valid = t < VT;
-      const uint32_t c = valid ? tile_count[t] : 0u;
-      const bool pre = valid && t < lo;
-      uint32_t l = 0, h = 0, hc = 0;
-      if (c > part_min) {
-        h = 1;
-        hc = (c + kChunk - 1) / kChunk;
-      } else if (!(c > (uint32_t)kChunk && c <= big_max)) {   // (a big list is ONE item of sort_big_kernel)
-        l = (c + kChunk - 1) / kChunk;           // one final item, or plain chunks finished by the rank merge
+    // (the loads of up to kPre rounds are issued together: one memory round trip instead of one per round)
+    constexpr int kPre = 8;
+    for (int tb = 0; tb < VT; tb += kPre * kScanThreads1) {
+      uint32_t cv[kPre];
+#pragma unroll
+      for (int u = 0; u < kPre; u++) {
+        const int t = tb + u * kScanThreads1 + tid;
+        cv[u] = t < VT ? tile_count[t] : 0u;
       }
-      a_sum += c; a_l += l; a_h += h; a_hc += hc;
-      a_nbig += c > (uint32_t)kChunk;
-      a_merge += l > 1u ? l : 0u;
-      if (pre) { b_sum += c; b_l += l; b_h += h; b_hc += hc; }
-      // class counters are warp-aggregated (match.any): most tiles are empty, and thousands of shared-memory
-      // atomics on one address would serialise
-      const int cls = valid ? size_class(c) : kClasses;
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
-      if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
-      if (lo > 0) {                                 // (block-uniform)
-        const uint32_t bpeers = __match_any_sync(0xFFFFFFFFu, pre ? cls : kClasses);
-        if (pre && lane == __ffs(bpeers) - 1) atomicAdd(&s_before[cls], (uint32_t)__popc(bpeers));
+#pragma unroll
+      for (int u = 0; u < kPre; u++) {
+        if (tb + u * kScanThreads1 >= VT) break;      // (block-uniform)
+        const int t = tb + u * kScanThreads1 + tid;
+        const bool valid = t < VT;
+        const uint32_t c = cv[u];
+        const bool pre = valid && t < lo;
+        uint32_t l = 0, h = 0, hc = 0;
+        if (c > part_min) {
+          h = 1;
+          hc = (c + kChunk - 1) / kChunk;
+        } else if (!(c > (uint32_t)kChunk && c <= big_max)) {   // (a big list is ONE item of sort_big_kernel)
+          l = (c + kChunk - 1) / kChunk;           // one final item, or plain chunks finished by the rank merge
+        }
+        a_sum += c; a_l += l; a_h += h; a_hc += hc;
+        a_nbig += c > (uint32_t)kChunk;
+        a_merge += l > 1u ? l : 0u;
+        if (pre) { b_sum += c; b_l += l; b_h += h; b_hc += hc; }
+        // class counters are warp-aggregated (match.any): most tiles are empty, and thousands of shared-memory
+        // atomics on one address would serialise
+        const int cls = valid ? size_class(c) : kClasses;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
+        if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
+        if (lo > 0) {                                 // (block-uniform)
+          const uint32_t bpeers = __match_any_sync(0xFFFFFFFFu, pre ? cls : kClasses);
+          if (pre && lane == __ffs(bpeers) - 1) atomicAdd(&s_before[cls], (uint32_t)__popc(bpeers));
+        }
       }
     }
 #pragma unroll
@@ -208,12 +220,24 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
     hoff += s_wh[w];
     hcoff += s_whc[w];
   }
-  if (tid == 0) {
-    uint32_t acc = 0;
-    for (int c = kClasses - 1; c >= 0; c--) {     // largest class first; empty tiles (class 0) last
-      s_cur[c] = acc + s_before[c];
-      acc += s_cls[c];
+  if (warp == 0) {
+    // launch-order offsets: largest class first, empty tiles (class 0) last.  Lane l owns the classes at the
+    // reversed positions 2l and 2l+1 (class = kClasses - 1 - position): one warp scan instead of a serial walk
+    static_assert(kClasses <= 64, "two classes per lane");
+    const int r0 = 2 * lane, r1 = r0 + 1;
+    const int c0 = kClasses - 1 - r0, c1 = kClasses - 1 - r1;
+    const uint32_t n0 = c0 >= 0 ? s_cls[c0] : 0u, n1 = c1 >= 0 ? s_cls[c1] : 0u;
+    uint32_t incl2 = n0 + n1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl2, o);
+      if (lane >= o) incl2 += up;
     }
+    const uint32_t base2 = incl2 - (n0 + n1);
+    if (c0 >= 0) s_cur[c0] = base2 + s_before[c0];
+    if (c1 >= 0) s_cur[c1] = base2 + n0 + s_before[c1];
+  }
+  if (tid == 0) {
     if (blockIdx.x == 0) {
       const uint64_t total = s_all.sum;
       // the whole status: preprocess left its two words in misc (zeroed with the rest of the temp prefix), the

@@ -103,7 +103,8 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
     s_pre = ScanTotals{0ull, 0u, 0u, 0u, 0u, 0u};
   }
   __syncthreads();
-  const int span = (VT + (int)gridDim.x - 1) / (int)gridDim.x;
+  // spans are multiples of the block size, so a pass-1 round lies entirely in front of the span or not at all
+  const int span = ((VT + (int)gridDim.x - 1) / (int)gridDim.x + kScanThreads1 - 1) / kScanThreads1 * kScanThreads1;
   const int lo = min(VT, (int)blockIdx.x * span), hi = min(VT, lo + span);
 
   // ---- pass 1: every count, reduced over all tiles and over the tiles in front of the span ----
@@ -125,7 +126,7 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
         const int t = tb + u * kScanThreads1 + tid;
         const bool valid = t < VT;
         const uint32_t c = cv[u];
-        const bool pre = valid && t < lo;
+        const bool pre = tb + u * kScanThreads1 < lo;   // block-uniform (lo is a multiple of the block size)
         uint32_t l = 0, h = 0, hc = 0;
         if (c > part_min) {
           h = 1;
@@ -141,10 +142,9 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
         // atomics on one address would serialise
         const int cls = valid ? size_class(c) : kClasses;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, cls);
-        if (lane == __ffs(peers) - 1) atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
-        if (lo > 0) {                                 // (block-uniform)
-          const uint32_t bpeers = __match_any_sync(0xFFFFFFFFu, pre ? cls : kClasses);
-          if (pre && lane == __ffs(bpeers) - 1) atomicAdd(&s_before[cls], (uint32_t)__popc(bpeers));
+        if (lane == __ffs(peers) - 1) {
+          atomicAdd(&s_cls[cls], (uint32_t)__popc(peers));
+          if (pre) atomicAdd(&s_before[cls], (uint32_t)__popc(peers));
         }
       }
     }
@@ -212,13 +212,29 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
     s_whc[warp] = hcincl;
   }
   __syncthreads();                             // (and the pass-1 totals are complete)
-  uint64_t start = s_pre.sum + (incl - sum);
-  uint32_t loff = s_pre.l + (lincl - lsum), hoff = s_pre.h + (hincl - hsum), hcoff = s_pre.hc + (hcincl - hcsum);
-  for (int w = 0; w < warp; w++) {
-    start += s_warp[w];
-    loff += s_wl[w];
-    hoff += s_wh[w];
-    hcoff += s_whc[w];
+  if (warp == 0) {
+    // exclusive prefix of the 32 warp totals, in place (one warp scan instead of a serial walk in every thread)
+    uint64_t a = s_warp[lane];
+    uint32_t b = s_wl[lane], c = s_wh[lane], d = s_whc[lane];
+    const uint64_t a0 = a;
+    const uint32_t b0 = b, c0 = c, d0 = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t ua = __shfl_up_sync(0xFFFFFFFFu, a, o);
+      const uint32_t ub = __shfl_up_sync(0xFFFFFFFFu, b, o);
+      const uint32_t uc = __shfl_up_sync(0xFFFFFFFFu, c, o);
+      const uint32_t ud = __shfl_up_sync(0xFFFFFFFFu, d, o);
+      if (lane >= o) {
+        a += ua;
+        b += ub;
+        c += uc;
+        d += ud;
+      }
+    }
+    s_warp[lane] = a - a0;
+    s_wl[lane] = b - b0;
+    s_wh[lane] = c - c0;
+    s_whc[lane] = d - d0;
   }
   if (warp == 0) {
     // launch-order offsets: largest class first, empty tiles (class 0) last.  Lane l owns the classes at the
@@ -257,6 +273,10 @@ tile_scan_schedule_kernel(int VT, uint64_t R_cap, uint32_t item_cap, uint32_t hc
     }
   }
   __syncthreads();
+  // this thread's run starts at: tiles in front of the span + earlier warps + earlier lanes
+  uint64_t start = s_pre.sum + s_warp[warp] + (incl - sum);
+  uint32_t loff = s_pre.l + s_wl[warp] + (lincl - lsum), hoff = s_pre.h + s_wh[warp] + (hincl - hsum),
+           hcoff = s_pre.hc + s_whc[warp] + (hcincl - hcsum);
   const uint32_t lt_mask = (1u << lane) - 1u;
   for (int j = 0; j < per; j++) {
     const int t = t0 + j;

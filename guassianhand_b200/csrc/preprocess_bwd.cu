@@ -72,18 +72,58 @@ preprocess_backward_kernel(int P, int V, int H, int W, int M, int D, float scale
   // SH gradients are accumulated over views directly in the output row (thread-private)
   bool sh_first = true;
 
+  // The per-view loads are software-pipelined: one thread walks its Gaussian's V views serially (the view sum
+  // stays in registers: deterministic, no atomics) and the kernel runs at ~20 % occupancy, so a view's loads must
+  // be in flight while the previous view is computed.  The radius (which gates the other loads: a culled
+  // (view, Gaussian) reads one float4) runs two views ahead, the record and the accumulator row one view ahead.
+  struct ViewLoads {
+    float4 q0, q1, a0, a1;
+    float m02;
+  };
+  auto load_view = [&](int v_, ViewLoads &L_) {
+    const size_t e_ = (size_t)v_ * P + i;
+    L_.q0 = geom[4 * e_ + 0];
+    L_.q1 = geom[4 * e_ + 1];
+    const float *a_ = acc + e_ * kAccStride;
+    L_.a0 = *reinterpret_cast<const float4 *>(a_);
+    L_.a1 = *reinterpret_cast<const float4 *>(a_ + 4);
+    L_.m02 = a_[8];
+  };
+  // (SH variants: the per-view SH arithmetic dominates and the extra live registers cost occupancy -- 167
+  // registers for the 128-bit variant -- so they load at the point of use)
+  constexpr bool kPipe = !HAS_SH;
+  int rad_cur = 0, rad_next = 0;
+  ViewLoads cur_l, next_l;
+  if (kPipe) {
+    rad_cur = __float_as_int(geom[4 * (size_t)i + 3].x);
+    rad_next = V > 1 ? __float_as_int(geom[4 * ((size_t)P + i) + 3].x) : 0;
+    if (rad_cur > 0) load_view(0, cur_l);
+  }
+
   for (int v = 0; v < V; v++) {
     const size_t e = (size_t)v * P + i;
-    const float4 q3 = geom[4 * e + 3];
-    const int radius = __float_as_int(q3.x);
+    int radius;
+    ViewLoads vl;
+    if (kPipe) {
+      radius = rad_cur;
+      vl = cur_l;
+      // issue the loads of the views ahead before this view's arithmetic
+      const int rad_next2 = v + 2 < V ? __float_as_int(geom[4 * ((size_t)(v + 2) * P + i) + 3].x) : 0;
+      if (rad_next > 0) load_view(v + 1, next_l);
+      rad_cur = rad_next;
+      rad_next = rad_next2;
+      cur_l = next_l;
+    } else {
+      radius = __float_as_int(geom[4 * e + 3].x);
+      if (radius > 0) load_view(v, vl);
+    }
     float g2x = 0.f, g2y = 0.f, gA = 0.f, gB = 0.f, gC = 0.f;
     if (radius > 0) {
-      const float4 q0 = geom[4 * e + 0];
-      const float4 q1 = geom[4 * e + 1];
-      const float *a = acc + e * kAccStride;
-      const float4 a0 = *reinterpret_cast<const float4 *>(a);
-      const float4 a1 = *reinterpret_cast<const float4 *>(a + 4);
-      const float m02 = a[8];
+      const float4 q0 = vl.q0;
+      const float4 q1 = vl.q1;
+      const float4 a0 = vl.a0;
+      const float4 a1 = vl.a1;
+      const float m02 = vl.m02;
       const float dcr = a0.x, dcg = a0.y, dcb = a0.z, m00 = a0.w, m10 = a1.x, m01 = a1.y, m20 = a1.z, m11 = a1.w;
       const float cA = q0.z, cB = q0.w, cC = q1.x;
       // A.6 tail, factored per Gaussian: moments of w = G * dL/dalpha
@@ -358,20 +398,24 @@ cudaError_t launch_preprocess_backward(const GhrDims &d, const Layout &L, const 
                                        const Gaussians &g, float scale_modifier, const char *state,
                                        const float *acc, const GradOut &go, cudaStream_t s) {
   if (d.P == 0) return cudaSuccess;
-  int nb = (d.P + 127) / 128;
+#ifndef GHR_PBWD_THREADS
+#define GHR_PBWD_THREADS 128
+#endif
+  constexpr int kT = GHR_PBWD_THREADS;          // (build-time A/B: 64 balances 469 blocks over 148 SMs better)
+  int nb = (d.P + kT - 1) / kT;
   const float4 *geom = (const float4 *)(state + L.pub.off_geom);
   const uint8_t *cl = (const uint8_t *)(state + L.pub.off_clamped);
   const bool has_sh = g.shs && !g.colors_precomp;
   const bool vec_sh = has_sh && (d.M * 3) % 4 == 0 && ((uintptr_t)g.shs & 15) == 0 &&
                       (go.dsh == nullptr || ((uintptr_t)go.dsh & 15) == 0);
   if (vec_sh)
-    preprocess_backward_kernel<true, true><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+    preprocess_backward_kernel<true, true><<<nb, kT, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
                                                               cam, g, geom, cl, acc, go);
   else if (has_sh)
-    preprocess_backward_kernel<true, false><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+    preprocess_backward_kernel<true, false><<<nb, kT, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
                                                                cam, g, geom, cl, acc, go);
   else
-    preprocess_backward_kernel<false, false><<<nb, 128, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
+    preprocess_backward_kernel<false, false><<<nb, kT, 0, s>>>(d.P, d.V, d.H, d.W, d.M, d.sh_degree, scale_modifier,
                                                                 cam, g, geom, cl, acc, go);
   return cudaGetLastError();
 }

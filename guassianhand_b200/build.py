@@ -53,6 +53,8 @@ VARIANTS = {
     # A/B: forward blend occupancy (registers via min CTAs, shared memory via ring depth) against per-warp ILP
     "fwdilp8occ5": ["-DGHR_FWD_ILP=8", "-DGHR_FWD_MINCTAS=4", "-DGHR_FWD_STAGES=6"],   # the round-2 start point
     "fwdilp8occ8": ["-DGHR_FWD_ILP=8", "-DGHR_FWD_MINCTAS=8", "-DGHR_FWD_STAGES=4"],
+    "nohalfq": ["-DGHR_BWD_NO_HALFQ"],    # A/B: backward blend with one survivor queue per warp (8x8 block)
+    "nohalfq_count": ["-DGHR_BWD_NO_HALFQ", "-DGHR_COUNT"],
     "pbwd64": ["-DGHR_PBWD_THREADS=64"],  # A/B: preprocess_backward with 64-thread blocks
     "nored": ["-DGHR_NO_RED"],           # experiment: backward blend without its global reductions (wrong results)
 }

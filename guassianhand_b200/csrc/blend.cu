@@ -43,10 +43,19 @@ constexpr float kLog2e = 1.4426950408889634f;
 #define GHR_BWD_MINCTAS 7       // 72 registers (A/B: 6 CTAs at 76 registers 191 us, 7 at 72: 188.5, 8 at 64: 197.6)
 #endif
 constexpr int kIlpB = GHR_BWD_ILP;   // instances per backward iteration (build-time A/B)
-constexpr int kDirectMax = 4;    // <= this many contributing lanes: no warp reduction, direct REDs
+#ifndef GHR_BWD_DIRECTMAX
+#define GHR_BWD_DIRECTMAX 4
+#endif
+constexpr int kDirectMax = GHR_BWD_DIRECTMAX;    // <= this many contributing lanes: no warp reduction, direct REDs
 constexpr int kQPad = 8;         // padding entries on both sides of a survivor queue
 #ifndef GHR_BWD_WARPS
 #define GHR_BWD_WARPS 4          // build-time A/B: 4 = one CTA per unit, 2 = two half-tile CTAs per unit
+#endif
+// Backward survivor queues per HALF-warp (one 8x4 sub-block each) instead of per warp (an 8x8 block): 12 % fewer
+// warp iterations on the two-hand scene (68.9M -> 60.5M evaluated pairs), kernel 189 -> 183.5 us.
+// -DGHR_BWD_NO_HALFQ builds the per-warp queues (A/B); the two-CTA variant keeps them.
+#if !defined(GHR_BWD_NO_HALFQ) && !defined(GHR_BWD_HALFQ) && GHR_BWD_WARPS == 4
+#define GHR_BWD_HALFQ 1
 #endif
 static_assert(kStageN == kSeg, "a forward stage is one backward segment");
 
@@ -223,6 +232,32 @@ __device__ __forceinline__ uint32_t build_queue_idx(const uint8_t *msk, uint32_t
   __syncwarp();
   return total;
 }
+#ifdef GHR_BWD_HALFQ
+// Build-time variant (A/B): the two halves of a backward warp own ONE 8x4 sub-block each (two pixels per thread,
+// two rows apart) and walk their OWN survivor queue, so an instance that reaches only one of the warp's two
+// sub-blocks costs half a warp iteration instead of a whole one.  Returns the upper half's count, totalL the lower's.
+__device__ __forceinline__ uint32_t build_queue_half(const uint8_t *msk, uint32_t cnt, uint32_t limitU, uint32_t limitL,
+                                                     uint32_t bitU, uint32_t bitL, int lane, uint8_t *qU, uint8_t *qL,
+                                                     uint32_t &totalL) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t tU = 0, tL = 0;
+#pragma unroll
+  for (int w = 0; w < kSeg / 32; w++) {
+    const uint32_t e = w * 32 + lane;
+    const uint32_t m = e < cnt ? (uint32_t)msk[e] : 0u;
+    const bool hitU = e < limitU && (m & bitU) != 0u, hitL = e < limitL && (m & bitL) != 0u;
+    const uint32_t mU = __ballot_sync(0xFFFFFFFFu, hitU), mL = __ballot_sync(0xFFFFFFFFu, hitL);
+    if (hitU) qU[kQPad + tU + __popc(mU & lt)] = (uint8_t)e;
+    if (hitL) qL[kQPad + tL + __popc(mL & lt)] = (uint8_t)e;
+    tU += __popc(mU);
+    tL += __popc(mL);
+  }
+  __syncwarp();
+  totalL = tL;
+  return tU;
+}
+#endif
+
 // ---- forward ----
 // Thread = ONE pixel, a warp = one 8x4 sub-block, 8 warps per tile in two CTAs.  A tile's list is a serial
 // chain per warp (the transmittance recursion), and a launch has only a few hundred non-empty tiles: its
@@ -587,6 +622,18 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
       sum = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
             (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
     }
+#ifdef GHR_BWD_HALFQ
+    // the two half-rows of a row belong to different instances (ids[2 * slot + half]): no join, one RED each
+    if (t < ntask && sum != 0.f) {
+      const uint32_t slot = (r * 57u) >> 9, val = r - 9u * slot;      // r / 9 for r < 27
+#ifdef GHR_NO_RED
+      if (sum == 123.456f) accb[(size_t)ids[2u * slot + (t & 1u)] * kAccStride + val] = sum;
+#else
+      atomicAdd(accb + (size_t)ids[2u * slot + (t & 1u)] * kAccStride + val, sum);
+#endif
+    }
+    continue;
+#endif
     sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
     if (t < ntask && !(t & 1u)) {
       const uint32_t slot = (r * 57u) >> 9, val = r - 9u * slot;      // r / 9 for r < 27
@@ -622,8 +669,14 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   __shared__ __align__(16) uint8_t s_msk[kSeg + 16];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ __align__(16) float s_red[kW][kRingSlots * kSlotFloats];
+#ifdef GHR_BWD_HALFQ
+  static_assert(kW == 4, "the half-warp queues are built for one CTA per unit");
+  __shared__ uint32_t s_ids[kW][8];
+  __shared__ __align__(16) uint8_t s_q[kW][2][kSeg + 2 * kQPad];
+#else
   __shared__ uint32_t s_ids[kW][4];
   __shared__ __align__(16) uint8_t s_q[kW][kSeg + 2 * kQPad];
+#endif
   constexpr uint32_t kParts = kBlendWarps / kW;       // CTAs per unit
   const uint32_t bid = blockIdx.x / kParts, part = blockIdx.x % kParts;
   // The unit record {view*T + tile, segment, start of the tile's slab, instances up to the tile's last
@@ -639,7 +692,12 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   const int v = vt / (uint32_t)T, tile = vt % (uint32_t)T;
   const int lane = threadIdx.x & 31, wloc = threadIdx.x >> 5;      // warp inside the CTA
   const int warp = (int)part * kW + wloc;                           // warp inside the tile
+#ifdef GHR_BWD_HALFQ
+  const int half = lane >> 4, hl = lane & 15;
+  uint8_t *q = &s_q[wloc][half][0];
+#else
   uint8_t *q = &s_q[wloc][0];
+#endif
   const uint32_t cnt = min((uint32_t)kSeg, unit.w - first);   // instances past the last contributor never matter
   const size_t g0 = (size_t)unit.z + first;
 
@@ -656,22 +714,36 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
 
   // per-pixel state while the segment is in flight (all loads independent of each other)
   int lx, ly0;
+#ifdef GHR_BWD_HALFQ
+  // half u of warp w owns sub-block (w&1, 2*(w>>1) + u): column hl & 7, rows hl >> 3 and (hl >> 3) + 2
+  lx = ((warp & 1) << 3) + (hl & 7);
+  ly0 = ((warp >> 1) << 3) + 4 * half + (hl >> 3);
+  const int px = (tile % gx) * kTile + lx, py0 = (tile / gx) * kTile + ly0, py1 = py0 + 2;
+#else
   pixels_of_thread(warp, lane, lx, ly0);
   const int px = (tile % gx) * kTile + lx, py0 = (tile / gx) * kTile + ly0, py1 = py0 + 4;
+#endif
   const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
   const size_t N = (size_t)H * W;
   const float pxf = (float)px;
   const f32x2 npy = pk2(-(float)py0, -(float)py1);
   // per-tile float4 arrays are indexed by the FORWARD's thread id (8x4 sub-block * 32 + lane): the
   // thread's upper pixel lies in sub-block 4*(warp>>1) + (warp&1), the lower one two sub-blocks on
+#ifdef GHR_BWD_HALFQ
+  // (forward lane of a pixel = (row % 4) * 8 + column % 8: hl for the first pixel, hl + 16 for the second)
+  constexpr size_t kSlot1 = 16;
+  const size_t slot0 = (size_t)(4 * (warp >> 1) + (warp & 1) + 2 * half) * 32 + hl;
+#else
+  constexpr size_t kSlot1 = 64;
   const size_t slot0 = (size_t)(4 * (warp >> 1) + (warp & 1)) * 32 + lane;
-  const float4 fin0 = tilefinal[(size_t)vt * 256 + slot0], fin1 = tilefinal[(size_t)vt * 256 + slot0 + 64];
+#endif
+  const float4 fin0 = tilefinal[(size_t)vt * 256 + slot0], fin1 = tilefinal[(size_t)vt * 256 + slot0 + kSlot1];
   float4 c0 = make_float4(1.f, 0.f, 0.f, 0.f), c1 = c0;
   // (a checkpoint no later unit needs was never written: whatever is read there is not used)
   if (first) {
     const float4 *ck = ckpt + ((size_t)(unit.z / kSeg) + vt + unit.y) * 256 + slot0;
     c0 = ck[0];
-    c1 = ck[64];
+    c1 = ck[kSlot1];
   }
   float d0[3] = {0.f, 0.f, 0.f}, d1[3] = {0.f, 0.f, 0.f}, dm0 = 0.f, dm1 = 0.f;
   uint32_t last0 = 0, last1 = 0;
@@ -716,9 +788,23 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
   uint32_t pend = 0;                // instances parked in the ring (warp-uniform)
 
   // survivors of this warp's block among the instances that precede the warp's last contributor
+#ifdef GHR_BWD_HALFQ
+  uint32_t hlast = max(last0, last1);                        // last contributor of the thread's HALF
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) hlast = max(hlast, __shfl_xor_sync(0xFFFFFFFFu, hlast, o));
+  const uint32_t lastU = __shfl_sync(0xFFFFFFFFu, hlast, 0), lastL = __shfl_sync(0xFFFFFFFFu, hlast, 16);
+  const uint32_t b0 = 4u * (uint32_t)(warp >> 1) + (uint32_t)(warp & 1);
+  uint32_t totalL;
+  const uint32_t totalU = build_queue_half(&s_msk[(uint32_t)g0 & 15u], cnt, lastU > first ? lastU - first : 0u,
+                                           lastL > first ? lastL - first : 0u, 1u << b0, 1u << (b0 + 2u), lane,
+                                           &s_q[wloc][0][0], &s_q[wloc][1][0], totalL);
+  const uint32_t mine = half ? totalL : totalU;             // survivors of this lane's half
+  const uint32_t total = max(totalU, totalL);
+#else
   const uint32_t total = build_queue_idx(&s_msk[(uint32_t)g0 & 15u], cnt, wlast - first, hitmask_of_warp(warp), lane, q);
+#endif
 #ifdef GHR_COUNT
-  count_add(2, total);              // x 64 pixels, applied on the host
+  count_add(2, total);              // warp iterations: x 64 pixels, applied on the host
   uint32_t n_contributing = 0;
 #endif
   for (uint32_t b = 0; b < total; b += kIlpB) {
@@ -728,7 +814,11 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
     uint32_t idk[kIlpB];
 #pragma unroll
     for (int k = 0; k < kIlpB; k++) {
+#ifdef GHR_BWD_HALFQ
+      const uint32_t jj = b + k < mine ? (uint32_t)q[kQPad + b + k] : (uint32_t)kSeg;   // exhausted half: zero record
+#else
       const uint32_t jj = q[kQPad + b + k];                // tail pad: the all-zero record (alpha = 0)
+#endif
       const float4 a = s_rec[3 * jj], bq = s_rec[3 * jj + 1], col = s_rec[3 * jj + 2];
       float p0, p1, G0, G1, a0, a1;
       pair_alpha(a, bq, pxf, npy, dxk[k], dyk[k], p0, p1, G0, G1, a0, a1);
@@ -794,7 +884,11 @@ blend_backward_kernel(int H, int W, int gx, int T, int P, Cameras cam, const Ghr
         float *row = ring + pend * kSlotFloats + lane;
 #pragma unroll
         for (int t = 0; t < 9; t++) row[t * kRowStride] = vals[k][t];
+#ifdef GHR_BWD_HALFQ
+        if (hl == 0) ids[2u * pend + half] = idk[k];
+#else
         if (lane == 0) ids[pend] = idk[k];
+#endif
         if (++pend == kRingSlots) {
           __syncwarp();
           ring_flush(ring, ids, kRingSlots, accb, lane);

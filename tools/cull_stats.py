@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from guassianhand_b200 import _native as NV, build  # noqa: E402
-NV.LIB_PATH = build.variant_path("count")
+NV.LIB_PATH = build.variant_path(os.environ.get("GHR_COUNT_VARIANT", "count"))   # (A/B: another counting variant)
 from guassianhand_b200 import scenes  # noqa: E402
 from guassianhand_b200.dist import PackedGrads, fit_step_grads  # noqa: E402
 import util  # noqa: E402

@@ -381,9 +381,10 @@ def run_ours(args):
             for j, x in enumerate(r.results):
                 per_group[j].append(x.R)
         caps = [int(max(v) * 1.25) + (1 << 14) for v in per_group]
-    # per group: init, preprocess, tile scan, duplicate, chunk sort, merge+gather, blend | 2 bwd; + partial-sum
-    # adds; + the all-reduce kernel
-    launches_per_step = (1 + 1 + 1 + 1 + 2 + 1 + 2) * G + (G - 1) + (1 if world > 1 else 0)
+    # libghr kernels per group: preprocess, tile scan, duplicate, sort_big + sort_chunks, merge_gather, blend forward |
+    # blend backward, preprocess backward (9; the ncu launch list of this command shows the same count); + the
+    # partial-sum adds; + the all-reduce kernel
+    launches_per_step = (1 + 1 + 1 + 2 + 1 + 1 + 2) * G + (G - 1) + (1 if world > 1 else 0)
 
     def step(i, fe=None, be=None):
         return fit_step_grads(gauss, view_groups[i % n_groups], dL, grads, R_cap=R_cap, check="none",

@@ -617,10 +617,12 @@ __device__ __forceinline__ void ring_flush(const float *ring, const uint32_t *id
     const uint32_t t = round * 32 + lane, r = t >> 1;
     float sum = 0.f;
     if (t < ntask) {
-      const float4 *p = reinterpret_cast<const float4 *>(ring + r * kRowStride + (t & 1u) * 16u);
-      const float4 a = p[0], b = p[1], c = p[2], d = p[3];
-      sum = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
-            (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+      // the 16 partials as 8 packed pairs (the four LDS.128 deliver aligned register pairs): 7 FADD2 + 1 FADD
+      // instead of 15 FADD
+      const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(ring + r * kRowStride + (t & 1u) * 16u);
+      const ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
+      const f32x2 s2 = add2(add2(add2(a.x, a.y), add2(b.x, b.y)), add2(add2(c.x, c.y), add2(d.x, d.y)));
+      sum = lo2(s2) + hi2(s2);
     }
 #ifdef GHR_BWD_HALFQ
     // the two half-rows of a row belong to different instances (ids[2 * slot + half]): no join, one RED each

@@ -85,3 +85,39 @@ def test_view_group_helpers_cpu():
     assert c.V == 2 and torch.equal(c.view, cams.view[2:4]) and torch.equal(c.bg, cams.bg[2:4])
     shared = cams._replace(bg=torch.zeros(3), bg_stride=0)
     assert api._slice_cams(shared, 1, 3).bg.shape == (3,)
+
+
+def test_argument_checks_of_the_small_entry_points(native):
+    """Entry points that validate before they launch: bad arguments come back as GHR_EINVAL with a message, without a GPU."""
+    L = native.lib()
+    assert L.ghr_sh_blend_forward(-1, None, None, None, None, None) == native.GHR_EINVAL
+    assert L.ghr_sh_blend_forward(8, None, None, None, None, None) == native.GHR_EINVAL
+    assert L.ghr_sh_blend_forward(0, None, None, None, None, None) == native.GHR_OK            # empty: nothing to do
+    buf = (C.c_float * 8)()
+    p = C.cast(buf, C.c_void_p)
+    assert L.ghr_sh_blend_forward(8, p, None, p, p, None) == native.GHR_EINVAL                  # color_b without color_w
+    assert b"color_w" in L.ghr_last_error()
+    assert L.ghr_sh_blend_backward(8, p, None, None, p, None, p, None, None) == native.GHR_EINVAL   # d_w of an absent w
+    assert L.ghr_cameras_from_w2c(1, None, None, 16, 16, 0.1, 100.0, None, None, None, None, None) == native.GHR_EINVAL
+    assert L.ghr_cameras_from_w2c(0, None, None, 16, 16, 100.0, 0.1, None, None, None, None, None) == native.GHR_EINVAL
+    assert L.ghr_mark_visible(-1, None, None, None, None, None) == native.GHR_EINVAL
+    a = native.GhrAttributeArgs()
+    a.P = 4
+    assert L.ghr_attributes_forward(C.byref(a), None) == native.GHR_EINVAL
+    assert b"required" in L.ghr_last_error()
+
+
+def test_bench_only_standin_builds_and_exports():
+    """baseline_standin/ (the upstream-structured GPU denominator of bench.py's gpu_baseline leg) compiles for
+    sm_100a and exports its entry points; it is never imported by the product package."""
+    from baseline_standin import build as sb
+    so = sb.build()
+    L = C.CDLL(so)
+    for name in ("sgs_create", "sgs_destroy", "sgs_unpack", "sgs_forward", "sgs_backward", "sgs_num_rendered",
+                 "sgs_n_contrib", "sgs_final_T", "sgs_ranges", "sgs_sorted_keys", "sgs_copy"):
+        assert hasattr(L, name), name
+    pkg = os.path.join(ROOT, "guassianhand_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "baseline_standin" not in src and "import oracle" not in src and "from oracle" not in src, fn

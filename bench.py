@@ -113,6 +113,35 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(local_index):
+    """Multi-rank runs: keep this rank's host threads -- and with them the pinned staging buffers it is about to
+    allocate (first touch) -- on the NUMA node its GPU hangs off.  Seen at 8 x B200 without it: the uploads /
+    downloads of four of the eight ranks ran at 17 GB/s instead of 31 GB/s (remote host memory) and their replays
+    waited for them.  The rank keeps ALL cores of the node (never a single core: see the note at the top).  Returns
+    a short description for the bench line, or None when the topology cannot be read."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}"
+        node = int(open(path + "/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= set(range(os.cpu_count()))
+        if len(cpus) < 2:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"host threads and pinned buffers of rank-local GPU {local_index} on NUMA node {node} ({len(cpus)} cpus)"
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- CPU arm
 
 def cpu_views_per_s(n_views, threads=None, budget_s=None, P=None, H=None, W=None, hands=2, sh_degree=None):
@@ -308,7 +337,9 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback exists for the product path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = None
     if world > 1:
+        numa_note = bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     NV.lib()
@@ -542,9 +573,13 @@ def run_ours(args):
         return out
 
     bg_dev = t(bg)
-    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    # the download stream also runs the step's loss reduction (a small kernel): high priority, or it queues behind
+    # the next replay's kernels and the results leave late
+    up, down = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
     main = torch.cuda.current_stream()
-    NG = max(1, int(os.environ.get('GHR_BENCH_E2E_SLOTS', '2')))      # (diagnostics: number of alternating graph instances)
+    # graph instances (each with its own static inputs and result buffers) the e2e loop rotates through; 3 keeps the
+    # host two steps ahead, which absorbs the jitter of ranks whose uploads and downloads share one copy path
+    NG = max(1, int(os.environ.get('GHR_BENCH_E2E_SLOTS', '3')))
     gslots = []
     for sl in range(NG):
         flat, camflat = torch.empty_like(host_flat, device=dev), torch.empty_like(host_cams[0], device=dev)
@@ -631,17 +666,30 @@ def run_ours(args):
         del g_base[:]
         g_base.append(torch.cuda.Event(enable_timing=True))
         g_base[0].record(main)
-        g_upload(0)
+        # pipeline depth = NG - 1: inputs are uploaded that many steps ahead of their replay and results are read
+        # that many launches after it (NG = 2: upload of step i+1 during step i, results of step i-1 read after
+        # launching step i)
+        depth = NG - 1
         last = None
-        for i in range(n):
-            if i + 1 < n:
-                g_timed("upload", g_upload, i + 1)
-            g_timed("render", g_render, i)
-            if i >= 1:
-                last = g_timed("collect", g_collect, i - 1)
+        if depth == 0:                                  # single slot: nothing overlaps
+            for i in range(n):
+                g_timed("upload", g_upload, i)
+                g_timed("render", g_render, i)
+                last = g_timed("collect", g_collect, i)
                 g_marks.append(time.perf_counter())
-        last = g_collect(n - 1)
-        g_marks.append(time.perf_counter())
+        else:
+            for j in range(min(depth, n)):
+                g_upload(j)
+            for i in range(n):
+                if i + depth < n:
+                    g_timed("upload", g_upload, i + depth)
+                g_timed("render", g_render, i)
+                if i >= depth:
+                    last = g_timed("collect", g_collect, i - depth)
+                    g_marks.append(time.perf_counter())
+            for i in range(max(n - depth, 0), n):
+                last = g_collect(i)
+                g_marks.append(time.perf_counter())
         torch.cuda.synchronize()
         return last
 
@@ -708,7 +756,8 @@ def run_ours(args):
                            " [+ all-reduce] of the step's views); per step: H2D of the Gaussian attributes + cameras "
                            "from pinned host memory into the step's static inputs, D2H of the packed gradients + the "
                            "loss; two graph instances alternate so uploads overlap the previous step, results read "
-                           "one launch later, wall clock"},
+                           "one launch later, wall clock",
+                    "host_placement": numa_note},
             "gpu_launches": launches_per_step * K,
             "clocks": clk.summary(),
         }

@@ -552,156 +552,44 @@ def run_ours(args):
                                             fit_step_grads, GraphedFitStep))
     fp32_scalar, fp32_packed = fp32_probes(NV, torch, dev, stream)
 
-    # ---- e2e through the graphed step API (GraphedFitStep) with host buffers: the headline e2e ----
-    # Every step uploads ITS Gaussian attributes + cameras from pinned host memory into the step's static
-    # input buffers (two H2D copies), replays the captured forward+backward(+all-reduce), and downloads the
-    # packed gradients + the loss (two D2H copies).  Two graph instances with their own static buffers
-    # alternate, so step i+1 uploads while step i runs; the host reads step i's results after it has
-    # launched step i+1.
-    names = list(gauss.keys())
-    sizes = {k: gauss[k].numel() for k in names}
-    host_flat = torch.cat([gauss[k].detach().reshape(-1).cpu() for k in names]).pin_memory()
-    cam_names = ["viewmatrix", "projmatrix", "campos", "tanfov"]
-    cam_sizes = {k: getattr(view_groups[0], k).numel() for k in cam_names}
-    host_cams = [torch.cat([getattr(vg, k).reshape(-1).cpu() for k in cam_names]).pin_memory() for vg in view_groups]
-
-    def carve(flat, names_, sizes_, like):
-        out, o = {}, 0
-        for k in names_:
-            out[k] = flat[o:o + sizes_[k]].view(like(k).shape)
-            o += sizes_[k]
-        return out
-
+    # ---- e2e through the public pipelined API (dist.PipelinedFitLoop) with host buffers: the headline e2e ----
+    # Every step uploads ITS Gaussian attributes + cameras from pinned host memory into a slot's static input
+    # buffers (two H2D copies), replays the captured forward+backward(+all-reduce) and downloads the packed
+    # gradients + the loss (two D2H copies).  Three graph instances with their own buffers rotate: inputs go up
+    # two steps ahead, the host reads a step's results two launches after it (PipelinedFitLoop.run).
+    from guassianhand_b200.dist import PipelinedFitLoop
+    NG = max(1, int(os.environ.get('GHR_BENCH_E2E_SLOTS', '3')))      # (diagnostics: other pipeline depths)
     bg_dev = t(bg)
-    # the download stream also runs the step's loss reduction (a small kernel): high priority, or it queues behind
-    # the next replay's kernels and the results leave late
-    up, down = torch.cuda.Stream(), torch.cuda.Stream(priority=-1)
-    main = torch.cuda.current_stream()
-    # graph instances (each with its own static inputs and result buffers) the e2e loop rotates through; 3 keeps the
-    # host two steps ahead, which absorbs the jitter of ranks whose uploads and downloads share one copy path
-    NG = max(1, int(os.environ.get('GHR_BENCH_E2E_SLOTS', '3')))
-    gslots = []
-    for sl in range(NG):
-        flat, camflat = torch.empty_like(host_flat, device=dev), torch.empty_like(host_cams[0], device=dev)
-        flat.copy_(host_flat)
-        camflat.copy_(host_cams[0])
-        gin = carve(flat, names, sizes, lambda k: gauss[k])
-        cin = carve(camflat, cam_names, cam_sizes, lambda k: getattr(view_groups[0], k))
-        sviews = api.ViewBatch(image_height=H, image_width=W, viewmatrix=cin["viewmatrix"],
-                               projmatrix=cin["projmatrix"], campos=cin["campos"], tanfov=cin["tanfov"], bg=bg_dev)
-        ggr = PackedGrads(P, 0, device=dev, peer=peer)
-        gs = GraphedFitStep(gin, sviews, dL, ggr, R_cap=caps, overlap=G)
-        gslots.append(dict(flat=flat, camflat=camflat, step=gs, grads=ggr,
-                           host_grads=torch.empty(ggr.flat.numel()).pin_memory(), host_loss=torch.zeros(1).pin_memory(),
-                           host_status=torch.zeros(G, 4, dtype=torch.int64).pin_memory(),
-                           ev_up=torch.cuda.Event(), ev_used=torch.cuda.Event(), ev_down=torch.cuda.Event()))
-    g_h2d = host_flat.numel() * 4 + host_cams[0].numel() * 4
-    g_d2h = gslots[0]["host_grads"].numel() * 4 + 4
-    dL_flat = dL.reshape(-1)
-
-    def g_upload(i):
-        sl = gslots[i % NG]
-        with torch.cuda.stream(up):
-            up.wait_event(sl["ev_used"])
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record(up)
-            sl["flat"].copy_(host_flat, non_blocking=True)
-            sl["camflat"].copy_(host_cams[i % n_groups], non_blocking=True)
-            c1.record(up)
-            g_copy["h2d"].append((c0, c1))
-            sl["ev_up"].record(up)
-
-    def g_render(i):
-        sl = gslots[i % NG]
-        main.wait_event(sl["ev_up"])
-        main.wait_event(sl["ev_down"])              # the slot's previous results have left the device
-        ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ge0.record(main)
-        res = sl["step"].replay()
-        ge1.record(main)
-        g_gpu.append((ge0, ge1))
-        sl["ev_used"].record(main)                  # the slot's inputs have been consumed
-        # everything that follows the replay -- the loss, the status reads and the downloads -- runs on the
-        # download stream, so the main stream goes straight on to the next step's replay (the other slot)
-        down.wait_stream(main)
-        with torch.cuda.stream(down):
-            loss = torch.vdot(res.color.reshape(-1), dL_flat)
-            for j, st in enumerate(sl["step"].states()):
-                NV.check(NV.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
-                                                        down.cuda_stream), "status")
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record(down)
-            sl["host_grads"].copy_(sl["grads"].flat, non_blocking=True)
-            sl["host_loss"].copy_(loss.reshape(1), non_blocking=True)
-            c1.record(down)
-            g_copy["d2h"].append((c0, c1))
-            sl["ev_down"].record(down)
-
-    def g_collect(i):
-        sl = gslots[i % NG]
-        sl["ev_down"].synchronize()
-        if int((sl["host_status"][:, 1] & 0xFFFFFFFF).sum()) != 0:
-            raise RuntimeError("bench: instance capacity overflow in the e2e graph leg")
-        return float(sl["host_loss"][0])
-
-    g_base = []
-    g_marks, g_host, g_gpu, g_copy = [], {"upload": [], "render": [], "collect": []}, [], {"h2d": [], "d2h": []}
-
-    def g_timed(name, fn, i):
-        t_ = time.perf_counter()
-        r_ = fn(i)
-        g_host[name].append((time.perf_counter() - t_) * 1e3)
-        return r_
+    v0 = view_groups[0]
+    loop_views = api.ViewBatch(image_height=H, image_width=W, viewmatrix=v0.viewmatrix, projmatrix=v0.projmatrix,
+                               campos=v0.campos, tanfov=v0.tanfov, bg=bg_dev)
+    loop = PipelinedFitLoop(gauss, loop_views, dL, caps, overlap=G, slots=NG, peer=peer, trace=True)
+    host_flat = loop.pack_attributes(gauss)
+    host_cams = [loop.pack_cameras(vg) for vg in view_groups]
+    g_h2d, g_d2h = loop.h2d_bytes_per_step, loop.d2h_bytes_per_step
 
     def g_run(n):
-        del g_marks[:]
-        del g_gpu[:]
-        for v_ in g_copy.values():
-            del v_[:]
-        for v_ in g_host.values():
-            del v_[:]
-        for sl in gslots:
-            sl["ev_used"].record(main)
-            sl["ev_down"].record(main)
-        del g_base[:]
-        g_base.append(torch.cuda.Event(enable_timing=True))
-        g_base[0].record(main)
-        # pipeline depth = NG - 1: inputs are uploaded that many steps ahead of their replay and results are read
-        # that many launches after it (NG = 2: upload of step i+1 during step i, results of step i-1 read after
-        # launching step i)
-        depth = NG - 1
-        last = None
-        if depth == 0:                                  # single slot: nothing overlaps
-            for i in range(n):
-                g_timed("upload", g_upload, i)
-                g_timed("render", g_render, i)
-                last = g_timed("collect", g_collect, i)
-                g_marks.append(time.perf_counter())
-        else:
-            for j in range(min(depth, n)):
-                g_upload(j)
-            for i in range(n):
-                if i + depth < n:
-                    g_timed("upload", g_upload, i + depth)
-                g_timed("render", g_render, i)
-                if i >= depth:
-                    last = g_timed("collect", g_collect, i - depth)
-                    g_marks.append(time.perf_counter())
-            for i in range(max(n - depth, 0), n):
-                last = g_collect(i)
-                g_marks.append(time.perf_counter())
+        loop.reset()
+        base = torch.cuda.Event(enable_timing=True)
+        base.record(torch.cuda.current_stream())
+        marks, last = [], None
+        for res in loop.run((host_flat, host_cams[i % n_groups]) for i in range(n)):
+            last = res.loss
+            marks.append(time.perf_counter())
         torch.cuda.synchronize()
-        return last
+        return last, marks, base
 
     g_run(8 if world > 1 else 4)
     sync_all()
     t0 = time.perf_counter()
-    g_loss = g_run(K)
+    g_loss, g_marks, g_base = g_run(K)
     g_s = time.perf_counter() - t0
     g_steps = np.diff(np.array([t0] + g_marks)) * 1e3          # wall ms between consecutive results on this rank
+    g_gpu, g_copy, g_host = loop.events["replay"], loop.events, loop.host_ms
+    g_host = {"upload": g_host["upload"], "render": g_host["launch"], "collect": g_host["result"]}
     g_gpu_ms = [a_.elapsed_time(b_) for a_, b_ in g_gpu]       # device ms of every replay on this rank
     def rel(ev):
-        return round(g_base[0].elapsed_time(ev), 3)
+        return round(g_base.elapsed_time(ev), 3)
     g_mine = {"timeline_ms": [{"h2d": [rel(g_copy["h2d"][i][0]), rel(g_copy["h2d"][i][1])] if i < len(g_copy["h2d"]) else None,
                                "replay": [rel(g_gpu[i][0]), rel(g_gpu[i][1])],
                                "d2h": [rel(g_copy["d2h"][i][0]), rel(g_copy["d2h"][i][1])]} for i in range(len(g_gpu))],
@@ -752,11 +640,11 @@ def run_ours(args):
                                      "host_call_ms_median": {k_: float(np.median(v_)) if v_ else None for k_, v_ in g_host.items()},
                                      "steps": [round(float(x), 3) for x in g_steps],
                                      "replay_device_ms_per_rank": g_all},
-                    "api": "guassianhand_b200.dist.GraphedFitStep.replay() (captured ghr_forward + ghr_backward"
-                           " [+ all-reduce] of the step's views); per step: H2D of the Gaussian attributes + cameras "
-                           "from pinned host memory into the step's static inputs, D2H of the packed gradients + the "
-                           "loss; two graph instances alternate so uploads overlap the previous step, results read "
-                           "one launch later, wall clock",
+                    "api": "guassianhand_b200.dist.PipelinedFitLoop.run() over GraphedFitStep instances (captured "
+                           "ghr_forward + ghr_backward [+ all-reduce] of the step's views); per step: H2D of the "
+                           "Gaussian attributes + cameras from pinned host memory into a slot's static inputs, D2H of "
+                           "the packed gradients + the loss; three graph instances rotate so uploads run two steps "
+                           "ahead and results are read two launches later, wall clock",
                     "host_placement": numa_note},
             "gpu_launches": launches_per_step * K,
             "clocks": clk.summary(),

@@ -338,3 +338,210 @@ class GraphedFitStep:
             R += int(self._pin[0])
             ov |= int(self._pin[1]) & 0xFFFFFFFF
         return R, ov
+
+
+class FitResult(NamedTuple):
+    """One step of PipelinedFitLoop.  `grads` is the slot's pinned host buffer (PackedGrads layout): valid until
+    the slot is reused, `slots` steps later -- copy what must live longer."""
+    grads: torch.Tensor
+    loss: float
+    R: int
+    overflow: int
+
+
+class PipelinedFitLoop:
+    """Host buffers in, host buffers out, at (almost) the device-resident rate of GraphedFitStep.
+
+    `slots` GraphedFitStep instances with their own static inputs and result buffers rotate.  Per step: the step's
+    Gaussian attributes and cameras are copied from PINNED host memory into the slot's static inputs on an upload
+    stream, `slots - 1` steps ahead of their replay; the replay (forward + backward [+ all-reduce], one graph
+    launch) follows the previous one back to back on the launch stream; the loss <color, dL_dout>, the status
+    reads and the download of the packed gradients run on a high-priority download stream; the host reads a
+    step's results `slots - 1` launches after it (an overflow of the instance capacity raises there).
+
+        loop = PipelinedFitLoop(gauss, views, dL_dout, R_cap, overlap=2)
+        for res in loop.run((loop.pack_attributes(g), loop.pack_cameras(v)) for g, v in steps):
+            optimizer_consumes(res.grads, res.loss)
+
+    gauss / views: device tensors that fix names, shapes and dtypes of a step's inputs (and their initial values).
+    Two slots are enough when a GPU's uploads and downloads overlap each other; the third absorbs the jitter where
+    they share one copy path (bench.py's e2e leg at 8 x B200: 128k -> 141k views/s)."""
+
+    CAM_FIELDS = ("viewmatrix", "projmatrix", "campos", "tanfov")
+
+    def __init__(self, gauss: Dict[str, torch.Tensor], views, dL_dout: torch.Tensor, R_cap, overlap: int = 2,
+                 slots: int = 3, peer: bool = False, group=None, sh_degree: int = 0, scale_modifier: float = 1.0,
+                 trace: bool = False):
+        from . import api
+        dev = dL_dout.device
+        self.names = list(gauss.keys())
+        self.shapes = {k: tuple(gauss[k].shape) for k in self.names}
+        self.sizes = {k: int(gauss[k].numel()) for k in self.names}
+        self.cam_shapes = {k: tuple(getattr(views, k).shape) for k in self.CAM_FIELDS}
+        self.cam_sizes = {k: int(getattr(views, k).numel()) for k in self.CAM_FIELDS}
+        n_attr, n_cam = sum(self.sizes.values()), sum(self.cam_sizes.values())
+        P = int(gauss["means3D"].shape[0])
+        M = int(gauss["shs"].shape[1]) if gauss.get("shs") is not None else 0
+        self.slots, self.trace = max(1, int(slots)), trace
+        self.main = torch.cuda.current_stream(dev)
+        self.up, self.down = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        self.dL_flat = dL_dout.reshape(-1)
+        self._slots = []
+        for _ in range(self.slots):
+            flat = torch.empty(n_attr, dtype=torch.float32, device=dev)
+            camflat = torch.empty(n_cam, dtype=torch.float32, device=dev)
+            flat.copy_(torch.cat([gauss[k].detach().reshape(-1).float() for k in self.names]))
+            camflat.copy_(torch.cat([getattr(views, k).reshape(-1).float() for k in self.CAM_FIELDS]))
+            gin = self._carve(flat, self.names, self.sizes, self.shapes)
+            cin = self._carve(camflat, self.CAM_FIELDS, self.cam_sizes, self.cam_shapes)
+            sviews = api.ViewBatch(image_height=views.image_height, image_width=views.image_width,
+                                   viewmatrix=cin["viewmatrix"], projmatrix=cin["projmatrix"], campos=cin["campos"],
+                                   tanfov=cin["tanfov"], bg=views.bg, sh_degree=views.sh_degree,
+                                   scale_modifier=views.scale_modifier)
+            grads = PackedGrads(P, M, device=dev, peer=peer, group=group)
+            step = GraphedFitStep(gin, sviews, dL_dout, grads, R_cap=R_cap, group=group, sh_degree=sh_degree,
+                                  scale_modifier=scale_modifier, overlap=overlap)
+            n_states = len(step.states())
+            self._slots.append(dict(
+                flat=flat, camflat=camflat, step=step, grads=grads,
+                host_grads=torch.empty(grads.flat.numel()).pin_memory(), host_loss=torch.zeros(1).pin_memory(),
+                host_status=torch.zeros(n_states, 4, dtype=torch.int64).pin_memory(),
+                ev_up=torch.cuda.Event(), ev_used=torch.cuda.Event(), ev_down=torch.cuda.Event()))
+        self.h2d_bytes_per_step = (n_attr + n_cam) * 4
+        self.d2h_bytes_per_step = self._slots[0]["host_grads"].numel() * 4 + 4
+        self.events = {"h2d": [], "replay": [], "d2h": []}      # trace=True: (start, stop) CUDA events per step
+        self.host_ms = {"upload": [], "launch": [], "result": []}
+        self.reset()
+
+    @staticmethod
+    def _carve(flat, names, sizes, shapes):
+        out, o = {}, 0
+        for k in names:
+            out[k] = flat[o:o + sizes[k]].view(shapes[k])
+            o += sizes[k]
+        return out
+
+    def pack_attributes(self, gauss: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One pinned host buffer with a step's Gaussian attributes in this loop's order."""
+        return torch.cat([gauss[k].detach().reshape(-1).float().cpu() for k in self.names]).pin_memory()
+
+    def pack_cameras(self, views) -> torch.Tensor:
+        """One pinned host buffer with a step's cameras (viewmatrix | projmatrix | campos | tanfov)."""
+        return torch.cat([getattr(views, k).detach().reshape(-1).float().cpu() for k in self.CAM_FIELDS]).pin_memory()
+
+    def reset(self):
+        """Forget the slots' history (and the trace)."""
+        for sl in self._slots:
+            sl["ev_used"].record(self.main)
+            sl["ev_down"].record(self.main)
+        for v in list(self.events.values()) + list(self.host_ms.values()):
+            del v[:]
+
+    def _timed(self, what, fn, *a):
+        if not self.trace:
+            return fn(*a)
+        import time
+        t0 = time.perf_counter()
+        r = fn(*a)
+        self.host_ms[what].append((time.perf_counter() - t0) * 1e3)
+        return r
+
+    def _pair(self, stream):
+        if not self.trace:
+            return None, None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        return a, b
+
+    def upload(self, i: int, host_attrs: torch.Tensor, host_cams: torch.Tensor):
+        """Stage step i's inputs into its slot (waits on the device for the slot's previous replay)."""
+        sl = self._slots[i % self.slots]
+        with torch.cuda.stream(self.up):
+            self.up.wait_event(sl["ev_used"])
+            a, b = self._pair(self.up)
+            sl["flat"].copy_(host_attrs, non_blocking=True)
+            sl["camflat"].copy_(host_cams, non_blocking=True)
+            if a is not None:
+                b.record(self.up)
+                self.events["h2d"].append((a, b))
+            sl["ev_up"].record(self.up)
+
+    def launch(self, i: int):
+        """Replay step i and enqueue its loss, status reads and downloads."""
+        from . import _native as N
+        sl = self._slots[i % self.slots]
+        main, down = self.main, self.down
+        main.wait_event(sl["ev_up"])
+        main.wait_event(sl["ev_down"])              # the slot's previous results have left the device
+        a, b = self._pair(main)
+        res = sl["step"].replay()
+        if a is not None:
+            b.record(main)
+            self.events["replay"].append((a, b))
+        sl["ev_used"].record(main)                  # the slot's inputs have been consumed
+        down.wait_stream(main)
+        with torch.cuda.stream(down):
+            loss = torch.vdot(res.color.reshape(-1), self.dL_flat)
+            for j, st in enumerate(sl["step"].states()):
+                N.check(N.lib().ghr_read_status_async(st.data_ptr(), sl["host_status"][j].data_ptr(),
+                                                      down.cuda_stream), "ghr_read_status_async")
+            a, b = self._pair(down)
+            sl["host_grads"].copy_(sl["grads"].flat, non_blocking=True)
+            sl["host_loss"].copy_(loss.reshape(1), non_blocking=True)
+            if a is not None:
+                b.record(down)
+                self.events["d2h"].append((a, b))
+            sl["ev_down"].record(down)
+
+    def result(self, i: int) -> FitResult:
+        """Block until step i's results are in host memory."""
+        sl = self._slots[i % self.slots]
+        sl["ev_down"].synchronize()
+        st = sl["host_status"]
+        overflow = int((st[:, 1] & 0xFFFFFFFF).sum())
+        if overflow:
+            raise RuntimeError("PipelinedFitLoop: a step exceeded its instance capacity R_cap (its results are invalid)")
+        return FitResult(sl["host_grads"], float(sl["host_loss"][0]), int(st[:, 0].sum()), overflow)
+
+    def run(self, inputs):
+        """inputs: iterable of (pinned attributes, pinned cameras) per step (pack_attributes / pack_cameras).
+        Yields one FitResult per step, in order, `slots - 1` launches behind the newest one."""
+        depth = self.slots - 1
+        it = iter(inputs)
+        n_up = n_launch = n_out = 0
+        pending = []                                   # uploaded, not yet launched (kept alive: async copies)
+        done = False
+
+        def pull():
+            nonlocal n_up, done
+            if done:
+                return False
+            try:
+                a, c = next(it)
+            except StopIteration:
+                done = True
+                return False
+            self._timed("upload", self.upload, n_up, a, c)
+            pending.append((a, c))
+            n_up += 1
+            return True
+
+        for _ in range(max(depth, 1)):
+            pull()
+        while n_launch < n_up:
+            if depth:
+                pull()                                 # step n_launch + depth goes up before step n_launch launches
+            self._timed("launch", self.launch, n_launch)
+            n_launch += 1
+            if len(pending) > self.slots:
+                pending.pop(0)
+            if not depth:
+                yield self._timed("result", self.result, n_out)
+                n_out += 1
+                pull()
+            elif n_launch - n_out > depth:
+                yield self._timed("result", self.result, n_out)
+                n_out += 1
+        while n_out < n_launch:
+            yield self._timed("result", self.result, n_out)
+            n_out += 1

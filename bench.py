@@ -12,8 +12,11 @@ of that buffer -- libghr's own NVLink peer-memory kernel (--allreduce peer, defa
 scaling: B views per rank per step.
   value   : views/s over all ranks, inputs resident in HBM, CUDA events per step, max over ranks, L2
             flushed between steps.  `step_ms` carries the per-step distribution of every rank.
-  e2e     : same metric through the graphed step API with host buffers: H2D of Gaussian attributes +
-            cameras and D2H of gradients + loss inside the timed region (wall clock, max over ranks).
+  e2e     : same metric through the public pipelined API (guassianhand_b200.dist.PipelinedFitLoop.run over
+            GraphedFitStep instances) with host buffers: H2D of Gaussian attributes + cameras and D2H of
+            gradients + loss inside the timed region (wall clock, max over ranks).
+  gpu_baseline (N = 1): an upstream-STRUCTURED GPU stand-in of the binning + blend stages (baseline_standin/,
+            kind "restatement": not the reference's package) on the same views.
   roofline: SURVEY.md §8(d): the dominant kernel against ITS roof (FP32 for the blend kernels, HBM for
             the streaming ones), a per-stage table, and the max-sum model of the whole step
             t_roof = bytes / hbm_peak + 94 I / fp32_peak against the measured step.

@@ -121,3 +121,34 @@ def test_bench_only_standin_builds_and_exports():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "baseline_standin" not in src and "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_geometry_cache_identity_and_version_rules_cpu():
+    """api._GeomCache (the caller-invisible sharing between the reference's RGB and mask calls,
+    renderer_one_shot.py:338-346 / :372-379): a hit needs the SAME tensors at the SAME autograd versions and the
+    same scalars, and a state blob that is still alive.  Pure host logic: checked with CPU tensors."""
+    import gc
+    import torch
+    from guassianhand_b200 import api
+    C_ = api._GeomCache
+    C_.entries.clear()
+    mk = lambda *s: torch.zeros(*s)
+    tensors = (mk(5, 3), mk(5, 1), mk(5, 3), mk(5, 4), None, mk(4, 4), mk(4, 4), mk(3))
+    scalars = (5, 32, 32, 0.5, 0.5, 1.0, 0)
+    state = torch.zeros(16, dtype=torch.uint8)
+    assert C_.lookup(0, tensors, scalars) is None
+    C_.store(0, tensors, scalars, state, 0, 1000, 123)
+    hit = C_.lookup(0, tensors, scalars)
+    assert hit is not None and hit[0] is state and hit[1:] == (0, 1000, 123)
+    assert C_.lookup(1, tensors, scalars) is None                       # another device
+    assert C_.lookup(0, tensors, scalars[:3] + (0.6,) + scalars[4:]) is None   # another tanfovx
+    clone = tuple(None if t is None else t.clone() for t in tensors)
+    assert C_.lookup(0, clone, scalars) is None                         # equal values, different tensors
+    tensors[0].add_(1.0)                                                # in-place update: autograd version moves
+    assert C_.lookup(0, tensors, scalars) is None
+    C_.store(0, tensors, scalars, state, 0, 1000, 123)
+    assert C_.lookup(0, tensors, scalars) is not None
+    del state, hit
+    gc.collect()
+    assert C_.lookup(0, tensors, scalars) is None                       # the first call's state is gone
+    C_.entries.clear()
